@@ -1,0 +1,209 @@
+// capi.cu -- the extern "C" surface of libhcspmm.so (declared in include/hcspmm.h).
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace hcspmm {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+Tuning &tuning() {
+  static Tuning t = {1024, 0};
+  return t;
+}
+
+size_t preprocess_workspace_bytes(int32_t n_rows, int64_t nnz);
+int launch_preprocess(const int32_t *, const int32_t *, int32_t, int64_t, int32_t, int, int32_t *,
+                      int32_t *, int32_t *, int32_t *, void *, size_t, cudaStream_t);
+int launch_spmm(const float *, int64_t, int32_t, const int32_t *, const int32_t *, const int32_t *,
+                const int32_t *, const int32_t *, const int32_t *, int32_t, int64_t, int32_t, int,
+                int, float *, int64_t, cudaStream_t);
+int launch_gemm_tf32(const float *, int64_t, const float *, int64_t, int32_t, int32_t, int32_t,
+                     float *, int64_t, cudaStream_t);
+
+}  // namespace hcspmm
+
+using namespace hcspmm;
+
+struct hcspmm_graph {
+  int32_t n_rows, x_rows, n_windows;
+  int64_t nnz;
+  int32_t *rowptr, *colidx, *bp, *etc, *etr, *ht;
+  float *x, *y;
+  int32_t buf_dim;
+  cudaStream_t stream;
+};
+
+#define CUDA_TRY(expr)                                                        \
+  do {                                                                        \
+    cudaError_t e_ = (expr);                                                  \
+    if (e_ != cudaSuccess) {                                                  \
+      set_error("%s: %s", #expr, cudaGetErrorString(e_));                     \
+      return (int)e_;                                                         \
+    }                                                                         \
+  } while (0)
+
+extern "C" {
+
+int hcspmm_version(void) { return 100; }
+
+const char *hcspmm_last_error(void) { return g_err; }
+
+int hcspmm_set_tuning(const char *key, int value) {
+  int *slot = nullptr;
+  if (key && !strcmp(key, "long_row")) slot = &tuning().long_row;
+  else if (key && !strcmp(key, "slab")) slot = &tuning().slab;
+  if (!slot) return -1;
+  int old = *slot;
+  *slot = value;
+  return old;
+}
+
+size_t hcspmm_preprocess_workspace_bytes(int32_t n_rows, int64_t nnz) {
+  return preprocess_workspace_bytes(n_rows, nnz);
+}
+
+int hcspmm_preprocess(const int32_t *d_colidx, const int32_t *d_rowptr, int32_t n_rows, int64_t nnz,
+                      int32_t n_windows, int classifier, int32_t *d_block_partition,
+                      int32_t *d_edge_to_column, int32_t *d_edge_to_row, int32_t *d_hybrid_type,
+                      void *d_workspace, size_t workspace_bytes, void *stream) {
+  return launch_preprocess(d_colidx, d_rowptr, n_rows, nnz, n_windows, classifier,
+                           d_block_partition, d_edge_to_column, d_edge_to_row, d_hybrid_type,
+                           d_workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int hcspmm_spmm(const float *d_x, int64_t ldx, int32_t x_rows, const int32_t *d_rowptr,
+                const int32_t *d_colidx, const int32_t *d_block_partition,
+                const int32_t *d_edge_to_column, const int32_t *d_edge_to_row,
+                const int32_t *d_hybrid_type, int32_t n_rows, int64_t nnz, int32_t dim,
+                int precision, int accumulate, float *d_y, int64_t ldy, void *stream) {
+  return launch_spmm(d_x, ldx, x_rows, d_rowptr, d_colidx, d_block_partition, d_edge_to_column,
+                     d_edge_to_row, d_hybrid_type, n_rows, nnz, dim, precision, accumulate, d_y,
+                     ldy, (cudaStream_t)stream);
+}
+
+int hcspmm_gemm_tf32(const float *d_a, int64_t lda, const float *d_b, int64_t ldb, int32_t m,
+                     int32_t k, int32_t n, float *d_out, int64_t ldo, void *stream) {
+  return launch_gemm_tf32(d_a, lda, d_b, ldb, m, k, n, d_out, ldo, (cudaStream_t)stream);
+}
+
+int hcspmm_spmm_gemm(const float *d_x, int64_t ldx, int32_t x_rows, const int32_t *d_rowptr,
+                     const int32_t *d_colidx, const int32_t *d_block_partition,
+                     const int32_t *d_edge_to_column, const int32_t *d_edge_to_row,
+                     const int32_t *d_hybrid_type, int32_t n_rows, int64_t nnz, int32_t dim,
+                     int precision, const float *d_w, int64_t ldw, int32_t hidden, float *d_out,
+                     int64_t ldo, float *d_z, int64_t ldz, void *stream) {
+  if (!d_z || !d_out || !d_w) {
+    set_error("spmm_gemm: null pointer argument");
+    return HCSPMM_E_INVALID;
+  }
+  int rc = launch_spmm(d_x, ldx, x_rows, d_rowptr, d_colidx, d_block_partition, d_edge_to_column,
+                       d_edge_to_row, d_hybrid_type, n_rows, nnz, dim, precision, 0, d_z, ldz,
+                       (cudaStream_t)stream);
+  if (rc) return rc;
+  return launch_gemm_tf32(d_z, ldz, d_w, ldw, n_rows, dim, hidden, d_out, ldo,
+                          (cudaStream_t)stream);
+}
+
+void hcspmm_graph_destroy(hcspmm_graph_t *g) {
+  if (!g) return;
+  cudaFree(g->rowptr); cudaFree(g->colidx); cudaFree(g->bp); cudaFree(g->etc);
+  cudaFree(g->etr); cudaFree(g->ht); cudaFree(g->x); cudaFree(g->y);
+  if (g->stream) cudaStreamDestroy(g->stream);
+  delete g;
+}
+
+int hcspmm_graph_create(const int32_t *h_rowptr, const int32_t *h_colidx, int32_t n_rows,
+                        int64_t nnz, int32_t x_rows, int classifier, hcspmm_graph_t **out) {
+  if (!out || !h_rowptr || n_rows < 0 || nnz < 0 || (nnz > 0 && !h_colidx)) {
+    set_error("graph_create: bad argument");
+    return HCSPMM_E_INVALID;
+  }
+  hcspmm_graph *g = new hcspmm_graph();
+  memset(g, 0, sizeof(*g));
+  g->n_rows = n_rows; g->x_rows = x_rows; g->nnz = nnz;
+  g->n_windows = (n_rows + HCSPMM_BLK_H - 1) / HCSPMM_BLK_H;
+  void *ws = nullptr;
+  size_t ws_bytes = preprocess_workspace_bytes(n_rows, nnz);
+  size_t e = (size_t)(nnz > 0 ? nnz : 1), w = (size_t)(g->n_windows > 0 ? g->n_windows : 1);
+  int rc = 0;
+#define G_TRY(expr)                                                           \
+  do {                                                                        \
+    cudaError_t e_ = (expr);                                                  \
+    if (e_ != cudaSuccess) {                                                  \
+      set_error("%s: %s", #expr, cudaGetErrorString(e_));                     \
+      rc = (int)e_;                                                           \
+      goto fail;                                                              \
+    }                                                                         \
+  } while (0)
+  G_TRY(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+  G_TRY(cudaMalloc(&g->rowptr, sizeof(int32_t) * ((size_t)n_rows + 1)));
+  G_TRY(cudaMalloc(&g->colidx, sizeof(int32_t) * e));
+  G_TRY(cudaMalloc(&g->bp, sizeof(int32_t) * w));
+  G_TRY(cudaMalloc(&g->etc, sizeof(int32_t) * e));
+  G_TRY(cudaMalloc(&g->etr, sizeof(int32_t) * e));
+  G_TRY(cudaMalloc(&g->ht, sizeof(int32_t) * w));
+  G_TRY(cudaMalloc(&ws, ws_bytes));
+  G_TRY(cudaMemcpyAsync(g->rowptr, h_rowptr, sizeof(int32_t) * ((size_t)n_rows + 1),
+                        cudaMemcpyHostToDevice, g->stream));
+  if (nnz > 0)
+    G_TRY(cudaMemcpyAsync(g->colidx, h_colidx, sizeof(int32_t) * (size_t)nnz,
+                          cudaMemcpyHostToDevice, g->stream));
+  rc = launch_preprocess(g->colidx, g->rowptr, n_rows, nnz, g->n_windows, classifier, g->bp,
+                         g->etc, g->etr, g->ht, ws, ws_bytes, g->stream);
+  if (rc) goto fail;
+  G_TRY(cudaStreamSynchronize(g->stream));
+  cudaFree(ws);
+  *out = g;
+  return 0;
+fail:
+  cudaFree(ws);
+  hcspmm_graph_destroy(g);
+  return rc;
+#undef G_TRY
+}
+
+int hcspmm_graph_spmm_host(hcspmm_graph_t *g, const float *h_x, int32_t dim, int precision,
+                           float *h_y) {
+  if (!g || !h_x || !h_y || dim <= 0) {
+    set_error("graph_spmm_host: bad argument");
+    return HCSPMM_E_INVALID;
+  }
+  if (dim != g->buf_dim) {
+    cudaFree(g->x); cudaFree(g->y);
+    g->x = g->y = nullptr; g->buf_dim = 0;
+    CUDA_TRY(cudaMalloc(&g->x, sizeof(float) * (size_t)g->x_rows * dim));
+    CUDA_TRY(cudaMalloc(&g->y, sizeof(float) * (size_t)(g->n_rows > 0 ? g->n_rows : 1) * dim));
+    g->buf_dim = dim;
+  }
+  CUDA_TRY(cudaMemcpyAsync(g->x, h_x, sizeof(float) * (size_t)g->x_rows * dim,
+                           cudaMemcpyHostToDevice, g->stream));
+  int rc = launch_spmm(g->x, dim, g->x_rows, g->rowptr, g->colidx, g->bp, g->etc, g->etr, g->ht,
+                       g->n_rows, g->nnz, dim, precision, 0, g->y, dim, g->stream);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(h_y, g->y, sizeof(float) * (size_t)g->n_rows * dim,
+                           cudaMemcpyDeviceToHost, g->stream));
+  CUDA_TRY(cudaStreamSynchronize(g->stream));
+  return 0;
+}
+
+int hcspmm_graph_get_preprocess(hcspmm_graph_t *g, int32_t *h_bp, int32_t *h_etc, int32_t *h_etr,
+                                int32_t *h_ht) {
+  if (!g) { set_error("graph_get_preprocess: null graph"); return HCSPMM_E_INVALID; }
+  if (h_bp) CUDA_TRY(cudaMemcpy(h_bp, g->bp, sizeof(int32_t) * (size_t)g->n_windows, cudaMemcpyDeviceToHost));
+  if (h_ht) CUDA_TRY(cudaMemcpy(h_ht, g->ht, sizeof(int32_t) * (size_t)g->n_windows, cudaMemcpyDeviceToHost));
+  if (h_etc) CUDA_TRY(cudaMemcpy(h_etc, g->etc, sizeof(int32_t) * (size_t)g->nnz, cudaMemcpyDeviceToHost));
+  if (h_etr) CUDA_TRY(cudaMemcpy(h_etr, g->etr, sizeof(int32_t) * (size_t)g->nnz, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,64 @@
+// common.cuh -- shared device helpers for the sm_100a kernels of libhcspmm.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/hcspmm.h"
+
+namespace hcspmm {
+
+constexpr int BLK_H = HCSPMM_BLK_H;  // rows per window   (reference config.h:4)
+constexpr int BLK_W = HCSPMM_BLK_W;  // condensed block width (reference config.h:5)
+constexpr int CTA_THREADS = 256;
+constexpr int CTA_WARPS = CTA_THREADS / 32;
+
+// thread-local error text, set by the launchers in capi.cu
+void set_error(const char *fmt, ...);
+
+struct Tuning {
+  int long_row;  // rows with >= long_row non-zeros are split over all warps of the CTA
+  int slab;      // feature-slab width in floats, 0 = no slabbing
+};
+Tuning &tuning();
+
+// ---- small PTX wrappers -------------------------------------------------------------
+__device__ __forceinline__ float4 ldg_f4(const float *p) {
+  return __ldg(reinterpret_cast<const float4 *>(p));
+}
+
+__device__ __forceinline__ uint32_t f32_to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+
+// D(16x8,f32) += A(16x8,tf32,row) * B(8x8,tf32,col)
+__device__ __forceinline__ void mma_m16n8k8_tf32(float (&d)[4], const uint32_t (&a)[4],
+                                                 uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 "
+      "{%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// 16-byte async copy global -> shared; src_bytes = 0 zero-fills the destination
+__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src, int src_bytes) {
+  uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem_src),
+               "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N));
+}
+
+__device__ __forceinline__ void add4(float4 &a, const float4 &b) {
+  a.x += b.x;
+  a.y += b.y;
+  a.z += b.z;
+  a.w += b.w;
+}
+
+}  // namespace hcspmm

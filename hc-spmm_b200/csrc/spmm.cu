@@ -1,0 +1,411 @@
+// spmm.cu -- the hybrid SpMM kernel  Y = A * X  (binary CSR A, FP32 X/Y) for sm_100a.
+//
+// Replaces the nine spmm_forward_cuda_kernel_arbi_warps_hybrid_* kernels of the reference
+// (/root/reference/hybrid_kernel/hybrid_all_kernel.cu:919-2770) for the plain-SpMM part:
+// one launch, one CTA per 16-row window, the window's hybrid_type picks the path --
+//
+//  CUDA-core path (hybrid_type == 0; reference :960-1037, :1371-1382)
+//    HBM/L2-gather bound.  A warp walks a row: 32 column ids are fetched with one
+//    coalesced load and broadcast by shuffle; each edge's X row is read with 128-bit
+//    loads by a group of LPE lanes (NV float4 per lane), 8/NV*... independent loads in
+//    flight per lane; FP32 register accumulators; groups are reduced by shuffles.  Rows
+//    with >= long_row non-zeros (power-law hubs) are split over all eight warps of the
+//    CTA and reduced through shared memory in a fixed order (deterministic, no atomics).
+//
+//  tensor-core path (hybrid_type != 0; reference :1039-1121)
+//    The window is condensed to its U distinct columns (edgeToColumn).  The CTA rebuilds,
+//    in shared memory, the column list and one 16-bit row mask per condensed column from
+//    edgeToColumn / edgeToRow / edgeList -- the same three arrays the reference scatters
+//    into its sparse_A tile (:1072-1079) -- so each distinct X row is gathered ONCE per
+//    window (cp.async 16-byte copies into a padded, bank-conflict-free tile, double
+//    buffered) and multiplied on the tensor cores: mma.sync.m16n8k8 TF32, A fragments
+//    built straight from the bit masks (no A tile in memory), FP32 accumulate.  Unlike the
+//    reference there is no cap on U (MAX_BLK, :23) or on dim (:1098).
+//
+// Feature slabs: blockIdx.y selects a slab of `slab` features.  CTAs are scheduled
+// x-fastest, so all windows of one slab run before the next slab starts and the
+// N x slab slice of X they gather from can stay L2-resident.
+#include "common.cuh"
+
+namespace hcspmm {
+
+constexpr int KC = 16;      // condensed columns staged per pipeline step (two k=8 MMA steps)
+constexpr int UCAP = 1024;  // condensed columns whose (col, mask) are resident at once
+
+struct SpmmParams {
+  const float *x;
+  long long ldx;
+  int x_rows;
+  const int *rowptr, *colidx, *bp, *etc, *etr, *ht;
+  int n_rows, dim, slab;
+  int precision, accumulate;
+  float *y;
+  long long ldy;
+  int long_row;
+};
+
+// ---------------------------------------------------------------------------------------
+// CUDA-core gather: accumulate X rows of edges [eb, ee), visiting 32-edge chunks
+// chunk0, chunk0 + chunk_stride, ...
+// ---------------------------------------------------------------------------------------
+template <int LPE, int NV>
+__device__ __forceinline__ void gather_accumulate(float4 (&acc)[NV], const float *__restrict__ xlane,
+                                                  long long ldx, int x_rows,
+                                                  const int *__restrict__ colidx, int eb, int ee,
+                                                  int chunk0, int chunk_stride, int lane, int q,
+                                                  const bool (&active)[NV]) {
+  constexpr int G = 32 / LPE;
+  constexpr int U = NV >= 4 ? 2 : (NV == 2 ? 4 : 8);
+  for (int base = eb + chunk0 * 32; base < ee; base += chunk_stride * 32) {
+    const int n = min(32, ee - base);
+    const int c = (lane < n) ? __ldg(colidx + base + lane) : -1;
+#pragma unroll 1
+    for (int t = 0; t * G < n; t += U) {
+      float4 v[U][NV];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int j = (t + u) * G + q;
+        const int cu = __shfl_sync(0xffffffffu, c, j & 31);
+        const bool ok = (j < n) && ((unsigned)cu < (unsigned)x_rows);
+        const float *src = xlane + (long long)cu * ldx;
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+          v[u][i] = (ok && active[i]) ? ldg_f4(src + i * LPE * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int i = 0; i < NV; ++i) add4(acc[i], v[u][i]);
+    }
+  }
+}
+
+template <int LPE, int NV>
+__device__ __forceinline__ void group_reduce(float4 (&acc)[NV]) {
+#pragma unroll
+  for (int o = LPE; o < 32; o <<= 1)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      acc[i].x += __shfl_xor_sync(0xffffffffu, acc[i].x, o);
+      acc[i].y += __shfl_xor_sync(0xffffffffu, acc[i].y, o);
+      acc[i].z += __shfl_xor_sync(0xffffffffu, acc[i].z, o);
+      acc[i].w += __shfl_xor_sync(0xffffffffu, acc[i].w, o);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Tensor-core window
+// ---------------------------------------------------------------------------------------
+template <int MAXNT>
+__device__ __forceinline__ void tc_window(const SpmmParams &p, int w, int e0, int e1, int feat0,
+                                          int S, float *smem) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int g = lane >> 2, tig = lane & 3;
+  const int stride = S + 8;
+  int *ucol = reinterpret_cast<int *>(smem);
+  unsigned *umask = reinterpret_cast<unsigned *>(smem) + (UCAP + KC);
+  float *xs = smem + 2 * (UCAP + KC);
+  const int NT = S >> 3;
+  const int nvec = S >> 2;
+  const int upad = p.bp[w] * BLK_W;
+  const float *xbase = p.x + feat0;
+
+  float acc[MAXNT][4];
+#pragma unroll
+  for (int k = 0; k < MAXNT; ++k) acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f;
+
+  for (int u0 = 0; u0 < upad; u0 += UCAP) {
+    const int ucnt = min(UCAP, upad - u0);
+    const int ucnt16 = (ucnt + KC - 1) / KC * KC;
+    __syncthreads();  // previous chunk fully consumed
+    for (int i = tid; i < ucnt16; i += CTA_THREADS) { ucol[i] = -1; umask[i] = 0u; }
+    __syncthreads();
+    for (int e = e0 + tid; e < e1; e += CTA_THREADS) {
+      const int r = __ldg(p.etc + e) - u0;
+      if (r >= 0 && r < ucnt) {
+        ucol[r] = __ldg(p.colidx + e);
+        atomicOr(&umask[r], 1u << (__ldg(p.etr + e) & (BLK_H - 1)));
+      }
+    }
+    __syncthreads();
+    const int nk = ucnt16 / KC;
+    auto stage = [&](int kc, int buf) {
+      float *dst = xs + buf * KC * stride;
+      for (int rr = wid; rr < KC; rr += CTA_WARPS) {
+        const int col = ucol[kc * KC + rr];
+        const bool ok = (unsigned)col < (unsigned)p.x_rows;
+        const float *src = ok ? xbase + (long long)col * p.ldx : p.x;
+        for (int v = lane; v < nvec; v += 32)
+          cp_async_16(dst + rr * stride + v * 4, ok ? src + v * 4 : src, ok ? 16 : 0);
+      }
+      cp_async_commit();
+    };
+    stage(0, 0);
+    for (int kc = 0; kc < nk; ++kc) {
+      const int buf = kc & 1;
+      if (kc + 1 < nk) {
+        stage(kc + 1, buf ^ 1);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncthreads();
+      const float *xt = xs + buf * KC * stride;
+#pragma unroll
+      for (int ks = 0; ks < KC / 8; ++ks) {
+        const int k0 = kc * KC + ks * 8;
+        const unsigned mlo = umask[k0 + tig], mhi = umask[k0 + tig + 4];
+        if (__any_sync(0xffffffffu, (mlo | mhi) != 0u)) {
+          uint32_t a[4];
+          a[0] = ((mlo >> g) & 1u) ? 0x3f800000u : 0u;
+          a[1] = ((mlo >> (g + 8)) & 1u) ? 0x3f800000u : 0u;
+          a[2] = ((mhi >> g) & 1u) ? 0x3f800000u : 0u;
+          a[3] = ((mhi >> (g + 8)) & 1u) ? 0x3f800000u : 0u;
+          const float *r0p = xt + (ks * 8 + tig) * stride + g;
+          const float *r1p = r0p + 4 * stride;
+#pragma unroll
+          for (int k = 0; k < MAXNT; ++k) {
+            const int nt = wid + k * CTA_WARPS;
+            if (nt < NT) {
+              const float x0 = r0p[nt * 8], x1 = r1p[nt * 8];
+              const uint32_t b0 = f32_to_tf32(x0), b1 = f32_to_tf32(x1);
+              mma_m16n8k8_tf32(acc[k], a, b0, b1);
+              if (p.precision == HCSPMM_PRECISION_TF32X2) {
+                const uint32_t c0 = f32_to_tf32(x0 - __uint_as_float(b0));
+                const uint32_t c1 = f32_to_tf32(x1 - __uint_as_float(b1));
+                mma_m16n8k8_tf32(acc[k], a, c0, c1);
+              }
+            }
+          }
+        }
+      }
+      __syncthreads();  // tile consumed before it is overwritten two steps later
+    }
+  }
+  const int row0 = w * BLK_H + g, row1 = row0 + 8;
+#pragma unroll
+  for (int k = 0; k < MAXNT; ++k) {
+    const int nt = wid + k * CTA_WARPS;
+    if (nt < NT) {
+      const int col = feat0 + nt * 8 + tig * 2;
+      if (row0 < p.n_rows) {
+        float2 *dst = reinterpret_cast<float2 *>(p.y + (long long)row0 * p.ldy + col);
+        float2 v = make_float2(acc[k][0], acc[k][1]);
+        if (p.accumulate) { float2 o = *dst; v.x += o.x; v.y += o.y; }
+        *dst = v;
+      }
+      if (row1 < p.n_rows) {
+        float2 *dst = reinterpret_cast<float2 *>(p.y + (long long)row1 * p.ldy + col);
+        float2 v = make_float2(acc[k][2], acc[k][3]);
+        if (p.accumulate) { float2 o = *dst; v.x += o.x; v.y += o.y; }
+        *dst = v;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// The hybrid kernel.  Slab width S <= LPE * NV * 4 floats; X/Y 16-byte aligned, ldx/ldy % 4 == 0.
+// ---------------------------------------------------------------------------------------
+template <int LPE, int NV>
+__global__ void __launch_bounds__(CTA_THREADS, 3) spmm_hybrid_kernel(const SpmmParams p) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ int rp[BLK_H + 1];
+  __shared__ int s_next;
+  const int w = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int r0 = w * BLK_H;
+  const int feat0 = blockIdx.y * p.slab;
+  const int S = min(p.slab, p.dim - feat0);
+  const int nvec = S >> 2;
+  if (tid <= BLK_H) rp[tid] = __ldg(p.rowptr + min(r0 + tid, p.n_rows));
+  if (tid == 0) s_next = 0;
+  __syncthreads();
+  const int e0 = rp[0], e1 = rp[BLK_H];
+
+  if (p.ht != nullptr && p.precision != HCSPMM_PRECISION_FP32 && (S & 7) == 0 && e1 > e0 &&
+      __ldg(p.ht + w) != 0) {
+    tc_window<(LPE * NV * 4 + 63) / 64>(p, w, e0, e1, feat0, S, smem);
+    return;
+  }
+
+  constexpr int G = 32 / LPE;
+  const int q = lane / LPE, g = lane % LPE;
+  bool active[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) active[i] = (g + i * LPE) < nvec;
+  const float *xlane = p.x + feat0 + g * 4;
+  const int rows_here = min(BLK_H, p.n_rows - r0);
+
+  // phase 1: short rows, one warp per row, rows claimed dynamically
+  for (;;) {
+    int r = 0;
+    if (lane == 0) r = atomicAdd(&s_next, 1);
+    r = __shfl_sync(0xffffffffu, r, 0);
+    if (r >= rows_here) break;
+    const int eb = rp[r], ee = rp[r + 1];
+    if (ee - eb >= p.long_row) continue;
+    float4 acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    gather_accumulate<LPE, NV>(acc, xlane, p.ldx, p.x_rows, p.colidx, eb, ee, 0, 1, lane, q, active);
+    group_reduce<LPE, NV>(acc);
+    if (q == 0) {
+      float *yrow = p.y + (long long)(r0 + r) * p.ldy + feat0 + g * 4;
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        if (active[i]) {
+          float4 *dst = reinterpret_cast<float4 *>(yrow + i * LPE * 4);
+          float4 v = acc[i];
+          if (p.accumulate) add4(v, *dst);
+          *dst = v;
+        }
+    }
+  }
+  (void)G;
+
+  // phase 2: long rows, all warps of the CTA share one row (CTA-uniform control flow)
+  bool any_long = false;
+  for (int r = 0; r < rows_here; ++r) any_long |= (rp[r + 1] - rp[r] >= p.long_row);
+  if (!any_long) return;
+  for (int r = 0; r < rows_here; ++r) {
+    const int eb = rp[r], ee = rp[r + 1];
+    if (ee - eb < p.long_row) continue;
+    float4 acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    gather_accumulate<LPE, NV>(acc, xlane, p.ldx, p.x_rows, p.colidx, eb, ee, wid, CTA_WARPS, lane, q,
+                               active);
+    group_reduce<LPE, NV>(acc);
+    if (q == 0) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        if (active[i])
+          *reinterpret_cast<float4 *>(smem + wid * S + (g + i * LPE) * 4) = acc[i];
+    }
+    __syncthreads();
+    for (int v = tid; v < nvec; v += CTA_THREADS) {
+      float4 s = *reinterpret_cast<const float4 *>(smem + v * 4);
+#pragma unroll
+      for (int ww = 1; ww < CTA_WARPS; ++ww)
+        add4(s, *reinterpret_cast<const float4 *>(smem + ww * S + v * 4));
+      float4 *dst = reinterpret_cast<float4 *>(p.y + (long long)(r0 + r) * p.ldy + feat0 + v * 4);
+      if (p.accumulate) add4(s, *dst);
+      *dst = s;
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Scalar kernel: any dim / alignment.  One warp per row, lane = feature (mod 32), FP32 sum in
+// CSR order -- bit-identical to the reference's CUDA-core arithmetic (:1003-1010).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CTA_THREADS) spmm_scalar_kernel(const SpmmParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * CTA_WARPS + (threadIdx.x >> 5);
+  if (row >= p.n_rows) return;
+  const int eb = __ldg(p.rowptr + row), ee = __ldg(p.rowptr + row + 1);
+  for (int f0 = 0; f0 < p.dim; f0 += 128) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int base = eb; base < ee; base += 32) {
+      const int n = min(32, ee - base);
+      const int c = (lane < n) ? __ldg(p.colidx + base + lane) : -1;
+#pragma unroll 4
+      for (int j = 0; j < n; ++j) {
+        const int cu = __shfl_sync(0xffffffffu, c, j);
+        if ((unsigned)cu < (unsigned)p.x_rows) {
+          const float *src = p.x + (long long)cu * p.ldx + f0 + lane;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (f0 + lane + 32 * i < p.dim) acc[i] += __ldg(src + 32 * i);
+        }
+      }
+    }
+    float *dst = p.y + row * p.ldy + f0 + lane;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (f0 + lane + 32 * i < p.dim) dst[32 * i] = p.accumulate ? dst[32 * i] + acc[i] : acc[i];
+  }
+}
+
+static size_t hybrid_smem_bytes(int S, bool tc) {
+  size_t cuda_path = (size_t)CTA_WARPS * S * sizeof(float);
+  size_t tc_path = tc ? (size_t)(2 * (UCAP + KC) + 2 * KC * (S + 8)) * sizeof(float) : 0;
+  return cuda_path > tc_path ? cuda_path : tc_path;
+}
+
+template <int LPE, int NV>
+static cudaError_t launch_hybrid(const SpmmParams &p, dim3 grid, size_t smem, cudaStream_t stream) {
+  cudaError_t err = cudaFuncSetAttribute(spmm_hybrid_kernel<LPE, NV>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  spmm_hybrid_kernel<LPE, NV><<<grid, CTA_THREADS, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+int launch_spmm(const float *x, int64_t ldx, int32_t x_rows, const int32_t *rowptr,
+                const int32_t *colidx, const int32_t *bp, const int32_t *etc, const int32_t *etr,
+                const int32_t *ht, int32_t n_rows, int64_t nnz, int32_t dim, int precision,
+                int accumulate, float *y, int64_t ldy, cudaStream_t stream) {
+  if (n_rows < 0 || dim < 0 || nnz < 0 || x_rows < 0) {
+    set_error("spmm: negative size");
+    return HCSPMM_E_INVALID;
+  }
+  if (n_rows == 0 || dim == 0) return 0;
+  if (!x || !rowptr || !y || (!colidx && nnz > 0)) {
+    set_error("spmm: null pointer argument");
+    return HCSPMM_E_INVALID;
+  }
+  if (ldx < dim || ldy < dim) {
+    set_error("spmm: leading dimension smaller than dim");
+    return HCSPMM_E_INVALID;
+  }
+  if (precision < 0 || precision > HCSPMM_PRECISION_FP32) {
+    set_error("spmm: unknown precision %d", precision);
+    return HCSPMM_E_INVALID;
+  }
+  const bool labels = ht != nullptr && precision != HCSPMM_PRECISION_FP32;
+  if (labels && (!bp || !etc || !etr)) {
+    set_error("spmm: hybrid_type given without blockPartition/edgeToColumn/edgeToRow");
+    return HCSPMM_E_INVALID;
+  }
+  SpmmParams p;
+  p.x = x; p.ldx = ldx; p.x_rows = x_rows;
+  p.rowptr = rowptr; p.colidx = colidx; p.bp = bp; p.etc = etc; p.etr = etr;
+  p.ht = labels ? ht : nullptr;
+  p.n_rows = n_rows; p.dim = dim;
+  p.precision = precision; p.accumulate = accumulate;
+  p.y = y; p.ldy = ldy;
+  p.long_row = tuning().long_row > 0 ? tuning().long_row : 0x7fffffff;
+
+  const int n_windows = (n_rows + BLK_H - 1) / BLK_H;
+  const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0 &&
+                   (ldx & 3) == 0 && (ldy & 3) == 0 && (dim & 3) == 0;
+  cudaError_t err;
+  if (!vec) {
+    p.slab = dim;
+    spmm_scalar_kernel<<<(n_rows + CTA_WARPS - 1) / CTA_WARPS, CTA_THREADS, 0, stream>>>(p);
+    err = cudaGetLastError();
+  } else {
+    int slab = tuning().slab > 0 ? (tuning().slab + 31) / 32 * 32 : 512;
+    if (slab > 512) slab = 512;
+    if (slab > dim) slab = dim;
+    p.slab = slab;
+    dim3 grid(n_windows, (dim + slab - 1) / slab, 1);
+    const bool tc = labels && (slab % 8 == 0);
+    const size_t smem = hybrid_smem_bytes(slab, tc);
+    if (slab <= 32) err = launch_hybrid<8, 1>(p, grid, smem, stream);
+    else if (slab <= 64) err = launch_hybrid<16, 1>(p, grid, smem, stream);
+    else if (slab <= 128) err = launch_hybrid<32, 1>(p, grid, smem, stream);
+    else if (slab <= 256) err = launch_hybrid<32, 2>(p, grid, smem, stream);
+    else err = launch_hybrid<32, 4>(p, grid, smem, stream);
+  }
+  if (err != cudaSuccess) {
+    set_error("spmm launch: %s", cudaGetErrorString(err));
+    return (int)err;
+  }
+  return 0;
+}
+
+}  // namespace hcspmm

@@ -1,0 +1,281 @@
+// torch_shim.cpp -- the `HCSPMM` Python extension module: a thin torch layer over the C ABI
+// of libhcspmm.so (include/hcspmm.h).
+//
+// Mirrors the reference's pybind module, /root/reference/hybrid_kernel/hybrid_all.cpp:500-525:
+// the same 18 names with the same positional signatures and list-of-tensor returns, so
+// /root/reference/GNN_model.py and HC-SpMM_main.py import and call it unchanged.  Differences,
+// all in the direction of "works where the reference does not":
+//   * every entry point accepts any dim / hidden (the reference needs 32 / 64 / <= 48);
+//   * inputs are checked for device, dtype, shape and contiguity (the reference checks
+//     "is CUDA" and "is contiguous" on the first six tensors only, hybrid_all.cpp:185-210);
+//   * `weights` may be a strided view -- it is made contiguous (the reference reads its raw
+//     memory, hybrid_all_kernel.cu:645,753; set_bug_compat(True) restores that reading);
+//   * launches go to the CURRENT stream of the input's device, outputs come from the caching
+//     allocator (the reference uses the legacy stream and leaks cudaMalloc blobs, :356-372);
+//   * the operator may be rectangular: output rows = nodePointer.size(0) - 1, X rows =
+//     input.size(0) (row-partitioned shards keep global column ids).
+// There is no CPU path: a non-CUDA tensor is an error.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/extension.h>
+
+#include <vector>
+
+#include "../../include/hcspmm.h"
+
+namespace {
+
+int g_classifier = HCSPMM_CLASSIFIER_SHIPPED;
+int g_precision = HCSPMM_PRECISION_TF32;
+bool g_bug_compat = false;
+
+void check_rc(int rc, const char *what) {
+  TORCH_CHECK(rc == 0, "HCSPMM.", what, " failed (code ", rc, "): ", hcspmm_last_error());
+}
+
+void check_i32(const torch::Tensor &t, const char *name, const torch::Tensor &like) {
+  TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor");
+  TORCH_CHECK(t.is_contiguous(), name, " must be contiguous");
+  TORCH_CHECK(t.scalar_type() == torch::kInt32, name, " must be int32");
+  TORCH_CHECK(t.device() == like.device(), name, " must be on the same device as the input");
+}
+
+void check_f32_2d(const torch::Tensor &t, const char *name) {
+  TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor");
+  TORCH_CHECK(t.is_contiguous(), name, " must be contiguous");
+  TORCH_CHECK(t.scalar_type() == torch::kFloat32, name, " must be float32");
+  TORCH_CHECK(t.dim() == 2, name, " must be 2-D");
+}
+
+struct Graph {
+  const int32_t *rowptr, *colidx, *bp, *etc, *etr, *ht;
+  int32_t n_rows;
+  int64_t nnz;
+};
+
+Graph check_graph(const torch::Tensor &input, const torch::Tensor &nodePointer,
+                  const torch::Tensor &edgeList, const torch::Tensor &blockPartition,
+                  const torch::Tensor &edgeToColumn, const torch::Tensor &edgeToRow,
+                  const torch::Tensor &hybrid_type) {
+  check_f32_2d(input, "input");
+  check_i32(nodePointer, "nodePointer", input);
+  check_i32(edgeList, "edgeList", input);
+  check_i32(blockPartition, "blockPartition", input);
+  check_i32(edgeToColumn, "edgeToColumn", input);
+  check_i32(edgeToRow, "edgeToRow", input);
+  check_i32(hybrid_type, "hybrid_type", input);
+  TORCH_CHECK(nodePointer.numel() >= 1, "nodePointer must have num_nodes + 1 entries");
+  Graph g;
+  g.n_rows = (int32_t)(nodePointer.size(0) - 1);  // hybrid_all.cpp:212
+  g.nnz = edgeList.size(0);                       // hybrid_all.cpp:213
+  const int64_t w = (g.n_rows + HCSPMM_BLK_H - 1) / HCSPMM_BLK_H;
+  TORCH_CHECK(blockPartition.numel() >= w && hybrid_type.numel() >= w,
+              "blockPartition / hybrid_type must have one entry per 16-row window");
+  TORCH_CHECK(edgeToColumn.numel() >= g.nnz && edgeToRow.numel() >= g.nnz,
+              "edgeToColumn / edgeToRow must have one entry per edge");
+  g.rowptr = nodePointer.data_ptr<int32_t>();
+  g.colidx = edgeList.data_ptr<int32_t>();
+  g.bp = blockPartition.data_ptr<int32_t>();
+  g.etc = edgeToColumn.data_ptr<int32_t>();
+  g.etr = edgeToRow.data_ptr<int32_t>();
+  g.ht = hybrid_type.data_ptr<int32_t>();
+  return g;
+}
+
+// preprocess, hybrid_all.cpp:13-17 / :501 -> hybrid_all_kernel.cu:339-408
+std::vector<torch::Tensor> preprocess(torch::Tensor edgeList, torch::Tensor nodePointer,
+                                      int64_t num_nodes, int64_t edge_num, int64_t num_row_windows) {
+  TORCH_CHECK(edgeList.is_cuda() && nodePointer.is_cuda(), "preprocess: tensors must be CUDA tensors");
+  TORCH_CHECK(edgeList.scalar_type() == torch::kInt32 && nodePointer.scalar_type() == torch::kInt32,
+              "preprocess: edgeList / nodePointer must be int32");
+  TORCH_CHECK(edgeList.is_contiguous() && nodePointer.is_contiguous(), "preprocess: tensors must be contiguous");
+  TORCH_CHECK(nodePointer.numel() == num_nodes + 1, "preprocess: nodePointer must have num_nodes + 1 entries");
+  TORCH_CHECK(edgeList.numel() == edge_num, "preprocess: edgeList must have edge_num entries");
+  TORCH_CHECK(num_row_windows == (num_nodes + HCSPMM_BLK_H - 1) / HCSPMM_BLK_H,
+              "preprocess: num_row_windows must be ceil(num_nodes / 16)");
+  c10::cuda::CUDAGuard guard(edgeList.device());
+  auto opts = torch::TensorOptions().dtype(torch::kInt32).device(edgeList.device());
+  auto bp = torch::zeros({num_row_windows}, opts);
+  auto ht = torch::zeros({num_row_windows}, opts);
+  auto etc = torch::zeros({edge_num}, opts);
+  auto etr = torch::zeros({edge_num}, opts);
+  const size_t ws_bytes = hcspmm_preprocess_workspace_bytes((int32_t)num_nodes, edge_num);
+  auto ws = torch::empty({(int64_t)ws_bytes}, opts.dtype(torch::kUInt8));
+  check_rc(hcspmm_preprocess(edgeList.data_ptr<int32_t>(), nodePointer.data_ptr<int32_t>(),
+                             (int32_t)num_nodes, edge_num, (int32_t)num_row_windows, g_classifier,
+                             bp.data_ptr<int32_t>(), etc.data_ptr<int32_t>(), etr.data_ptr<int32_t>(),
+                             ht.data_ptr<int32_t>(), ws.data_ptr(), ws_bytes,
+                             at::cuda::getCurrentCUDAStream().stream()),
+           "preprocess");
+  // row_nzr / col_nzr are one-element placeholders in the reference too (:405)
+  auto row_nzr = torch::zeros({1}, opts), col_nzr = torch::zeros({1}, opts);
+  return {bp, etc, etr, ht, row_nzr, col_nzr};
+}
+
+// forward / forward_more / forward_fixed32 / forward_fixed64 and their backward_* aliases,
+// hybrid_all.cpp:194-308 -> hybrid_all_kernel.cu:410-595
+std::vector<torch::Tensor> spmm_forward(torch::Tensor input, torch::Tensor nodePointer,
+                                        torch::Tensor edgeList, torch::Tensor blockPartition,
+                                        torch::Tensor edgeToColumn, torch::Tensor edgeToRow,
+                                        torch::Tensor hybrid_type, torch::Tensor row_nzr,
+                                        torch::Tensor col_nzr) {
+  (void)row_nzr; (void)col_nzr;
+  Graph g = check_graph(input, nodePointer, edgeList, blockPartition, edgeToColumn, edgeToRow, hybrid_type);
+  c10::cuda::CUDAGuard guard(input.device());
+  const int64_t dim = input.size(1);
+  auto out = torch::empty({g.n_rows, dim}, input.options());
+  check_rc(hcspmm_spmm(input.data_ptr<float>(), dim, (int32_t)input.size(0), g.rowptr, g.colidx, g.bp,
+                       g.etc, g.etr, g.ht, g.n_rows, g.nnz, (int32_t)dim, g_precision, 0,
+                       out.data_ptr<float>(), dim, at::cuda::getCurrentCUDAStream().stream()),
+           "forward");
+  return {out};
+}
+
+// Y += A * X into a caller-provided tensor (shard-pipelined multi-GPU aggregation)
+torch::Tensor spmm_accumulate(torch::Tensor input, torch::Tensor nodePointer, torch::Tensor edgeList,
+                              torch::Tensor blockPartition, torch::Tensor edgeToColumn,
+                              torch::Tensor edgeToRow, torch::Tensor hybrid_type, torch::Tensor out,
+                              bool accumulate) {
+  Graph g = check_graph(input, nodePointer, edgeList, blockPartition, edgeToColumn, edgeToRow, hybrid_type);
+  check_f32_2d(out, "out");
+  TORCH_CHECK(out.device() == input.device(), "out must be on the input's device");
+  TORCH_CHECK(out.size(0) == g.n_rows && out.size(1) == input.size(1), "out must be [num_nodes, dim]");
+  c10::cuda::CUDAGuard guard(input.device());
+  const int64_t dim = input.size(1);
+  check_rc(hcspmm_spmm(input.data_ptr<float>(), dim, (int32_t)input.size(0), g.rowptr, g.colidx, g.bp,
+                       g.etc, g.etr, g.ht, g.n_rows, g.nnz, (int32_t)dim, g_precision,
+                       accumulate ? 1 : 0, out.data_ptr<float>(), dim,
+                       at::cuda::getCurrentCUDAStream().stream()),
+           "spmm_accumulate");
+  return out;
+}
+
+torch::Tensor dense_weights(const torch::Tensor &weights, const torch::Tensor &input) {
+  TORCH_CHECK(weights.is_cuda() && weights.device() == input.device(), "weights must be on the input's device");
+  TORCH_CHECK(weights.scalar_type() == torch::kFloat32 && weights.dim() == 2, "weights must be 2-D float32");
+  TORCH_CHECK(weights.size(0) == input.size(1), "weights must be [dim, hidden]");
+  if (g_bug_compat && !weights.is_contiguous())
+    // what the reference multiplies by: the view's raw memory read as row-major [dim, hidden]
+    return weights.as_strided({weights.size(0), weights.size(1)}, {weights.size(1), 1});
+  return weights.contiguous();
+}
+
+std::vector<torch::Tensor> fused_impl(const torch::Tensor &input, const Graph &g,
+                                      const torch::Tensor &weights, torch::Tensor out, const char *what) {
+  c10::cuda::CUDAGuard guard(input.device());
+  auto w = dense_weights(weights, input);
+  const int64_t dim = input.size(1), hidden = w.size(1);
+  auto z = torch::empty({g.n_rows, dim}, input.options());
+  check_rc(hcspmm_spmm_gemm(input.data_ptr<float>(), dim, (int32_t)input.size(0), g.rowptr, g.colidx, g.bp,
+                            g.etc, g.etr, g.ht, g.n_rows, g.nnz, (int32_t)dim, g_precision,
+                            w.data_ptr<float>(), hidden, (int32_t)hidden, out.data_ptr<float>(), hidden,
+                            z.data_ptr<float>(), dim, at::cuda::getCurrentCUDAStream().stream()),
+           what);
+  return {out, z};
+}
+
+// forward_fixed32_fused / forward_fixed64_fused / forward_GIN_final_fused (+ backward_*),
+// hybrid_all.cpp:310-403, 469-498 -> hybrid_all_kernel.cu:596-700, 810-863
+std::vector<torch::Tensor> spmm_forward_fused(torch::Tensor input, torch::Tensor nodePointer,
+                                              torch::Tensor edgeList, torch::Tensor blockPartition,
+                                              torch::Tensor edgeToColumn, torch::Tensor edgeToRow,
+                                              torch::Tensor hybrid_type, torch::Tensor row_nzr,
+                                              torch::Tensor col_nzr, torch::Tensor weights) {
+  (void)row_nzr; (void)col_nzr;
+  Graph g = check_graph(input, nodePointer, edgeList, blockPartition, edgeToColumn, edgeToRow, hybrid_type);
+  TORCH_CHECK(weights.dim() == 2, "weights must be 2-D");
+  auto out = torch::empty({g.n_rows, weights.size(1)}, input.options());
+  return fused_impl(input, g, weights, out, "forward_fused");
+}
+
+// forward_final_fused / forward_final_fused_64 (+ backward_*): writes the caller's `output`,
+// hybrid_all.cpp:405-467 -> hybrid_all_kernel.cu:701-809
+std::vector<torch::Tensor> spmm_forward_final_fused(torch::Tensor input, torch::Tensor nodePointer,
+                                                    torch::Tensor edgeList, torch::Tensor blockPartition,
+                                                    torch::Tensor edgeToColumn, torch::Tensor edgeToRow,
+                                                    torch::Tensor hybrid_type, torch::Tensor row_nzr,
+                                                    torch::Tensor col_nzr, torch::Tensor weights,
+                                                    torch::Tensor output) {
+  (void)row_nzr; (void)col_nzr;
+  Graph g = check_graph(input, nodePointer, edgeList, blockPartition, edgeToColumn, edgeToRow, hybrid_type);
+  check_f32_2d(output, "output");
+  TORCH_CHECK(weights.dim() == 2, "weights must be 2-D");
+  TORCH_CHECK(output.device() == input.device(), "output must be on the input's device");
+  TORCH_CHECK(output.size(0) == g.n_rows && output.size(1) == weights.size(1),
+              "output must be [num_nodes, hidden] = [", g.n_rows, ", ", weights.size(1), "]");
+  return fused_impl(input, g, weights, output, "forward_final_fused");
+}
+
+torch::Tensor gemm_tf32(torch::Tensor a, torch::Tensor b) {
+  check_f32_2d(a, "a");
+  check_f32_2d(b, "b");
+  TORCH_CHECK(a.device() == b.device() && a.size(1) == b.size(0), "gemm_tf32: shape/device mismatch");
+  c10::cuda::CUDAGuard guard(a.device());
+  auto out = torch::empty({a.size(0), b.size(1)}, a.options());
+  check_rc(hcspmm_gemm_tf32(a.data_ptr<float>(), a.size(1), b.data_ptr<float>(), b.size(1), (int32_t)a.size(0),
+                            (int32_t)a.size(1), (int32_t)b.size(1), out.data_ptr<float>(), b.size(1),
+                            at::cuda::getCurrentCUDAStream().stream()),
+           "gemm_tf32");
+  return out;
+}
+
+std::string set_classifier(const std::string &mode) {
+  static const char *names[] = {"shipped", "intended", "b200", "all_cuda", "all_tc"};
+  std::string old = names[g_classifier];
+  for (int i = 0; i < 5; ++i)
+    if (mode == names[i]) { g_classifier = i; return old; }
+  TORCH_CHECK(false, "unknown classifier '", mode, "' (shipped|intended|b200|all_cuda|all_tc)");
+}
+
+std::string set_precision(const std::string &mode) {
+  static const char *names[] = {"tf32", "tf32x2", "fp32"};
+  std::string old = names[g_precision];
+  for (int i = 0; i < 3; ++i)
+    if (mode == names[i]) { g_precision = i; return old; }
+  TORCH_CHECK(false, "unknown precision '", mode, "' (tf32|tf32x2|fp32)");
+}
+
+bool set_bug_compat(bool on) {
+  bool old = g_bug_compat;
+  g_bug_compat = on;
+  return old;
+}
+
+int64_t set_tuning(const std::string &key, int64_t value) {
+  int old = hcspmm_set_tuning(key.c_str(), (int)value);
+  TORCH_CHECK(old != -1 || key == "slab" || key == "long_row", "unknown tuning key '", key, "'");
+  return old;
+}
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.doc() = "HCSPMM: B200-native hybrid SpMM (drop-in for the HC-SpMM reference extension)";
+  m.def("preprocess", &preprocess, "Preprocess Step (GPU)");
+  // forward computation -- names of hybrid_all.cpp:503-512
+  m.def("forward", &spmm_forward, "HCSPMM SPMM forward (CUDA)");
+  m.def("forward_more", &spmm_forward, "HCSPMM SPMM forward more (CUDA)");
+  m.def("forward_fixed32", &spmm_forward, "HCSPMM SPMM forward fixed32 (CUDA)");
+  m.def("forward_fixed32_fused", &spmm_forward_fused, "HCSPMM SPMM forward fixed32 fused (CUDA)");
+  m.def("forward_final_fused", &spmm_forward_final_fused, "HCSPMM SPMM forward final fused (CUDA)");
+  m.def("forward_fixed64", &spmm_forward, "HCSPMM SPMM forward fixed64 (CUDA)");
+  m.def("forward_fixed64_fused", &spmm_forward_fused, "HCSPMM SPMM forward fixed64 fused (CUDA)");
+  m.def("forward_final_fused_64", &spmm_forward_final_fused, "HCSPMM SPMM forward final fused 64 (CUDA)");
+  m.def("forward_GIN_final_fused", &spmm_forward_fused, "HCSPMM SPMM forward for GIN final fused (CUDA)");
+  // backward -- names of hybrid_all.cpp:516-523 (same functions, as in the reference)
+  m.def("backward", &spmm_forward, "HCSPMM SPMM backward (CUDA)");
+  m.def("backward_fixed32", &spmm_forward, "HCSPMM SPMM backward fixed32 (CUDA)");
+  m.def("backward_fixed32_fused", &spmm_forward_fused, "HCSPMM SPMM backward fixed32 fused (CUDA)");
+  m.def("backward_final_fused", &spmm_forward_final_fused, "HCSPMM SPMM backward final fused (CUDA)");
+  m.def("backward_fixed64", &spmm_forward, "HCSPMM SPMM backward fixed 64 (CUDA)");
+  m.def("backward_fixed64_fused", &spmm_forward_fused, "HCSPMM SPMM backward fixed 64 fused (CUDA)");
+  m.def("backward_final_fused_64", &spmm_forward_final_fused, "HCSPMM SPMM backward final fused 64 (CUDA)");
+  m.def("backward_GIN_final_fused", &spmm_forward_fused, "HCSPMM SPMM backward for GIN final fused (CUDA)");
+  // additions (not in the reference)
+  m.def("spmm_accumulate", &spmm_accumulate, "out (+)= A @ input into a caller tensor");
+  m.def("gemm_tf32", &gemm_tf32, "a @ b with TF32 tensor-core product");
+  m.def("set_classifier", &set_classifier, "shipped | intended | b200 | all_cuda | all_tc; returns the previous mode");
+  m.def("set_precision", &set_precision, "tf32 | tf32x2 | fp32; returns the previous mode");
+  m.def("set_bug_compat", &set_bug_compat, "read strided `weights` as raw memory like the reference");
+  m.def("set_tuning", &set_tuning, "kernel tuning knob (long_row, slab); returns the previous value");
+}

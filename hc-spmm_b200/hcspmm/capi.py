@@ -1,0 +1,189 @@
+"""ctypes binding of the C ABI (include/hcspmm.h) -- what a non-torch host binds.
+
+torch is used here only to own device memory and to name the current stream; every call goes
+through ``libhcspmm.so``'s ``extern "C"`` entry points with raw pointers.  There is no CPU
+fallback: if the library is missing, loading raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+from .build import LIB_PATH
+
+BLK_H, BLK_W = 16, 8
+CLASSIFIERS = {"shipped": 0, "intended": 1, "b200": 2, "all_cuda": 3, "all_tc": 4}
+PRECISIONS = {"tf32": 0, "tf32x2": 1, "fp32": 2}
+
+EXPORTS = [
+    "hcspmm_version", "hcspmm_last_error", "hcspmm_set_tuning",
+    "hcspmm_preprocess_workspace_bytes", "hcspmm_preprocess", "hcspmm_spmm", "hcspmm_spmm_gemm",
+    "hcspmm_gemm_tf32", "hcspmm_graph_create", "hcspmm_graph_spmm_host",
+    "hcspmm_graph_get_preprocess", "hcspmm_graph_destroy",
+]
+
+_lib = None
+_vp, _i32, _i64, _int, _sz = (ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_int,
+                              ctypes.c_size_t)
+
+
+class HcspmmError(RuntimeError):
+    pass
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise HcspmmError(f"{LIB_PATH} is missing: run `python __graft_entry__.py build` "
+                              "(there is no CPU fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        L.hcspmm_version.restype = _int
+        L.hcspmm_last_error.restype = ctypes.c_char_p
+        L.hcspmm_set_tuning.argtypes = [ctypes.c_char_p, _int]
+        L.hcspmm_preprocess_workspace_bytes.restype = _sz
+        L.hcspmm_preprocess_workspace_bytes.argtypes = [_i32, _i64]
+        L.hcspmm_preprocess.argtypes = [_vp, _vp, _i32, _i64, _i32, _int, _vp, _vp, _vp, _vp, _vp, _sz, _vp]
+        L.hcspmm_spmm.argtypes = [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _int,
+                                  _int, _vp, _i64, _vp]
+        L.hcspmm_spmm_gemm.argtypes = [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32,
+                                       _int, _vp, _i64, _i32, _vp, _i64, _vp, _i64, _vp]
+        L.hcspmm_gemm_tf32.argtypes = [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _i64, _vp]
+        L.hcspmm_graph_create.argtypes = [_vp, _vp, _i32, _i64, _i32, _int, ctypes.POINTER(_vp)]
+        L.hcspmm_graph_spmm_host.argtypes = [_vp, _vp, _i32, _int, _vp]
+        L.hcspmm_graph_get_preprocess.argtypes = [_vp, _vp, _vp, _vp, _vp]
+        L.hcspmm_graph_destroy.argtypes = [_vp]
+        L.hcspmm_graph_destroy.restype = None
+        _lib = L
+    return _lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise HcspmmError(f"{what} failed (code {rc}): {lib().hcspmm_last_error().decode()}")
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def num_windows(n_rows: int) -> int:
+    return (n_rows + BLK_H - 1) // BLK_H
+
+
+def set_tuning(key: str, value: int) -> int:
+    return lib().hcspmm_set_tuning(key.encode(), int(value))
+
+
+def preprocess(colidx: torch.Tensor, rowptr: torch.Tensor, classifier="shipped"):
+    """hcspmm_preprocess on device tensors -> (blockPartition, edgeToColumn, edgeToRow, hybrid_type)."""
+    assert colidx.is_cuda and rowptr.is_cuda and colidx.dtype == torch.int32 and rowptr.dtype == torch.int32
+    n, nnz = rowptr.numel() - 1, colidx.numel()
+    w = num_windows(n)
+    mode = CLASSIFIERS[classifier] if isinstance(classifier, str) else int(classifier)
+    with torch.cuda.device(colidx.device):
+        o = dict(dtype=torch.int32, device=colidx.device)
+        bp, ht = torch.zeros(w, **o), torch.zeros(w, **o)
+        etc, etr = torch.zeros(nnz, **o), torch.zeros(nnz, **o)
+        nbytes = lib().hcspmm_preprocess_workspace_bytes(n, nnz)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=colidx.device)
+        _check(lib().hcspmm_preprocess(_ptr(colidx), _ptr(rowptr), n, nnz, w, mode, _ptr(bp), _ptr(etc),
+                                       _ptr(etr), _ptr(ht), _ptr(ws), nbytes, _stream(colidx)),
+               "hcspmm_preprocess")
+    return bp, etc, etr, ht
+
+
+def spmm(x: torch.Tensor, rowptr, colidx, bp=None, etc=None, etr=None, ht=None, precision="tf32",
+         out: torch.Tensor | None = None, accumulate: bool = False, n_rows: int | None = None):
+    """hcspmm_spmm on device tensors.  x may be a row-strided view (stride(1) == 1)."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    n = rowptr.numel() - 1 if n_rows is None else n_rows
+    d = x.shape[1]
+    if out is None:
+        assert not accumulate
+        out = torch.empty((n, d), dtype=torch.float32, device=x.device)
+    assert out.stride(1) == 1 or d == 1
+    prec = PRECISIONS[precision] if isinstance(precision, str) else int(precision)
+    with torch.cuda.device(x.device):
+        _check(lib().hcspmm_spmm(_ptr(x), x.stride(0), x.shape[0], _ptr(rowptr), _ptr(colidx), _ptr(bp),
+                                 _ptr(etc), _ptr(etr), _ptr(ht), n, colidx.numel(), d, prec,
+                                 1 if accumulate else 0, _ptr(out), out.stride(0), _stream(x)),
+               "hcspmm_spmm")
+    return out
+
+
+def spmm_gemm(x, rowptr, colidx, bp, etc, etr, ht, w: torch.Tensor, precision="tf32"):
+    """hcspmm_spmm_gemm -> (out [n, hidden], z [n, dim])."""
+    assert x.is_cuda and x.is_contiguous() and w.is_cuda and w.is_contiguous()
+    n, d, h = rowptr.numel() - 1, x.shape[1], w.shape[1]
+    out = torch.empty((n, h), dtype=torch.float32, device=x.device)
+    z = torch.empty((n, d), dtype=torch.float32, device=x.device)
+    prec = PRECISIONS[precision] if isinstance(precision, str) else int(precision)
+    with torch.cuda.device(x.device):
+        _check(lib().hcspmm_spmm_gemm(_ptr(x), d, x.shape[0], _ptr(rowptr), _ptr(colidx), _ptr(bp), _ptr(etc),
+                                      _ptr(etr), _ptr(ht), n, colidx.numel(), d, prec, _ptr(w), h, h,
+                                      _ptr(out), h, _ptr(z), d, _stream(x)),
+               "hcspmm_spmm_gemm")
+    return out, z
+
+
+def gemm_tf32(a: torch.Tensor, b: torch.Tensor):
+    assert a.is_cuda and b.is_cuda and a.stride(1) == 1 and b.stride(1) == 1
+    out = torch.empty((a.shape[0], b.shape[1]), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        _check(lib().hcspmm_gemm_tf32(_ptr(a), a.stride(0), _ptr(b), b.stride(0), a.shape[0], a.shape[1],
+                                      b.shape[1], _ptr(out), out.stride(0), _stream(a)),
+               "hcspmm_gemm_tf32")
+    return out
+
+
+class HostGraph:
+    """hcspmm_graph_*: the host-buffer path (CSR and X/Y live in host memory; the library owns the
+    device copies and runs H2D -> kernel -> D2H inside each call)."""
+
+    def __init__(self, rowptr_cpu: torch.Tensor, colidx_cpu: torch.Tensor, x_rows: int | None = None,
+                 classifier="shipped"):
+        assert not rowptr_cpu.is_cuda and rowptr_cpu.dtype == torch.int32
+        self.n_rows = rowptr_cpu.numel() - 1
+        self.nnz = colidx_cpu.numel()
+        self.x_rows = self.n_rows if x_rows is None else x_rows
+        self._h = _vp()
+        mode = CLASSIFIERS[classifier] if isinstance(classifier, str) else int(classifier)
+        _check(lib().hcspmm_graph_create(rowptr_cpu.contiguous().data_ptr(), colidx_cpu.contiguous().data_ptr(),
+                                         self.n_rows, self.nnz, self.x_rows, mode, ctypes.byref(self._h)),
+               "hcspmm_graph_create")
+
+    def spmm(self, x_cpu: torch.Tensor, out_cpu: torch.Tensor | None = None, precision="tf32"):
+        assert not x_cpu.is_cuda and x_cpu.is_contiguous() and x_cpu.shape[0] == self.x_rows
+        d = x_cpu.shape[1]
+        if out_cpu is None:
+            out_cpu = torch.empty((self.n_rows, d), dtype=torch.float32)
+        prec = PRECISIONS[precision] if isinstance(precision, str) else int(precision)
+        _check(lib().hcspmm_graph_spmm_host(self._h, x_cpu.data_ptr(), d, prec, out_cpu.data_ptr()),
+               "hcspmm_graph_spmm_host")
+        return out_cpu
+
+    def preprocess_arrays(self):
+        w = num_windows(self.n_rows)
+        bp, ht = torch.zeros(w, dtype=torch.int32), torch.zeros(w, dtype=torch.int32)
+        etc, etr = torch.zeros(self.nnz, dtype=torch.int32), torch.zeros(self.nnz, dtype=torch.int32)
+        _check(lib().hcspmm_graph_get_preprocess(self._h, bp.data_ptr(), etc.data_ptr(), etr.data_ptr(),
+                                                 ht.data_ptr()), "hcspmm_graph_get_preprocess")
+        return bp, etc, etr, ht
+
+    def close(self):
+        if self._h:
+            lib().hcspmm_graph_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,138 @@
+/*
+ * hcspmm.h -- C ABI of the B200-native HC-SpMM hot path (libhcspmm.so).
+ *
+ * Drop-in boundary for the reference's operator layer: every entry point below is
+ * what a binding of the reference's `HCSPMM` extension would call in place of the
+ * C++ launchers in /root/reference/hybrid_kernel/hybrid_all_kernel.cu.  Plain
+ * pointers and sizes only -- no torch types.  All `d_*` pointers are DEVICE
+ * pointers on the current CUDA device; `stream` is a cudaStream_t passed as
+ * void* (NULL = legacy default stream, which is what the reference launches on,
+ * hybrid_all_kernel.cu:438).
+ *
+ * Conventions
+ *   - A is a binary CSR adjacency (no values array, like the reference):
+ *     rowptr int32[n_rows+1], colidx int32[nnz] (dataset.py:93-103).
+ *   - The operator is rectangular: n_rows output rows, x_rows rows of X; a column
+ *     id outside [0, x_rows) contributes 0 (row-partitioned multi-GPU shards keep
+ *     GLOBAL column ids).
+ *   - Row windows are 16 rows (BLK_H), condensed column blocks are 8 wide
+ *     (BLK_W): hybrid_kernel/config.h:4-5.
+ *   - Return value: 0 on success; a positive value is a cudaError_t; a negative
+ *     value is an argument error (HCSPMM_E_*).  hcspmm_last_error() returns a
+ *     thread-local description of the last failure.
+ *   - No CPU fallback exists.  Without a usable CUDA device every compute entry
+ *     point fails with a cudaError_t.
+ */
+#ifndef HCSPMM_H_
+#define HCSPMM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HCSPMM_BLK_H 16
+#define HCSPMM_BLK_W 8
+
+#define HCSPMM_E_INVALID  (-1) /* bad size / null pointer            */
+#define HCSPMM_E_ALIGN    (-2) /* pointer or leading dim misaligned  */
+#define HCSPMM_E_WORKSPACE (-3) /* workspace too small               */
+#define HCSPMM_E_UNSUPPORTED (-4)
+
+/* Core selector (hybrid_type) variants.  0/1 are bit-exact restatements of the
+ * reference, hybrid_all_kernel.cu:262 (shipped) and :261 (intended, commented
+ * out in the reference).  2 is the B200 re-fit.                    */
+#define HCSPMM_CLASSIFIER_SHIPPED   0
+#define HCSPMM_CLASSIFIER_INTENDED  1
+#define HCSPMM_CLASSIFIER_B200      2
+#define HCSPMM_CLASSIFIER_ALL_CUDA  3
+#define HCSPMM_CLASSIFIER_ALL_TC    4
+
+/* Arithmetic of windows labelled "tensor core" (hybrid_type != 0).  CUDA-core
+ * windows are always an exact FP32 sum, as in the reference (:982-990).
+ *   TF32   : X rounded cvt.rna to TF32, FP32 accumulate -- the reference (:1102-1111)
+ *   TF32X2 : X split hi+lo into two TF32 MMAs (FP32-accurate result on tensor cores)
+ *   FP32   : ignore labels, every window on the CUDA-core path                      */
+#define HCSPMM_PRECISION_TF32    0
+#define HCSPMM_PRECISION_TF32X2  1
+#define HCSPMM_PRECISION_FP32    2
+
+int hcspmm_version(void);
+const char *hcspmm_last_error(void);
+
+/* Runtime tuning knobs (process-wide; for experiments and tests).
+ *   "long_row"   rows with >= this many non-zeros are split over all warps of a CTA
+ *   "slab"       feature-slab width in floats (0 = whole row); slabs are scheduled
+ *                slab-major so that one slab of X stays L2-resident
+ * Returns the previous value, or -1 for an unknown key.                          */
+int hcspmm_set_tuning(const char *key, int value);
+
+/* ---- A1-A5: preprocessing -------------------------------------------------------
+ * Replaces preprocess(), hybrid_all_kernel.cu:339-408 (pybind: hybrid_all.cpp:501):
+ * fill_edgeToRow (:314-326), fill_segment + thrust::sort (:289-301, :386-399) and
+ * generate_edgetocolumn (:242-269), as one window-parallel pass (no global sort).
+ * Outputs are bit-exact with the reference for every non-empty window; empty
+ * windows are defined as 0 (the reference leaves them uninitialised, :252-253,
+ * :356-366).  d_workspace: hcspmm_preprocess_workspace_bytes() bytes of scratch.   */
+size_t hcspmm_preprocess_workspace_bytes(int32_t n_rows, int64_t nnz);
+int hcspmm_preprocess(const int32_t *d_colidx, const int32_t *d_rowptr, int32_t n_rows,
+                      int64_t nnz, int32_t n_windows, int classifier,
+                      int32_t *d_block_partition, int32_t *d_edge_to_column,
+                      int32_t *d_edge_to_row, int32_t *d_hybrid_type, void *d_workspace,
+                      size_t workspace_bytes, void *stream);
+
+/* ---- A6/A7: Y = A * X ------------------------------------------------------------
+ * Replaces spmm_forward_plus / _more / _fixed32 / _fixed64 and their kernels
+ * (hybrid_all_kernel.cu:410-595, 919-1637; pybind hybrid_all.cpp:194-308) for ANY
+ * dim (the reference needs dim == 32 / 64 / <= 48 depending on the entry point).
+ * One launch; each 16-row window takes the CUDA-core or the tensor-core path by
+ * d_hybrid_type[w].  d_hybrid_type may be NULL (all CUDA-core).  accumulate != 0
+ * computes Y += A*X (used by the shard-pipelined multi-GPU path).
+ * Fast paths need d_x/d_y 16-byte aligned and ldx/ldy/dim multiples of 4; anything
+ * else takes a scalar kernel.                                                       */
+int hcspmm_spmm(const float *d_x, int64_t ldx, int32_t x_rows, const int32_t *d_rowptr,
+                const int32_t *d_colidx, const int32_t *d_block_partition,
+                const int32_t *d_edge_to_column, const int32_t *d_edge_to_row,
+                const int32_t *d_hybrid_type, int32_t n_rows, int64_t nnz, int32_t dim,
+                int precision, int accumulate, float *d_y, int64_t ldy, void *stream);
+
+/* ---- A8: fused Aggregation + Update ----------------------------------------------
+ * Replaces spmm_forward_plus_fixed32_fused / _final_fused / _GIN_final_fused (and
+ * the _64 variants), hybrid_all_kernel.cu:596-863, 1639-2770 (pybind
+ * hybrid_all.cpp:310-498) for ANY dim / hidden:  Z = A*X  (written to d_z) and
+ * out = Z*W with W row-major [dim, hidden] (leading dim ldw), both operands of the
+ * second product rounded to TF32, FP32 accumulate (:1809-1837).                     */
+int hcspmm_spmm_gemm(const float *d_x, int64_t ldx, int32_t x_rows, const int32_t *d_rowptr,
+                     const int32_t *d_colidx, const int32_t *d_block_partition,
+                     const int32_t *d_edge_to_column, const int32_t *d_edge_to_row,
+                     const int32_t *d_hybrid_type, int32_t n_rows, int64_t nnz, int32_t dim,
+                     int precision, const float *d_w, int64_t ldw, int32_t hidden,
+                     float *d_out, int64_t ldo, float *d_z, int64_t ldz, void *stream);
+
+/* out[m, n] = a[m, k] * b[k, n], row-major FP32 in/out, TF32 tensor-core product
+ * (the Update GEMM on its own).                                                      */
+int hcspmm_gemm_tf32(const float *d_a, int64_t lda, const float *d_b, int64_t ldb,
+                     int32_t m, int32_t k, int32_t n, float *d_out, int64_t ldo,
+                     void *stream);
+
+/* ---- host-buffer convenience (what a non-torch caller binds) ----------------------
+ * A graph handle owns device copies of the CSR and of the preprocessing products.
+ * hcspmm_graph_spmm_host copies X from (ideally pinned) host memory, runs the
+ * kernel, and copies Y back: host -> device -> host inside the call.                 */
+typedef struct hcspmm_graph hcspmm_graph_t;
+int hcspmm_graph_create(const int32_t *h_rowptr, const int32_t *h_colidx, int32_t n_rows,
+                        int64_t nnz, int32_t x_rows, int classifier, hcspmm_graph_t **out);
+int hcspmm_graph_spmm_host(hcspmm_graph_t *g, const float *h_x, int32_t dim, int precision,
+                           float *h_y);
+/* copies the four preprocessing arrays to host buffers (any of them may be NULL)      */
+int hcspmm_graph_get_preprocess(hcspmm_graph_t *g, int32_t *h_block_partition,
+                                int32_t *h_edge_to_column, int32_t *h_edge_to_row,
+                                int32_t *h_hybrid_type);
+void hcspmm_graph_destroy(hcspmm_graph_t *g);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HCSPMM_H_ */

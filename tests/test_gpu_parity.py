@@ -1,0 +1,239 @@
+"""GPU parity tests (B200): the CUDA path, called through the C ABI (hcspmm.capi -> libhcspmm.so),
+against the CPU oracle on the same seeded inputs.
+
+Bars: integer / index outputs bit-exact; FP32 (CUDA-core) windows <= 1e-5 normwise; TF32
+(tensor-core) windows <= 1e-3 normwise against the FP32 result (north star), BF16 n/a here."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from helpers import rel_fro, small_graphs, torch_sparse_ref
+
+pytestmark = pytest.mark.gpu
+
+GRAPHS = small_graphs()
+TOL_FP32 = 1e-5
+TOL_TF32 = 1e-3
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from hcspmm import capi as c
+    c.lib()
+    return c
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def xmat(rows, dim, seed=0):
+    return np.random.default_rng(seed).standard_normal((rows, dim)).astype(np.float32)
+
+
+def x_rows_for(rp, ci):
+    n = rp.size - 1
+    return max(n, int(ci.max()) + 1 if ci.size else n)
+
+
+# ---- A1-A5 preprocessing: bit-exact ---------------------------------------------------------
+@pytest.mark.parametrize("mode", ["shipped", "intended"])
+@pytest.mark.parametrize("name", sorted(GRAPHS))
+def test_preprocess_bit_exact(capi, name, mode):
+    rp, ci = GRAPHS[name]
+    want = oracle.preprocess(ci, rp, capi.CLASSIFIERS[mode])
+    got = capi.preprocess(dev(ci), dev(rp), mode)
+    for g, w, what in zip(got, want, ("blockPartition", "edgeToColumn", "edgeToRow", "hybrid_type")):
+        assert np.array_equal(g.cpu().numpy(), w), f"{what} differs on {name}/{mode}"
+
+
+def test_preprocess_forced_modes(capi):
+    rp, ci = GRAPHS["holes_777"]
+    nonempty = np.array([rp[min(16 * w + 16, rp.size - 1)] > rp[16 * w] for w in range(oracle.num_windows(rp.size - 1))])
+    ht = capi.preprocess(dev(ci), dev(rp), "all_tc")[3].cpu().numpy()
+    assert np.array_equal(ht != 0, nonempty)        # empty windows stay 0
+    assert not capi.preprocess(dev(ci), dev(rp), "all_cuda")[3].any()
+
+
+def test_preprocess_rejects_bad_window_count(capi):
+    rp, ci = GRAPHS["ring3_256"]
+    d_ci, d_rp = dev(ci), dev(rp)
+    buf = torch.zeros(1024, dtype=torch.int32, device="cuda")
+    rc = capi.lib().hcspmm_preprocess(d_ci.data_ptr(), d_rp.data_ptr(), 256, ci.size, 15, 0, buf.data_ptr(),
+                                      buf.data_ptr(), buf.data_ptr(), buf.data_ptr(), buf.data_ptr(), 4096, None)
+    assert rc == -1 and b"n_windows" in capi.lib().hcspmm_last_error()
+
+
+# ---- A6/A7 SpMM, CUDA-core path ----------------------------------------------------------------
+DIMS = [1, 3, 22, 32, 47, 64, 96, 100, 128, 200, 256, 512, 640]
+
+
+@pytest.mark.parametrize("dim", DIMS)
+@pytest.mark.parametrize("name", ["ring3_256", "rmat_1000", "holes_777", "empty_48", "single_row", "sbm_1024"])
+def test_spmm_fp32(capi, name, dim):
+    rp, ci = GRAPHS[name]
+    x = xmat(x_rows_for(rp, ci), dim, seed=dim)
+    want = oracle.spmm(rp, ci, x, precision=1)
+    got = capi.spmm(dev(x), dev(rp), dev(ci), precision="fp32").cpu().numpy()
+    assert got.shape == want.shape
+    assert rel_fro(got, want) <= TOL_FP32
+    if ci.size:
+        assert rel_fro(got, torch_sparse_ref(rp, ci, x)) <= TOL_FP32
+
+
+@pytest.mark.parametrize("long_row", [32, 100, 1024])
+@pytest.mark.parametrize("dim", [32, 64, 128, 256, 512])
+def test_spmm_long_rows_split_over_warps(capi, dim, long_row):
+    rp, ci = GRAPHS["rmat_hub_4096"]
+    x = xmat(4096, dim, seed=3)
+    want = oracle.spmm(rp, ci, x, precision=1)
+    old = capi.set_tuning("long_row", long_row)
+    try:
+        got = capi.spmm(dev(x), dev(rp), dev(ci), precision="fp32").cpu().numpy()
+    finally:
+        capi.set_tuning("long_row", old)
+    assert rel_fro(got, want) <= TOL_FP32
+
+
+@pytest.mark.parametrize("slab", [32, 64, 96, 128])
+def test_spmm_feature_slabs(capi, slab):
+    rp, ci = GRAPHS["rmat_1000"]
+    ht = np.zeros(oracle.num_windows(1000), np.int32)
+    ht[::2] = 1
+    bp, etc, etr, _ = oracle.preprocess(ci, rp, 0)
+    for dim in (256, 200, 520):
+        x = xmat(1000, dim, seed=slab)
+        want = oracle.spmm(rp, ci, x, hybrid_type=ht, precision=0)
+        old = capi.set_tuning("slab", slab)
+        try:
+            got = capi.spmm(dev(x), dev(rp), dev(ci), dev(bp), dev(etc), dev(etr), dev(ht)).cpu().numpy()
+        finally:
+            capi.set_tuning("slab", old)
+        assert rel_fro(got, want) <= 2e-5
+
+
+def test_spmm_strided_and_unaligned(capi):
+    rp, ci = GRAPHS["rmat_1000"]
+    big = dev(xmat(1000, 80, seed=9))
+    want_full = oracle.spmm(rp, ci, big.cpu().numpy(), precision=1)
+    # row-strided view, 16-byte aligned start: vector kernel with ldx != dim
+    v = big[:, 16:48]
+    got = capi.spmm(v, dev(rp), dev(ci), precision="fp32").cpu().numpy()
+    assert rel_fro(got, want_full[:, 16:48]) <= TOL_FP32
+    # 4-byte aligned start: scalar kernel
+    v = big[:, 3:35]
+    got = capi.spmm(v, dev(rp), dev(ci), precision="fp32").cpu().numpy()
+    assert rel_fro(got, want_full[:, 3:35]) <= TOL_FP32
+
+
+def test_spmm_accumulate(capi):
+    rp, ci = GRAPHS["rmat_1000"]
+    bp, etc, etr, _ = oracle.preprocess(ci, rp, 0)
+    ht = np.zeros(oracle.num_windows(1000), np.int32)
+    ht[1::3] = 1
+    for dim in (32, 100, 47):
+        x = xmat(1000, dim, seed=4)
+        y0 = xmat(1000, dim, seed=5)
+        want = oracle.spmm(rp, ci, x, hybrid_type=ht, precision=0, y_init=y0)
+        out = dev(y0)
+        capi.spmm(dev(x), dev(rp), dev(ci), dev(bp), dev(etc), dev(etr), dev(ht), out=out, accumulate=True)
+        assert rel_fro(out.cpu().numpy(), want) <= 2e-5
+
+
+def test_spmm_rectangular_shard(capi):
+    """Row-partitioned shard: 72 output rows, 100000 rows of X, global column ids."""
+    rp, ci = GRAPHS["rect_72x100000"]
+    for classifier in ("all_cuda", "all_tc"):
+        bp, etc, etr, ht = capi.preprocess(dev(ci), dev(rp), classifier)
+        x = xmat(100000, 64, seed=6)
+        got = capi.spmm(dev(x), dev(rp), dev(ci), bp, etc, etr, ht).cpu().numpy()
+        assert got.shape == (72, 64)
+        want = oracle.spmm(rp, ci, x, precision=1)
+        assert rel_fro(got, want) <= (TOL_FP32 if classifier == "all_cuda" else TOL_TF32)
+    # column ids beyond x_rows contribute zero (reference TC path does the same, :1093)
+    xs = x[:50000]
+    keep = ci < 50000
+    deg = np.array([keep[rp[r]:rp[r + 1]].sum() for r in range(rp.size - 1)])
+    rp_f = np.zeros_like(rp)
+    rp_f[1:] = np.cumsum(deg)
+    want = torch_sparse_ref(rp_f, ci[keep], xs)
+    assert rel_fro(oracle.spmm(rp, ci, xs, precision=1), want) <= 1e-6
+    got = capi.spmm(dev(xs), dev(rp), dev(ci), precision="fp32").cpu().numpy()
+    assert rel_fro(got, want) <= TOL_FP32
+
+
+# ---- tensor-core path -----------------------------------------------------------------------
+@pytest.mark.parametrize("dim", [8, 16, 32, 48, 64, 128, 256, 512])
+@pytest.mark.parametrize("name", ["band2_320", "sbm_1024", "rmat_1000", "holes_777", "dense_2048"])
+def test_spmm_tensor_core_windows(capi, name, dim):
+    rp, ci = GRAPHS[name]
+    bp, etc, etr, ht = capi.preprocess(dev(ci), dev(rp), "all_tc")
+    x = xmat(x_rows_for(rp, ci), dim, seed=dim + 1)
+    fp32 = oracle.spmm(rp, ci, x, precision=1)
+    tf32 = oracle.spmm(rp, ci, x, hybrid_type=ht.cpu().numpy(), precision=0)
+    got = capi.spmm(dev(x), dev(rp), dev(ci), bp, etc, etr, ht, precision="tf32").cpu().numpy()
+    assert rel_fro(got, fp32) <= TOL_TF32            # the north star's bar
+    assert rel_fro(got, tf32) <= 2e-5                # same rounding as the oracle's TF32 restatement
+    got2 = capi.spmm(dev(x), dev(rp), dev(ci), bp, etc, etr, ht, precision="tf32x2").cpu().numpy()
+    assert rel_fro(got2, fp32) <= TOL_FP32           # split-TF32 recovers FP32 accuracy
+
+
+def test_spmm_mixed_labels_intended_selector(capi):
+    """A graph whose windows straddle the intended selector's boundary: both paths in one launch."""
+    rng = np.random.default_rng(8)
+    n = 640
+    rows = []
+    for r in range(n):
+        w = r // 16
+        span = 12 + (w % 5) * 9           # 12..48 distinct candidate columns per window
+        k = int(rng.integers(1, min(span, 14)))
+        rows.append(np.sort(rng.choice(span, size=k, replace=False) + (w * 7) % (n - 64)).astype(np.int32))
+    rp = np.zeros(n + 1, np.int32)
+    rp[1:] = np.cumsum([len(r) for r in rows])
+    ci = np.concatenate(rows)
+    want_pre = oracle.preprocess(ci, rp, oracle.MODE_INTENDED)
+    got_pre = capi.preprocess(dev(ci), dev(rp), "intended")
+    for g, w in zip(got_pre, want_pre):
+        assert np.array_equal(g.cpu().numpy(), w)
+    ht = want_pre[3]
+    assert 0 < ht.sum() < ht.size, "fixture must mix CUDA-core and tensor-core windows"
+    x = xmat(n, 32, seed=2)
+    got = capi.spmm(dev(x), dev(rp), dev(ci), *got_pre).cpu().numpy()
+    want = oracle.spmm(rp, ci, x, hybrid_type=ht, precision=0)
+    assert rel_fro(got, want) <= 2e-5
+    assert rel_fro(got, oracle.spmm(rp, ci, x, precision=1)) <= TOL_TF32
+
+
+# ---- A8 fused aggregation + update ----------------------------------------------------------
+@pytest.mark.parametrize("dim,hidden", [(32, 32), (22, 32), (100, 47), (128, 128), (256, 64), (64, 256), (5, 3)])
+def test_spmm_gemm(capi, dim, hidden):
+    rp, ci = GRAPHS["rmat_1000"]
+    pre = capi.preprocess(dev(ci), dev(rp), "shipped")
+    x = xmat(1000, dim, seed=7)
+    w = xmat(dim, hidden, seed=8)
+    out, z = capi.spmm_gemm(dev(x), dev(rp), dev(ci), *pre, dev(w))
+    z_want = oracle.spmm(rp, ci, x, precision=1)
+    assert rel_fro(z.cpu().numpy(), z_want) <= TOL_FP32
+    assert rel_fro(out.cpu().numpy(), oracle.gemm(z_want, w, tf32=True)) <= 1e-4
+    assert rel_fro(out.cpu().numpy(), z_want.astype(np.float64) @ w.astype(np.float64)) <= 2e-3
+
+
+@pytest.mark.parametrize("m,k,n", [(1, 1, 1), (127, 33, 65), (300, 16, 64), (1000, 128, 128), (513, 100, 47)])
+def test_gemm_tf32(capi, m, k, n):
+    a, b = xmat(m, k, 1), xmat(k, n, 2)
+    got = capi.gemm_tf32(dev(a), dev(b)).cpu().numpy()
+    assert rel_fro(got, oracle.gemm(a, b, tf32=True)) <= 1e-4
+
+
+# ---- host-buffer path -------------------------------------------------------------------------
+def test_host_graph_roundtrip(capi):
+    rp, ci = GRAPHS["rmat_1000"]
+    g = capi.HostGraph(torch.from_numpy(rp), torch.from_numpy(ci), classifier="intended")
+    want_pre = oracle.preprocess(ci, rp, oracle.MODE_INTENDED)
+    for a, b in zip(g.preprocess_arrays(), want_pre):
+        assert np.array_equal(a.numpy(), b)
+    x = torch.from_numpy(xmat(1000, 96, seed=3)).pin_memory()
+    y = g.spmm(x)
+    assert rel_fro(y.numpy(), oracle.spmm(rp, ci, x.numpy(), hybrid_type=want_pre[3], precision=0)) <= 2e-5
+    g.close()
