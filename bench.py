@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hybrid SpMM hot path (BASELINE.json configs[1]).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  (N > 1: launched by torchrun, one rank per GPU)
+
+A "step" is one pass of the hot path over one batch of synthetic input: Y = A * X on the
+Reddit-shape power-law graph (232 965 vertices, ~114.6 M stored entries, dim 256, FP32).
+At N > 1 the adjacency is row-window partitioned (nnz-balanced) and every step first
+all-gathers the row-sharded X over NCCL, then runs the local SpMM -- the per-layer exchange of
+a row-partitioned GCN (strong scaling: the total work is fixed).
+
+Prints ONE JSON line (rank 0).  Keys follow the driver's contract; see DESIGN.md "Measurement".
+Nothing here reads /root/reference.  The CPU oracle / torch.sparse.mm is executed only in the
+`cpu_baseline` leg and under `--impl reference`.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "hc-spmm_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--shape", default="reddit", choices=["reddit", "products", "proteins"])
+    ap.add_argument("--dim", type=int, default=0, help="feature width (0 = the shape's own)")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink N and nnz (smoke runs only)")
+    ap.add_argument("--classifier", default="shipped",
+                    help="core selector: shipped (reference, all CUDA-core) | intended | b200 | all_tc")
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "tf32x2", "fp32"])
+    ap.add_argument("--slab", type=int, default=-1, help="feature-slab width (-1 = library default)")
+    ap.add_argument("--long-row", type=int, default=-1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline budget per timed run")
+    return ap.parse_args()
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json, copy bandwidth)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [l.split(", ") for t, l in self.lines if t0 - 0.05 <= t <= t1 + 0.15] or \
+               [l.split(", ") for _, l in self.lines]
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_spmm_baseline(rp_cpu, ci_cpu, x_cpu, seconds: float):
+    """torch.sparse.mm (CSR, FP32) on the host cores -- the paper's 'PyTorch CPU SpMM' baseline and the
+    north star's stated reference -- on a BOUNDED sample: the first n_s rows of the same graph against
+    the full X, n_s sized so one run takes about `seconds`."""
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    n, dim = rp_cpu.numel() - 1, x_cpu.shape[1]
+
+    def run(n_s):
+        e = int(rp_cpu[n_s])
+        a = torch.sparse_csr_tensor(rp_cpu[: n_s + 1].to(torch.int64), ci_cpu[:e].to(torch.int64),
+                                    torch.ones(e, dtype=torch.float32), size=(n_s, x_cpu.shape[0]))
+        t = time.perf_counter()
+        y = torch.sparse.mm(a, x_cpu)
+        dt = time.perf_counter() - t
+        return dt, e, y
+
+    probe_rows = max(16, n // 64)
+    run(probe_rows)                                  # warm-up (thread pool, page-in)
+    dt, e, _ = run(probe_rows)
+    rate = max(e, 1) / max(dt, 1e-6)                 # entries / s
+    want_e = min(int(rp_cpu[-1]), int(rate * seconds))
+    n_s = int(torch.searchsorted(rp_cpu.to(torch.int64), torch.tensor(want_e)).clamp(16, n))
+    times = []
+    for _ in range(2):
+        dt, e, _ = run(n_s)
+        times.append(dt)
+    dt = statistics.median(times)
+    return {"value": 2.0 * e * dim / dt / 1e9, "unit": "GFLOP/s", "cores": threads, "kind": "port",
+            "sample": f"torch.sparse.mm CSR FP32 on CPU, rows [0,{n_s}) of {n} ({e} of {int(rp_cpu[-1])} "
+                      f"stored entries) x full X[{x_cpu.shape[0]},{dim}], median of 2 runs, {dt:.2f} s each",
+            "seconds": dt, "entries": e, "rows": n_s}
+
+
+def main():
+    args = parse()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    from hcspmm import graphs, partition
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        shape = graphs.SHAPES[args.shape]
+        dim = args.dim or shape["dim"]
+        dev = "cuda" if torch.cuda.is_available() else "cpu"
+        rp, ci, info = graphs.named(args.shape, device=dev, scale=args.scale)
+        rp_c, ci_c = rp.cpu(), ci.cpu()
+        x = torch.randn(info["n"], dim, generator=torch.Generator().manual_seed(0))
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        budget = min(args.cpu_seconds, 120.0 / max(1, args.steps + args.warmup))
+        base = cpu_spmm_baseline(rp_c, ci_c, x, budget)
+        n_s, e = base["rows"], base["entries"]
+        a = torch.sparse_csr_tensor(rp_c[: n_s + 1].to(torch.int64), ci_c[:e].to(torch.int64),
+                                    torch.ones(e, dtype=torch.float32), size=(n_s, info["n"]))
+        for _ in range(args.warmup):
+            torch.sparse.mm(a, x)
+        t = time.perf_counter()
+        for _ in range(args.steps):
+            torch.sparse.mm(a, x)
+        dt = (time.perf_counter() - t) / max(1, args.steps)
+        val = 2.0 * e * dim / dt / 1e9
+        line = {"impl": "reference", "metric": "spmm_gflops", "value": val, "unit": "GFLOP/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"{args.shape}-shape SpMM N={info['n']} nnz={info['nnz']} dim={dim}",
+                           "note": "the reference's SpMM is a CUDA kernel that overflows its shared-memory "
+                                   "tables above 62 edges / 16-row window (hybrid_all_kernel.cu:26,964-967), so it "
+                                   "cannot run this shape; this arm times the north star's CPU reference, "
+                                   "torch.sparse.mm, on all host threads"},
+                "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": threads, "kind": "port",
+                                 "sample": base["sample"]},
+                "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm (GPU)
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    import HCSPMM
+    from hcspmm import capi
+
+    shape = graphs.SHAPES[args.shape]
+    dim = args.dim or shape["dim"]
+    t_gen = time.perf_counter()
+    rp, ci, info = graphs.named(args.shape, device=dev, scale=args.scale)
+    torch.cuda.synchronize()
+    t_gen = time.perf_counter() - t_gen
+    n, nnz = info["n"], info["nnz"]
+
+    cuts = partition.window_cuts(rp, world)
+    r0, r1 = cuts[rank], cuts[rank + 1]
+    rp_l, ci_l = partition.local_shard(rp, ci, r0, r1)
+    n_l, nnz_l = r1 - r0, ci_l.numel()
+
+    if args.slab >= 0:
+        HCSPMM.set_tuning("slab", args.slab)
+    if args.long_row >= 0:
+        HCSPMM.set_tuning("long_row", args.long_row)
+    HCSPMM.set_classifier(args.classifier)
+    HCSPMM.set_precision(args.precision)
+
+    # preprocessing (reported separately, like the paper: "x one SpMM")
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pre = HCSPMM.preprocess(ci_l, rp_l, n_l, nnz_l, (n_l + 15) // 16)
+    ev0.record()
+    pre = HCSPMM.preprocess(ci_l, rp_l, n_l, nnz_l, (n_l + 15) // 16)
+    ev1.record()
+    torch.cuda.synchronize()
+    prep_ms = ev0.elapsed_time(ev1)
+    tc_windows = int((pre[3] != 0).sum())
+
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234)
+    x_full = torch.randn(n, dim, device=dev, generator=g)       # same on every rank (same seed)
+    x_loc = x_full[r0:r1].contiguous()
+    if world > 1:
+        # all_gather_into_tensor needs equal shards: pad every shard to the largest
+        max_rows = max(cuts[i + 1] - cuts[i] for i in range(world))
+        x_pad = torch.zeros(max_rows, dim, device=dev)
+        x_pad[:n_l] = x_loc
+        gathered = torch.empty(world * max_rows, dim, device=dev)
+        # column ids must address the padded layout: shard s starts at s * max_rows
+        bounds = torch.tensor(cuts, device=dev, dtype=torch.int32)
+        owner = torch.bucketize(ci_l, bounds[1:-1], right=True).to(torch.int32)
+        ci_run = (ci_l - bounds[owner.long()] + owner * max_rows).to(torch.int32).contiguous()
+        x_rows_run = world * max_rows
+    else:
+        ci_run, x_rows_run = ci_l, n
+
+    def step():
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, x_pad)
+            return HCSPMM.forward(gathered, rp_l, ci_run, *pre)[0]
+        return HCSPMM.forward(x_full, rp_l, ci_run, *pre)[0]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        y = step()
+    barrier()
+
+    # timed region: exactly K steps, CUDA events on the launching (current) stream
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    kern_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t0 = time.time()
+    ev0.record()
+    for i in range(args.steps):
+        kern_ev[i][0].record()
+        y = step()
+        kern_ev[i][1].record()
+    ev1.record()
+    barrier()
+    t1 = time.time()
+    total_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    step_ms = [a.elapsed_time(b) for a, b in kern_ev]
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t)
+    ms_per_step = total_ms / args.steps
+    flops = 2.0 * nnz * dim
+    value = flops / (ms_per_step * 1e-3) / 1e9
+
+    # quick full-size sanity inside the bench (not timed): X = 1 gives the row degrees exactly
+    ones = torch.ones(x_rows_run, 8, device=dev)
+    deg = HCSPMM.forward(ones, rp_l, ci_run, *pre)[0][:, 0]
+    want = (rp_l[1:] - rp_l[:-1]).float()
+    assert torch.equal(deg, want) or float((deg - want).abs().max()) <= 1e-3 * float(want.max()), \
+        "degree check failed: kernel output is wrong"
+
+    # roofline of the dominant kernel (the one hybrid SpMM launch per step); single-GPU figures
+    peak, peak_src = measured_peak_gbs()
+    bytes_alg = nnz_l * (4 + 4 * dim) + n_l * (4 * dim + 4)
+    bytes_min = 4 * nnz_l + 4 * (n_l + 1) + 4 * (n + n_l) * dim
+    kern_ms = statistics.mean(step_ms) if world == 1 else None
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj.get(f"{args.shape}_dim{dim}_{args.classifier}")
+    except Exception:
+        pass
+    roofline = None
+    if kern_ms:
+        ach = bytes_alg / (kern_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": traffic, "peak_source": peak_src, "kernel": "spmm_hybrid_kernel",
+                    "kernel_ms": kern_ms, "algorithmic_bytes": bytes_alg,
+                    "compulsory_bytes": bytes_min, "compulsory_frac": bytes_min / (kern_ms * 1e-3) / 1e9 / peak,
+                    "frac_of_nominal_8TBs": ach / 8000.0}
+
+    # e2e: the reference-facing module with HOST buffers, H2D of X and D2H of Y inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        rows_in = n if world == 1 else n_l
+        xh = torch.empty(rows_in, dim, pin_memory=True)
+        xh.copy_(x_full if world == 1 else x_loc)
+        yh = torch.empty(n_l, dim, pin_memory=True)
+
+        def e2e_step():
+            xd = xh.to(dev, non_blocking=True)
+            if world > 1:
+                x_pad[:n_l].copy_(xd)
+                dist.all_gather_into_tensor(gathered, x_pad)
+                out = HCSPMM.forward(gathered, rp_l, ci_run, *pre)[0]
+            else:
+                out = HCSPMM.forward(xd, rp_l, ci_run, *pre)[0]
+            yh.copy_(out, non_blocking=True)
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        k2 = max(3, min(args.steps, 10))
+        ev0.record()
+        for _ in range(k2):
+            e2e_step()
+        ev1.record()
+        barrier()
+        e_ms = ev0.elapsed_time(ev1) / k2
+        if world > 1:
+            t = torch.tensor([e_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e_ms = float(t)
+        e2e = {"value": flops / (e_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": e_ms,
+               "h2d_bytes_per_step": rows_in * dim * 4 * world if world > 1 else rows_in * dim * 4,
+               "d2h_bytes_per_step": n * dim * 4}
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_base = cpu_spmm_baseline(rp.cpu(), ci.cpu(), x_full.cpu(), args.cpu_seconds)
+        for k in ("seconds", "entries", "rows"):
+            cpu_base.pop(k, None)
+
+    if rank == 0:
+        line = {"metric": "spmm_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"{args.shape}-shape power-law graph, single-kernel SpMM Y=A*X "
+                                       f"(BASELINE.json configs[1])" if args.shape == "reddit" else f"{args.shape}-shape SpMM",
+                           "nodes": n, "stored_entries": nnz, "dim": dim, "classifier": args.classifier,
+                           "precision_tc_windows": args.precision, "tc_windows": tc_windows,
+                           "windows": (n_l + 15) // 16, "partition": f"row windows, nnz-balanced, {world} shard(s)",
+                           "exchange": "NCCL all_gather_into_tensor of row-sharded X per step" if world > 1 else "none",
+                           "l2": "inputs larger than L2 (X %.0f MB + CSR %.0f MB vs 126 MB), no flush" %
+                                 (n * dim * 4 / 1e6, nnz * 4 / 1e6),
+                           "preprocess_ms": prep_ms, "graph_gen_s": t_gen,
+                           "generator": "R-MAT(0.57,0.19,0.19,0.05) folded mod N, symmetrised, de-duplicated, "
+                                        "ids permuted, seed %d" % shape["seed"]},
+                "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e, "clocks": clocks,
+                "gpu_launches": args.steps,
+                "step_ms": {"min": min(step_ms), "median": statistics.median(step_ms), "max": max(step_ms)}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -54,11 +54,11 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N));
 }
 
+// a += b with two packed FP32 adds (FADD2, new on sm_100): same IEEE result as four FADDs
 __device__ __forceinline__ void add4(float4 &a, const float4 &b) {
-  a.x += b.x;
-  a.y += b.y;
-  a.z += b.z;
-  a.w += b.w;
+  const float2 lo = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+  const float2 hi = __fadd2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w));
+  a = make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 
 }  // namespace hcspmm

@@ -239,7 +239,7 @@ int launch_preprocess(const int32_t *colidx, const int32_t *rowptr, int32_t n_ro
   }
   if (n_windows == 0) return 0;
   if (!colidx && nnz > 0) { set_error("preprocess: null colidx"); return HCSPMM_E_INVALID; }
-  if (!rowptr || !bp || !etc || !etr || !ht || !ws) {
+  if (!rowptr || !bp || !ht || !ws || (nnz > 0 && (!etc || !etr))) {
     set_error("preprocess: null pointer argument");
     return HCSPMM_E_INVALID;
   }

@@ -29,6 +29,9 @@
 
 namespace hcspmm {
 
+#ifndef HCSPMM_MIN_CTAS
+#define HCSPMM_MIN_CTAS 2
+#endif
 constexpr int KC = 16;      // condensed columns staged per pipeline step (two k=8 MMA steps)
 constexpr int UCAP = 1024;  // condensed columns whose (col, mask) are resident at once
 
@@ -53,29 +56,60 @@ __device__ __forceinline__ void gather_accumulate(float4 (&acc)[NV], const float
                                                   long long ldx, int x_rows,
                                                   const int *__restrict__ colidx, int eb, int ee,
                                                   int chunk0, int chunk_stride, int lane, int q,
-                                                  const bool (&active)[NV]) {
-  constexpr int G = 32 / LPE;
-  constexpr int U = NV >= 4 ? 2 : (NV == 2 ? 4 : 8);
-  for (int base = eb + chunk0 * 32; base < ee; base += chunk_stride * 32) {
+                                                  const bool (&active)[NV], bool all_active) {
+  constexpr int G = 32 / LPE;         // edges handled concurrently by one warp
+  constexpr int STEPS = 32 / G;       // gather steps per full 32-edge chunk
+  constexpr int U = NV >= 4 ? 2 : (NV == 2 ? 4 : 8);  // loads kept in flight per lane (x NV)
+  int base = eb + chunk0 * 32;
+  int c_next = (base + lane < ee) ? __ldg(colidx + base + lane) : -1;
+  for (; base < ee; base += chunk_stride * 32) {
     const int n = min(32, ee - base);
-    const int c = (lane < n) ? __ldg(colidx + base + lane) : -1;
-#pragma unroll 1
-    for (int t = 0; t * G < n; t += U) {
+    const int c = c_next;
+    const int nb = base + chunk_stride * 32;
+    c_next = (nb + lane < ee) ? __ldg(colidx + nb + lane) : -1;  // next chunk's ids, early
+    const bool fast = all_active && n == 32 &&
+                      __all_sync(0xffffffffu, (unsigned)c < (unsigned)x_rows);
+    if (fast) {
+      // full chunk, every id valid, every lane active: unpredicated ring of U loads in flight --
+      // slot s % U is consumed and immediately refilled with step s + U
       float4 v[U][NV];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int j = (t + u) * G + q;
-        const int cu = __shfl_sync(0xffffffffu, c, j & 31);
-        const bool ok = (j < n) && ((unsigned)cu < (unsigned)x_rows);
+        const int cu = __shfl_sync(0xffffffffu, c, u * G + q);
         const float *src = xlane + (long long)cu * ldx;
 #pragma unroll
-        for (int i = 0; i < NV; ++i)
-          v[u][i] = (ok && active[i]) ? ldg_f4(src + i * LPE * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < NV; ++i) v[u][i] = ldg_f4(src + i * LPE * 4);
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u)
+      for (int s = 0; s < STEPS; ++s) {
 #pragma unroll
-        for (int i = 0; i < NV; ++i) add4(acc[i], v[u][i]);
+        for (int i = 0; i < NV; ++i) add4(acc[i], v[s % U][i]);
+        if (s + U < STEPS) {
+          const int cu = __shfl_sync(0xffffffffu, c, (s + U) * G + q);
+          const float *src = xlane + (long long)cu * ldx;
+#pragma unroll
+          for (int i = 0; i < NV; ++i) v[s % U][i] = ldg_f4(src + i * LPE * 4);
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int t = 0; t * G < n; t += U) {
+        float4 v[U][NV];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int j = (t + u) * G + q;
+          const int cu = __shfl_sync(0xffffffffu, c, j & 31);
+          const bool ok = (j < n) && ((unsigned)cu < (unsigned)x_rows);
+          const float *src = xlane + (long long)cu * ldx;
+#pragma unroll
+          for (int i = 0; i < NV; ++i)
+            v[u][i] = (ok && active[i]) ? ldg_f4(src + i * LPE * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int i = 0; i < NV; ++i) add4(acc[i], v[u][i]);
+      }
     }
   }
 }
@@ -208,7 +242,7 @@ __device__ __forceinline__ void tc_window(const SpmmParams &p, int w, int e0, in
 // The hybrid kernel.  Slab width S <= LPE * NV * 4 floats; X/Y 16-byte aligned, ldx/ldy % 4 == 0.
 // ---------------------------------------------------------------------------------------
 template <int LPE, int NV>
-__global__ void __launch_bounds__(CTA_THREADS, 3) spmm_hybrid_kernel(const SpmmParams p) {
+__global__ void __launch_bounds__(CTA_THREADS, HCSPMM_MIN_CTAS) spmm_hybrid_kernel(const SpmmParams p) {
   extern __shared__ __align__(16) float smem[];
   __shared__ int rp[BLK_H + 1];
   __shared__ int s_next;
@@ -234,6 +268,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) spmm_hybrid_kernel(const SpmmP
   bool active[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) active[i] = (g + i * LPE) < nvec;
+  const bool all_active = nvec == LPE * NV;
   const float *xlane = p.x + feat0 + g * 4;
   const int rows_here = min(BLK_H, p.n_rows - r0);
 
@@ -248,7 +283,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) spmm_hybrid_kernel(const SpmmP
     float4 acc[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    gather_accumulate<LPE, NV>(acc, xlane, p.ldx, p.x_rows, p.colidx, eb, ee, 0, 1, lane, q, active);
+    gather_accumulate<LPE, NV>(acc, xlane, p.ldx, p.x_rows, p.colidx, eb, ee, 0, 1, lane, q, active, all_active);
     group_reduce<LPE, NV>(acc);
     if (q == 0) {
       float *yrow = p.y + (long long)(r0 + r) * p.ldy + feat0 + g * 4;
@@ -275,7 +310,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) spmm_hybrid_kernel(const SpmmP
 #pragma unroll
     for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     gather_accumulate<LPE, NV>(acc, xlane, p.ldx, p.x_rows, p.colidx, eb, ee, wid, CTA_WARPS, lane, q,
-                               active);
+                               active, all_active);
     group_reduce<LPE, NV>(acc);
     if (q == 0) {
 #pragma unroll

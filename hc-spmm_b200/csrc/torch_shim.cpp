@@ -56,8 +56,8 @@ struct Graph {
 Graph check_graph(const torch::Tensor &input, const torch::Tensor &nodePointer,
                   const torch::Tensor &edgeList, const torch::Tensor &blockPartition,
                   const torch::Tensor &edgeToColumn, const torch::Tensor &edgeToRow,
-                  const torch::Tensor &hybrid_type) {
-  check_f32_2d(input, "input");
+                  const torch::Tensor &hybrid_type, bool strided_input = false) {
+  if (!strided_input) check_f32_2d(input, "input");
   check_i32(nodePointer, "nodePointer", input);
   check_i32(edgeList, "edgeList", input);
   check_i32(blockPartition, "blockPartition", input);
@@ -131,22 +131,26 @@ std::vector<torch::Tensor> spmm_forward(torch::Tensor input, torch::Tensor nodeP
   return {out};
 }
 
-// Y += A * X into a caller-provided tensor (shard-pipelined multi-GPU aggregation)
-torch::Tensor spmm_accumulate(torch::Tensor input, torch::Tensor nodePointer, torch::Tensor edgeList,
-                              torch::Tensor blockPartition, torch::Tensor edgeToColumn,
-                              torch::Tensor edgeToRow, torch::Tensor hybrid_type, torch::Tensor out,
-                              bool accumulate) {
-  Graph g = check_graph(input, nodePointer, edgeList, blockPartition, edgeToColumn, edgeToRow, hybrid_type);
-  check_f32_2d(out, "out");
+// out (+)= A * X with row-strided X / out views (stride(1) == 1): the kernel takes ldx / ldy.  Used by
+// the multi-GPU layer (feature-slab pipelining, shard accumulation).
+torch::Tensor spmm_strided(torch::Tensor input, torch::Tensor nodePointer, torch::Tensor edgeList,
+                           torch::Tensor blockPartition, torch::Tensor edgeToColumn,
+                           torch::Tensor edgeToRow, torch::Tensor hybrid_type, torch::Tensor out,
+                           bool accumulate) {
+  TORCH_CHECK(input.is_cuda() && input.scalar_type() == torch::kFloat32 && input.dim() == 2 &&
+              (input.stride(1) == 1 || input.size(1) == 1), "input must be a 2-D float32 CUDA tensor with unit column stride");
+  TORCH_CHECK(out.is_cuda() && out.scalar_type() == torch::kFloat32 && out.dim() == 2 &&
+              (out.stride(1) == 1 || out.size(1) == 1), "out must be a 2-D float32 CUDA tensor with unit column stride");
   TORCH_CHECK(out.device() == input.device(), "out must be on the input's device");
+  Graph g = check_graph(input, nodePointer, edgeList, blockPartition, edgeToColumn, edgeToRow, hybrid_type, true);
   TORCH_CHECK(out.size(0) == g.n_rows && out.size(1) == input.size(1), "out must be [num_nodes, dim]");
   c10::cuda::CUDAGuard guard(input.device());
   const int64_t dim = input.size(1);
-  check_rc(hcspmm_spmm(input.data_ptr<float>(), dim, (int32_t)input.size(0), g.rowptr, g.colidx, g.bp,
+  check_rc(hcspmm_spmm(input.data_ptr<float>(), input.stride(0), (int32_t)input.size(0), g.rowptr, g.colidx, g.bp,
                        g.etc, g.etr, g.ht, g.n_rows, g.nnz, (int32_t)dim, g_precision,
-                       accumulate ? 1 : 0, out.data_ptr<float>(), dim,
+                       accumulate ? 1 : 0, out.data_ptr<float>(), out.stride(0),
                        at::cuda::getCurrentCUDAStream().stream()),
-           "spmm_accumulate");
+           "spmm_strided");
   return out;
 }
 
@@ -272,7 +276,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("backward_final_fused_64", &spmm_forward_final_fused, "HCSPMM SPMM backward final fused 64 (CUDA)");
   m.def("backward_GIN_final_fused", &spmm_forward_fused, "HCSPMM SPMM backward for GIN final fused (CUDA)");
   // additions (not in the reference)
-  m.def("spmm_accumulate", &spmm_accumulate, "out (+)= A @ input into a caller tensor");
+  m.def("spmm_strided", &spmm_strided, "out (+)= A @ input; input / out may be row-strided views");
+  m.def("spmm_accumulate", &spmm_strided, "alias of spmm_strided");
   m.def("gemm_tf32", &gemm_tf32, "a @ b with TF32 tensor-core product");
   m.def("set_classifier", &set_classifier, "shipped | intended | b200 | all_cuda | all_tc; returns the previous mode");
   m.def("set_precision", &set_precision, "tf32 | tf32x2 | fp32; returns the previous mode");

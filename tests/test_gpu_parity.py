@@ -135,7 +135,8 @@ def test_spmm_accumulate(capi):
     for dim in (32, 100, 47):
         x = xmat(1000, dim, seed=4)
         y0 = xmat(1000, dim, seed=5)
-        want = oracle.spmm(rp, ci, x, hybrid_type=ht, precision=0, y_init=y0)
+        # dim % 8 != 0: tensor-core windows fall back to the exact FP32 path
+        want = oracle.spmm(rp, ci, x, hybrid_type=ht, precision=0 if dim % 8 == 0 else 1, y_init=y0)
         out = dev(y0)
         capi.spmm(dev(x), dev(rp), dev(ci), dev(bp), dev(etc), dev(etr), dev(ht), out=out, accumulate=True)
         assert rel_fro(out.cpu().numpy(), want) <= 2e-5
