@@ -17,7 +17,7 @@ void set_error(const char *fmt, ...) {
 }
 
 Tuning &tuning() {
-  static Tuning t = {1024, 0};
+  static Tuning t = {1024, 0, 1};
   return t;
 }
 
@@ -62,6 +62,7 @@ int hcspmm_set_tuning(const char *key, int value) {
   int *slot = nullptr;
   if (key && !strcmp(key, "long_row")) slot = &tuning().long_row;
   else if (key && !strcmp(key, "slab")) slot = &tuning().slab;
+  else if (key && !strcmp(key, "vec8")) slot = &tuning().vec8;
   if (!slot) return -1;
   int old = *slot;
   *slot = value;

@@ -18,6 +18,7 @@ void set_error(const char *fmt, ...);
 struct Tuning {
   int long_row;  // rows with >= long_row non-zeros are split over all warps of the CTA
   int slab;      // feature-slab width in floats, 0 = no slabbing
+  int vec8;      // use 256-bit gathers when alignment allows (1) or always 128-bit (0)
 };
 Tuning &tuning();
 

@@ -33,6 +33,10 @@ namespace hcspmm {
 #define HCSPMM_MIN_CTAS 2
 #endif
 constexpr int KC = 16;      // condensed columns staged per pipeline step (two k=8 MMA steps)
+#ifndef HCSPMM_TC_STAGES
+#define HCSPMM_TC_STAGES 4
+#endif
+constexpr int NSTAGE = HCSPMM_TC_STAGES;  // cp.async pipeline depth of the tensor-core path
 constexpr int UCAP = 1024;  // condensed columns whose (col, mask) are resident at once
 
 struct SpmmParams {
@@ -48,18 +52,73 @@ struct SpmmParams {
 };
 
 // ---------------------------------------------------------------------------------------
-// CUDA-core gather: accumulate X rows of edges [eb, ee), visiting 32-edge chunks
-// chunk0, chunk0 + chunk_stride, ...
+// Per-lane feature vector: VW = 4 floats (LDG.128) or 8 floats (LDG.256, new on sm_100).
+// The 256-bit form also carries an L2 eviction priority: X rows are loaded evict_last so the
+// streamed column ids / Y writes do not push the gathered matrix out of the 126 MB L2.
 // ---------------------------------------------------------------------------------------
-template <int LPE, int NV>
-__device__ __forceinline__ void gather_accumulate(float4 (&acc)[NV], const float *__restrict__ xlane,
+template <int VW> struct Vec;
+template <> struct Vec<4> {
+  float4 a;
+  __device__ __forceinline__ void zero() { a = make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ void load(const float *p) { a = ldg_f4(p); }
+  __device__ __forceinline__ void add(const Vec &o) { add4(a, o.a); }
+  __device__ __forceinline__ void xor_reduce(int off) {
+    a.x += __shfl_xor_sync(0xffffffffu, a.x, off);
+    a.y += __shfl_xor_sync(0xffffffffu, a.y, off);
+    a.z += __shfl_xor_sync(0xffffffffu, a.z, off);
+    a.w += __shfl_xor_sync(0xffffffffu, a.w, off);
+  }
+  __device__ __forceinline__ void load_plain(const float *p) { a = *reinterpret_cast<const float4 *>(p); }
+  __device__ __forceinline__ void store(float *p) const { *reinterpret_cast<float4 *>(p) = a; }
+};
+template <> struct Vec<8> {
+  float4 a, b;
+  __device__ __forceinline__ void zero() { a = b = make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ void load(const float *p) {
+    asm volatile("ld.global.nc.L2::evict_last.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+  }
+  __device__ __forceinline__ void add(const Vec &o) { add4(a, o.a); add4(b, o.b); }
+  __device__ __forceinline__ void xor_reduce(int off) {
+    a.x += __shfl_xor_sync(0xffffffffu, a.x, off);
+    a.y += __shfl_xor_sync(0xffffffffu, a.y, off);
+    a.z += __shfl_xor_sync(0xffffffffu, a.z, off);
+    a.w += __shfl_xor_sync(0xffffffffu, a.w, off);
+    b.x += __shfl_xor_sync(0xffffffffu, b.x, off);
+    b.y += __shfl_xor_sync(0xffffffffu, b.y, off);
+    b.z += __shfl_xor_sync(0xffffffffu, b.z, off);
+    b.w += __shfl_xor_sync(0xffffffffu, b.w, off);
+  }
+  __device__ __forceinline__ void load_plain(const float *p) {
+    a = *reinterpret_cast<const float4 *>(p);
+    b = *reinterpret_cast<const float4 *>(p + 4);
+  }
+  __device__ __forceinline__ void store(float *p) const {
+    *reinterpret_cast<float4 *>(p) = a;
+    *reinterpret_cast<float4 *>(p + 4) = b;
+  }
+};
+
+#ifndef HCSPMM_INFLIGHT_BYTES
+#define HCSPMM_INFLIGHT_BYTES 128  // gathered bytes kept in flight per lane (ring depth x vector bytes)
+#endif
+
+// ---------------------------------------------------------------------------------------
+// CUDA-core gather: accumulate X rows of edges [eb, ee), visiting 32-edge chunks
+// chunk0, chunk0 + chunk_stride, ...   A group of LPE lanes reads one X row, lane g of the group
+// owning vectors g, g + LPE, ... (NV of them, VW floats each).
+// ---------------------------------------------------------------------------------------
+template <int LPE, int NV, int VW>
+__device__ __forceinline__ void gather_accumulate(Vec<VW> (&acc)[NV], const float *__restrict__ xlane,
                                                   long long ldx, int x_rows,
                                                   const int *__restrict__ colidx, int eb, int ee,
                                                   int chunk0, int chunk_stride, int lane, int q,
                                                   const bool (&active)[NV], bool all_active) {
   constexpr int G = 32 / LPE;         // edges handled concurrently by one warp
   constexpr int STEPS = 32 / G;       // gather steps per full 32-edge chunk
-  constexpr int U = NV >= 4 ? 2 : (NV == 2 ? 4 : 8);  // loads kept in flight per lane (x NV)
+  constexpr int U0 = HCSPMM_INFLIGHT_BYTES / (NV * VW * 4);
+  constexpr int U = U0 < 1 ? 1 : (U0 > STEPS ? STEPS : U0);   // ring depth
   int base = eb + chunk0 * 32;
   int c_next = (base + lane < ee) ? __ldg(colidx + base + lane) : -1;
   for (; base < ee; base += chunk_stride * 32) {
@@ -72,29 +131,29 @@ __device__ __forceinline__ void gather_accumulate(float4 (&acc)[NV], const float
     if (fast) {
       // full chunk, every id valid, every lane active: unpredicated ring of U loads in flight --
       // slot s % U is consumed and immediately refilled with step s + U
-      float4 v[U][NV];
+      Vec<VW> v[U][NV];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int cu = __shfl_sync(0xffffffffu, c, u * G + q);
         const float *src = xlane + (long long)cu * ldx;
 #pragma unroll
-        for (int i = 0; i < NV; ++i) v[u][i] = ldg_f4(src + i * LPE * 4);
+        for (int i = 0; i < NV; ++i) v[u][i].load(src + i * LPE * VW);
       }
 #pragma unroll
       for (int s = 0; s < STEPS; ++s) {
 #pragma unroll
-        for (int i = 0; i < NV; ++i) add4(acc[i], v[s % U][i]);
+        for (int i = 0; i < NV; ++i) acc[i].add(v[s % U][i]);
         if (s + U < STEPS) {
           const int cu = __shfl_sync(0xffffffffu, c, (s + U) * G + q);
           const float *src = xlane + (long long)cu * ldx;
 #pragma unroll
-          for (int i = 0; i < NV; ++i) v[s % U][i] = ldg_f4(src + i * LPE * 4);
+          for (int i = 0; i < NV; ++i) v[s % U][i].load(src + i * LPE * VW);
         }
       }
     } else {
 #pragma unroll 1
       for (int t = 0; t * G < n; t += U) {
-        float4 v[U][NV];
+        Vec<VW> v[U][NV];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int j = (t + u) * G + q;
@@ -102,29 +161,26 @@ __device__ __forceinline__ void gather_accumulate(float4 (&acc)[NV], const float
           const bool ok = (j < n) && ((unsigned)cu < (unsigned)x_rows);
           const float *src = xlane + (long long)cu * ldx;
 #pragma unroll
-          for (int i = 0; i < NV; ++i)
-            v[u][i] = (ok && active[i]) ? ldg_f4(src + i * LPE * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int i = 0; i < NV; ++i) {
+            if (ok && active[i]) v[u][i].load(src + i * LPE * VW);
+            else v[u][i].zero();
+          }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u)
 #pragma unroll
-          for (int i = 0; i < NV; ++i) add4(acc[i], v[u][i]);
+          for (int i = 0; i < NV; ++i) acc[i].add(v[u][i]);
       }
     }
   }
 }
 
-template <int LPE, int NV>
-__device__ __forceinline__ void group_reduce(float4 (&acc)[NV]) {
+template <int LPE, int NV, int VW>
+__device__ __forceinline__ void group_reduce(Vec<VW> (&acc)[NV]) {
 #pragma unroll
   for (int o = LPE; o < 32; o <<= 1)
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      acc[i].x += __shfl_xor_sync(0xffffffffu, acc[i].x, o);
-      acc[i].y += __shfl_xor_sync(0xffffffffu, acc[i].y, o);
-      acc[i].z += __shfl_xor_sync(0xffffffffu, acc[i].z, o);
-      acc[i].w += __shfl_xor_sync(0xffffffffu, acc[i].w, o);
-    }
+    for (int i = 0; i < NV; ++i) acc[i].xor_reduce(o);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -174,16 +230,19 @@ __device__ __forceinline__ void tc_window(const SpmmParams &p, int w, int e0, in
       }
       cp_async_commit();
     };
-    stage(0, 0);
+    // NSTAGE-deep cp.async pipeline: NSTAGE-1 chunks of KC gathered rows are in flight while one
+    // is multiplied; one barrier per chunk
+#pragma unroll
+    for (int s0 = 0; s0 < NSTAGE - 1; ++s0) {
+      if (s0 < nk) stage(s0, s0);
+      else cp_async_commit();
+    }
     for (int kc = 0; kc < nk; ++kc) {
-      const int buf = kc & 1;
-      if (kc + 1 < nk) {
-        stage(kc + 1, buf ^ 1);
-        cp_async_wait<1>();
-      } else {
-        cp_async_wait<0>();
-      }
-      __syncthreads();
+      const int buf = kc % NSTAGE;
+      cp_async_wait<NSTAGE - 2>();
+      __syncthreads();  // chunk kc visible to all; buffer (kc-1) % NSTAGE free for refill
+      if (kc + NSTAGE - 1 < nk) stage(kc + NSTAGE - 1, (kc + NSTAGE - 1) % NSTAGE);
+      else cp_async_commit();
       const float *xt = xs + buf * KC * stride;
 #pragma unroll
       for (int ks = 0; ks < KC / 8; ++ks) {
@@ -213,8 +272,8 @@ __device__ __forceinline__ void tc_window(const SpmmParams &p, int w, int e0, in
           }
         }
       }
-      __syncthreads();  // tile consumed before it is overwritten two steps later
     }
+    cp_async_wait<0>();
   }
   const int row0 = w * BLK_H + g, row1 = row0 + 8;
 #pragma unroll
@@ -241,7 +300,7 @@ __device__ __forceinline__ void tc_window(const SpmmParams &p, int w, int e0, in
 // ---------------------------------------------------------------------------------------
 // The hybrid kernel.  Slab width S <= LPE * NV * 4 floats; X/Y 16-byte aligned, ldx/ldy % 4 == 0.
 // ---------------------------------------------------------------------------------------
-template <int LPE, int NV>
+template <int LPE, int NV, int VW>
 __global__ void __launch_bounds__(CTA_THREADS, HCSPMM_MIN_CTAS) spmm_hybrid_kernel(const SpmmParams p) {
   extern __shared__ __align__(16) float smem[];
   __shared__ int rp[BLK_H + 1];
@@ -251,7 +310,7 @@ __global__ void __launch_bounds__(CTA_THREADS, HCSPMM_MIN_CTAS) spmm_hybrid_kern
   const int r0 = w * BLK_H;
   const int feat0 = blockIdx.y * p.slab;
   const int S = min(p.slab, p.dim - feat0);
-  const int nvec = S >> 2;
+  const int nvec = S / VW;
   if (tid <= BLK_H) rp[tid] = __ldg(p.rowptr + min(r0 + tid, p.n_rows));
   if (tid == 0) s_next = 0;
   __syncthreads();
@@ -259,17 +318,16 @@ __global__ void __launch_bounds__(CTA_THREADS, HCSPMM_MIN_CTAS) spmm_hybrid_kern
 
   if (p.ht != nullptr && p.precision != HCSPMM_PRECISION_FP32 && (S & 7) == 0 && e1 > e0 &&
       __ldg(p.ht + w) != 0) {
-    tc_window<(LPE * NV * 4 + 63) / 64>(p, w, e0, e1, feat0, S, smem);
+    tc_window<(LPE * NV * VW + 63) / 64>(p, w, e0, e1, feat0, S, smem);
     return;
   }
 
-  constexpr int G = 32 / LPE;
   const int q = lane / LPE, g = lane % LPE;
   bool active[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) active[i] = (g + i * LPE) < nvec;
   const bool all_active = nvec == LPE * NV;
-  const float *xlane = p.x + feat0 + g * 4;
+  const float *xlane = p.x + feat0 + g * VW;
   const int rows_here = min(BLK_H, p.n_rows - r0);
 
   // phase 1: short rows, one warp per row, rows claimed dynamically
@@ -280,46 +338,48 @@ __global__ void __launch_bounds__(CTA_THREADS, HCSPMM_MIN_CTAS) spmm_hybrid_kern
     if (r >= rows_here) break;
     const int eb = rp[r], ee = rp[r + 1];
     if (ee - eb >= p.long_row) continue;
-    float4 acc[NV];
+    Vec<VW> acc[NV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    gather_accumulate<LPE, NV>(acc, xlane, p.ldx, p.x_rows, p.colidx, eb, ee, 0, 1, lane, q, active, all_active);
-    group_reduce<LPE, NV>(acc);
+    for (int i = 0; i < NV; ++i) acc[i].zero();
+    gather_accumulate<LPE, NV, VW>(acc, xlane, p.ldx, p.x_rows, p.colidx, eb, ee, 0, 1, lane, q, active,
+                                   all_active);
+    group_reduce<LPE, NV, VW>(acc);
     if (q == 0) {
-      float *yrow = p.y + (long long)(r0 + r) * p.ldy + feat0 + g * 4;
+      float *yrow = p.y + (long long)(r0 + r) * p.ldy + feat0 + g * VW;
 #pragma unroll
       for (int i = 0; i < NV; ++i)
         if (active[i]) {
-          float4 *dst = reinterpret_cast<float4 *>(yrow + i * LPE * 4);
-          float4 v = acc[i];
-          if (p.accumulate) add4(v, *dst);
-          *dst = v;
+          if (p.accumulate) {
+            Vec<VW> o;
+            o.load_plain(yrow + i * LPE * VW);
+            acc[i].add(o);
+          }
+          acc[i].store(yrow + i * LPE * VW);
         }
     }
   }
-  (void)G;
 
   // phase 2: long rows, all warps of the CTA share one row (CTA-uniform control flow)
   bool any_long = false;
   for (int r = 0; r < rows_here; ++r) any_long |= (rp[r + 1] - rp[r] >= p.long_row);
   if (!any_long) return;
+  const int nvec4 = S >> 2;
   for (int r = 0; r < rows_here; ++r) {
     const int eb = rp[r], ee = rp[r + 1];
     if (ee - eb < p.long_row) continue;
-    float4 acc[NV];
+    Vec<VW> acc[NV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    gather_accumulate<LPE, NV>(acc, xlane, p.ldx, p.x_rows, p.colidx, eb, ee, wid, CTA_WARPS, lane, q,
-                               active, all_active);
-    group_reduce<LPE, NV>(acc);
+    for (int i = 0; i < NV; ++i) acc[i].zero();
+    gather_accumulate<LPE, NV, VW>(acc, xlane, p.ldx, p.x_rows, p.colidx, eb, ee, wid, CTA_WARPS, lane, q,
+                                   active, all_active);
+    group_reduce<LPE, NV, VW>(acc);
     if (q == 0) {
 #pragma unroll
       for (int i = 0; i < NV; ++i)
-        if (active[i])
-          *reinterpret_cast<float4 *>(smem + wid * S + (g + i * LPE) * 4) = acc[i];
+        if (active[i]) acc[i].store(smem + wid * S + (g + i * LPE) * VW);
     }
     __syncthreads();
-    for (int v = tid; v < nvec; v += CTA_THREADS) {
+    for (int v = tid; v < nvec4; v += CTA_THREADS) {
       float4 s = *reinterpret_cast<const float4 *>(smem + v * 4);
 #pragma unroll
       for (int ww = 1; ww < CTA_WARPS; ++ww)
@@ -366,16 +426,16 @@ __global__ void __launch_bounds__(CTA_THREADS) spmm_scalar_kernel(const SpmmPara
 
 static size_t hybrid_smem_bytes(int S, bool tc) {
   size_t cuda_path = (size_t)CTA_WARPS * S * sizeof(float);
-  size_t tc_path = tc ? (size_t)(2 * (UCAP + KC) + 2 * KC * (S + 8)) * sizeof(float) : 0;
+  size_t tc_path = tc ? (size_t)(2 * (UCAP + KC) + NSTAGE * KC * (S + 8)) * sizeof(float) : 0;
   return cuda_path > tc_path ? cuda_path : tc_path;
 }
 
-template <int LPE, int NV>
+template <int LPE, int NV, int VW>
 static cudaError_t launch_hybrid(const SpmmParams &p, dim3 grid, size_t smem, cudaStream_t stream) {
-  cudaError_t err = cudaFuncSetAttribute(spmm_hybrid_kernel<LPE, NV>,
+  cudaError_t err = cudaFuncSetAttribute(spmm_hybrid_kernel<LPE, NV, VW>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
-  spmm_hybrid_kernel<LPE, NV><<<grid, CTA_THREADS, smem, stream>>>(p);
+  spmm_hybrid_kernel<LPE, NV, VW><<<grid, CTA_THREADS, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
@@ -401,7 +461,7 @@ int launch_spmm(const float *x, int64_t ldx, int32_t x_rows, const int32_t *rowp
     return HCSPMM_E_INVALID;
   }
   const bool labels = ht != nullptr && precision != HCSPMM_PRECISION_FP32;
-  if (labels && (!bp || !etc || !etr)) {
+  if (labels && (!bp || (nnz > 0 && (!etc || !etr)))) {
     set_error("spmm: hybrid_type given without blockPartition/edgeToColumn/edgeToRow");
     return HCSPMM_E_INVALID;
   }
@@ -430,11 +490,23 @@ int launch_spmm(const float *x, int64_t ldx, int32_t x_rows, const int32_t *rowp
     dim3 grid(n_windows, (dim + slab - 1) / slab, 1);
     const bool tc = labels && (slab % 8 == 0);
     const size_t smem = hybrid_smem_bytes(slab, tc);
-    if (slab <= 32) err = launch_hybrid<8, 1>(p, grid, smem, stream);
-    else if (slab <= 64) err = launch_hybrid<16, 1>(p, grid, smem, stream);
-    else if (slab <= 128) err = launch_hybrid<32, 1>(p, grid, smem, stream);
-    else if (slab <= 256) err = launch_hybrid<32, 2>(p, grid, smem, stream);
-    else err = launch_hybrid<32, 4>(p, grid, smem, stream);
+    // 256-bit loads need 32-byte aligned rows in every slab
+    const bool v8 = tuning().vec8 != 0 &&
+                    ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 31) == 0 &&
+                    (ldx & 7) == 0 && (ldy & 7) == 0 && (dim & 7) == 0 && (slab & 7) == 0;
+    if (v8) {
+      if (slab <= 32) err = launch_hybrid<4, 1, 8>(p, grid, smem, stream);
+      else if (slab <= 64) err = launch_hybrid<8, 1, 8>(p, grid, smem, stream);
+      else if (slab <= 128) err = launch_hybrid<16, 1, 8>(p, grid, smem, stream);
+      else if (slab <= 256) err = launch_hybrid<32, 1, 8>(p, grid, smem, stream);
+      else err = launch_hybrid<32, 2, 8>(p, grid, smem, stream);
+    } else {
+      if (slab <= 32) err = launch_hybrid<8, 1, 4>(p, grid, smem, stream);
+      else if (slab <= 64) err = launch_hybrid<16, 1, 4>(p, grid, smem, stream);
+      else if (slab <= 128) err = launch_hybrid<32, 1, 4>(p, grid, smem, stream);
+      else if (slab <= 256) err = launch_hybrid<32, 2, 4>(p, grid, smem, stream);
+      else err = launch_hybrid<32, 4, 4>(p, grid, smem, stream);
+    }
   }
   if (err != cudaSuccess) {
     set_error("spmm launch: %s", cudaGetErrorString(err));

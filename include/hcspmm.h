@@ -66,6 +66,7 @@ const char *hcspmm_last_error(void);
  *   "long_row"   rows with >= this many non-zeros are split over all warps of a CTA
  *   "slab"       feature-slab width in floats (0 = whole row); slabs are scheduled
  *                slab-major so that one slab of X stays L2-resident
+ *   "vec8"       1 (default): 256-bit gathers when rows are 32-byte aligned; 0: 128-bit
  * Returns the previous value, or -1 for an unknown key.                          */
 int hcspmm_set_tuning(const char *key, int value);
 
