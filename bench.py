@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--slab", type=int, default=-1, help="feature-slab width (-1 = library default)")
     ap.add_argument("--long-row", type=int, default=-1)
     ap.add_argument("--vec8", type=int, default=-1, help="256-bit gathers: 1 on, 0 off (-1 = library default)")
+    ap.add_argument("--tune", action="append", default=[], help="library tuning knob key=value (repeatable)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline budget per timed run")
@@ -257,6 +258,9 @@ def main():
         HCSPMM.set_tuning("long_row", args.long_row)
     if args.vec8 >= 0:
         HCSPMM.set_tuning("vec8", args.vec8)
+    for kv in args.tune:
+        k, v = kv.split("=")
+        HCSPMM.set_tuning(k, int(v))
     HCSPMM.set_classifier(args.classifier)
     HCSPMM.set_precision(args.precision)
 

@@ -1,0 +1,89 @@
+#!/usr/bin/env python
+"""GCN / GIN epoch time on a BASELINE shape (configs[2] / configs[3]) at 1/2/4/8 GPUs.
+
+  python benchmarks/gcn_epoch.py [--shape products --hidden 128 --feat 100 --classes 47 --layers 2]
+  torchrun --nproc-per-node N benchmarks/gcn_epoch.py ...
+
+Row-partitioned training (hcspmm.dist): every rank owns a nnz-balanced range of 16-row windows of A and
+the matching rows of X / labels; each layer = local Update GEMM + all-gather + local hybrid SpMM.
+Prints one JSON line: median epoch ms (forward + backward + Adam) over --epochs after --warmup, max over ranks.
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "hc-spmm_b200")]
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--shape", default="products")
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--feat", type=int, default=100)
+    ap.add_argument("--hidden", type=int, default=128)
+    ap.add_argument("--classes", type=int, default=47)
+    ap.add_argument("--layers", type=int, default=2)
+    ap.add_argument("--epochs", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--schedule", default="gather", choices=["gather", "slabs"])
+    ap.add_argument("--slabs", type=int, default=2)
+    ap.add_argument("--classifier", default="shipped")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    lr = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(lr)
+    dev = torch.device("cuda", lr)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import HCSPMM
+    from hcspmm import dist as hd, graphs
+    HCSPMM.set_classifier(args.classifier)
+    rp, ci, info = graphs.named(args.shape, device=dev, scale=args.scale)
+    g = hd.ShardedGraph(rp, ci, schedule=args.schedule, n_slabs=args.slabs)
+    del rp, ci
+    gen = torch.Generator(device=dev).manual_seed(100 + rank)
+    x = torch.randn(g.n_local, args.feat, device=dev, generator=gen)
+    y = torch.randint(0, args.classes, (g.n_local,), device=dev, generator=gen)
+    model = hd.DistGCN(g, args.feat, args.hidden, args.classes, num_layers=args.layers, seed=0).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=0.01)
+    times, losses = [], []
+    for ep in range(args.warmup + args.epochs):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        opt.zero_grad()
+        loss = model.loss(x, y)
+        loss.backward()
+        model.sync_grads()
+        opt.step()
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
+        l = loss.detach().double().reshape(1)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(l)
+        if ep >= args.warmup:
+            times.append(float(t))
+            losses.append(float(l))
+    times.sort()
+    if rank == 0:
+        print(json.dumps({"metric": "gcn_epoch_ms", "value": times[len(times) // 2], "unit": "ms", "n_gpus": world,
+                          "higher_is_better": False, "scaling": "strong", "min_ms": times[0],
+                          "config": {"workload": f"{args.layers}-layer GCN, {args.shape}-shape graph", "nodes": info["n"],
+                                     "stored_entries": info["nnz"], "feat": args.feat, "hidden": args.hidden,
+                                     "classes": args.classes, "schedule": args.schedule, "classifier": args.classifier},
+                          "loss_first": losses[0], "loss_last": losses[-1]}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -17,7 +17,7 @@ void set_error(const char *fmt, ...) {
 }
 
 Tuning &tuning() {
-  static Tuning t = {1024, 0, 1};
+  static Tuning t = {1024, 0, 1, 1, 0};
   return t;
 }
 
@@ -29,6 +29,10 @@ int launch_spmm(const float *, int64_t, int32_t, const int32_t *, const int32_t 
                 int, float *, int64_t, cudaStream_t);
 int launch_gemm_tf32(const float *, int64_t, const float *, int64_t, int32_t, int32_t, int32_t,
                      float *, int64_t, cudaStream_t);
+
+size_t loa_workspace_bytes(int32_t n, int64_t nnz, int32_t max_degree);
+int launch_loa(const int32_t *, const int32_t *, const int32_t *, const int32_t *, int32_t, int64_t, int32_t,
+               int32_t *, int32_t *, int32_t *, void *, size_t, cudaStream_t);
 
 }  // namespace hcspmm
 
@@ -63,6 +67,8 @@ int hcspmm_set_tuning(const char *key, int value) {
   if (key && !strcmp(key, "long_row")) slot = &tuning().long_row;
   else if (key && !strcmp(key, "slab")) slot = &tuning().slab;
   else if (key && !strcmp(key, "vec8")) slot = &tuning().vec8;
+  else if (key && !strcmp(key, "short_row")) slot = &tuning().short_row;
+  else if (key && !strcmp(key, "wpc")) slot = &tuning().wpc;
   if (!slot) return -1;
   int old = *slot;
   *slot = value;
@@ -113,6 +119,18 @@ int hcspmm_spmm_gemm(const float *d_x, int64_t ldx, int32_t x_rows, const int32_
   if (rc) return rc;
   return launch_gemm_tf32(d_z, ldz, d_w, ldw, n_rows, dim, hidden, d_out, ldo,
                           (cudaStream_t)stream);
+}
+
+size_t hcspmm_loa_workspace_bytes(int32_t n, int64_t nnz, int32_t max_degree) {
+  return loa_workspace_bytes(n, nnz, max_degree);
+}
+
+int hcspmm_loa_reorder(const int32_t *d_rowptr, const int32_t *d_colidx, const int32_t *d_rowptr_in,
+                       const int32_t *d_colidx_in, int32_t n, int64_t nnz, int32_t max_degree,
+                       int32_t *d_perm, int32_t *d_block_start, int32_t *d_counts, void *d_workspace,
+                       size_t workspace_bytes, void *stream) {
+  return launch_loa(d_rowptr, d_colidx, d_rowptr_in, d_colidx_in, n, nnz, max_degree, d_perm,
+                    d_block_start, d_counts, d_workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 void hcspmm_graph_destroy(hcspmm_graph_t *g) {

@@ -19,6 +19,8 @@ struct Tuning {
   int long_row;  // rows with >= long_row non-zeros are split over all warps of the CTA
   int slab;      // feature-slab width in floats, 0 = no slabbing
   int vec8;      // use 256-bit gathers when alignment allows (1) or always 128-bit (0)
+  int short_row; // rows shorter than short_row * (32 / lanes-per-row) go one lane group per row
+  int wpc;       // windows per CTA, 0 = automatic from the mean window population
 };
 Tuning &tuning();
 

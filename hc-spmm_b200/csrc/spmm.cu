@@ -48,8 +48,12 @@ struct SpmmParams {
   int precision, accumulate;
   float *y;
   long long ldy;
-  int long_row;
+  int long_row;   // rows with >= long_row entries: all warps of the CTA share the row
+  int short_row;  // rows with <  short_row entries: one lane GROUP per row (G rows per warp at once)
+  int wpc;        // 16-row windows per CTA (1..MAX_WPC), > 1 on low-degree graphs
+  int n_windows;
 };
+constexpr int MAX_WPC = 8;
 
 // ---------------------------------------------------------------------------------------
 // Per-lane feature vector: VW = 4 floats (LDG.128) or 8 floats (LDG.256, new on sm_100).
@@ -171,6 +175,45 @@ __device__ __forceinline__ void gather_accumulate(Vec<VW> (&acc)[NV], const floa
 #pragma unroll
           for (int i = 0; i < NV; ++i) acc[i].add(v[u][i]);
       }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Low-degree rows: one group of LPE lanes owns a whole row, so a warp advances G = 32 / LPE rows at
+// once and nothing is reduced across lanes.  The group fetches LPE column ids with one load and
+// broadcasts them inside the group (sub-warp shuffle masks: groups may run different trip counts).
+// ---------------------------------------------------------------------------------------
+template <int LPE, int NV, int VW>
+__device__ __forceinline__ void gather_group_row(Vec<VW> (&acc)[NV], const float *__restrict__ xlane,
+                                                 long long ldx, int x_rows,
+                                                 const int *__restrict__ colidx, int eb, int ee, int lane,
+                                                 int q, int g, const bool (&active)[NV]) {
+  constexpr int UB0 = HCSPMM_INFLIGHT_BYTES / (NV * VW * 4);
+  constexpr int UB = UB0 < 1 ? 1 : (UB0 > LPE ? LPE : UB0);
+  const unsigned gmask = LPE == 32 ? 0xffffffffu : (((1u << LPE) - 1u) << (q * LPE));
+  (void)lane;
+  for (int e = eb; e < ee; e += LPE) {
+    const int my = (e + g < ee) ? __ldg(colidx + e + g) : -1;
+    const int cnt = min(LPE, ee - e);
+#pragma unroll 1
+    for (int j0 = 0; j0 < cnt; j0 += UB) {
+      Vec<VW> v[UB][NV];
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const int cu = __shfl_sync(gmask, my, q * LPE + ((j0 + u) & (LPE - 1)));
+        const bool ok = (j0 + u < cnt) && ((unsigned)cu < (unsigned)x_rows);
+        const float *src = xlane + (long long)cu * ldx;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          if (ok && active[i]) v[u][i].load(src + i * LPE * VW);
+          else v[u][i].zero();
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UB; ++u)
+#pragma unroll
+        for (int i = 0; i < NV; ++i) acc[i].add(v[u][i]);
     }
   }
 }
@@ -303,23 +346,49 @@ __device__ __forceinline__ void tc_window(const SpmmParams &p, int w, int e0, in
 template <int LPE, int NV, int VW>
 __global__ void __launch_bounds__(CTA_THREADS, HCSPMM_MIN_CTAS) spmm_hybrid_kernel(const SpmmParams p) {
   extern __shared__ __align__(16) float smem[];
-  __shared__ int rp[BLK_H + 1];
+  __shared__ int rp[BLK_H * MAX_WPC + 1];
   __shared__ int s_next;
-  const int w = blockIdx.x;
+  __shared__ unsigned s_tcmask;
+  constexpr int G = 32 / LPE;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int r0 = w * BLK_H;
+  const int w0 = blockIdx.x * p.wpc;
+  const int nwin = min(p.wpc, p.n_windows - w0);
+  const int r0 = w0 * BLK_H;
+  const int rows_here = min(BLK_H * nwin, p.n_rows - r0);
   const int feat0 = blockIdx.y * p.slab;
   const int S = min(p.slab, p.dim - feat0);
   const int nvec = S / VW;
-  if (tid <= BLK_H) rp[tid] = __ldg(p.rowptr + min(r0 + tid, p.n_rows));
-  if (tid == 0) s_next = 0;
+  for (int i = tid; i <= rows_here; i += CTA_THREADS) rp[i] = __ldg(p.rowptr + r0 + i);
+  if (tid == 0) {
+    s_next = 0;
+    unsigned m = 0;
+    if (p.ht != nullptr && p.precision != HCSPMM_PRECISION_FP32 && (S & 7) == 0)
+      for (int i = 0; i < nwin; ++i)
+        if (__ldg(p.ht + w0 + i) != 0) m |= 1u << i;
+    s_tcmask = m;
+  }
   __syncthreads();
-  const int e0 = rp[0], e1 = rp[BLK_H];
+  const unsigned tcmask = s_tcmask;
 
-  if (p.ht != nullptr && p.precision != HCSPMM_PRECISION_FP32 && (S & 7) == 0 && e1 > e0 &&
-      __ldg(p.ht + w) != 0) {
-    tc_window<(LPE * NV * VW + 63) / 64>(p, w, e0, e1, feat0, S, smem);
-    return;
+  // tensor-core windows of this CTA, one after another (CTA-wide)
+  if (tcmask != 0u) {
+    for (int i = 0; i < nwin; ++i) {
+      if (!((tcmask >> i) & 1u)) continue;
+      const int e0 = rp[i * BLK_H], e1 = rp[min((i + 1) * BLK_H, rows_here)];
+      if (e1 > e0) {
+        tc_window<(LPE * NV * VW + 63) / 64>(p, w0 + i, e0, e1, feat0, S, smem);
+      } else {
+        // empty window labelled TC: rows are zero
+        for (int t = tid; t < BLK_H * (S >> 2); t += CTA_THREADS) {
+          const int r = i * BLK_H + t / (S >> 2), v = t % (S >> 2);
+          if (r < rows_here && !p.accumulate)
+            *reinterpret_cast<float4 *>(p.y + (long long)(r0 + r) * p.ldy + feat0 + v * 4) =
+                make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      __syncthreads();
+    }
+    if (tcmask == (nwin >= 32 ? 0xffffffffu : ((1u << nwin) - 1u))) return;
   }
 
   const int q = lane / LPE, g = lane % LPE;
@@ -328,16 +397,58 @@ __global__ void __launch_bounds__(CTA_THREADS, HCSPMM_MIN_CTAS) spmm_hybrid_kern
   for (int i = 0; i < NV; ++i) active[i] = (g + i * LPE) < nvec;
   const bool all_active = nvec == LPE * NV;
   const float *xlane = p.x + feat0 + g * VW;
-  const int rows_here = min(BLK_H, p.n_rows - r0);
+  const int short_row = G > 1 ? p.short_row : 0;
 
-  // phase 1: short rows, one warp per row, rows claimed dynamically
-  for (;;) {
+  // phase A: short rows, one lane group per row, static round-robin over the CTA's rows
+  if (short_row > 0) {
+    for (int r = wid * G + q; r < rows_here; r += CTA_WARPS * G) {
+      const int eb = rp[r], ee = rp[r + 1];
+      if (ee - eb >= short_row || ((tcmask >> (r / BLK_H)) & 1u)) continue;
+      Vec<VW> acc[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) acc[i].zero();
+      gather_group_row<LPE, NV, VW>(acc, xlane, p.ldx, p.x_rows, p.colidx, eb, ee, lane, q, g, active);
+      float *yrow = p.y + (long long)(r0 + r) * p.ldy + feat0 + g * VW;
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        if (active[i]) {
+          if (p.accumulate) {
+            Vec<VW> o;
+            o.load_plain(yrow + i * LPE * VW);
+            acc[i].add(o);
+          }
+          acc[i].store(yrow + i * LPE * VW);
+        }
+    }
+    __syncwarp();
+  }
+
+  // which of the remaining phases does this CTA need?  (one barrier-reduction each)
+  int has_medium = 0, has_long = 0;
+  for (int r = tid; r < rows_here; r += CTA_THREADS) {
+    const int d = rp[r + 1] - rp[r];
+    if (!((tcmask >> (r / BLK_H)) & 1u)) {
+      has_long |= d >= p.long_row;
+      has_medium |= d >= short_row && d < p.long_row && d > 0;
+    }
+    if (d == 0 && short_row == 0 && !p.accumulate && !((tcmask >> (r / BLK_H)) & 1u)) {
+      // empty rows are written here when phase A is off (phase B skips them)
+      for (int v = 0; v < (S >> 2); ++v)
+        *reinterpret_cast<float4 *>(p.y + (long long)(r0 + r) * p.ldy + feat0 + v * 4) =
+            make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  has_medium = __syncthreads_or(has_medium);
+  has_long = __syncthreads_or(has_long);
+
+  // phase B: medium rows, one warp per row, rows claimed dynamically
+  while (has_medium) {
     int r = 0;
     if (lane == 0) r = atomicAdd(&s_next, 1);
     r = __shfl_sync(0xffffffffu, r, 0);
     if (r >= rows_here) break;
     const int eb = rp[r], ee = rp[r + 1];
-    if (ee - eb >= p.long_row) continue;
+    if (ee - eb >= p.long_row || ee - eb < short_row || ee == eb || ((tcmask >> (r / BLK_H)) & 1u)) continue;
     Vec<VW> acc[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) acc[i].zero();
@@ -359,14 +470,12 @@ __global__ void __launch_bounds__(CTA_THREADS, HCSPMM_MIN_CTAS) spmm_hybrid_kern
     }
   }
 
-  // phase 2: long rows, all warps of the CTA share one row (CTA-uniform control flow)
-  bool any_long = false;
-  for (int r = 0; r < rows_here; ++r) any_long |= (rp[r + 1] - rp[r] >= p.long_row);
-  if (!any_long) return;
+  // phase C: long rows, all warps of the CTA share one row (CTA-uniform control flow)
+  if (!has_long) return;
   const int nvec4 = S >> 2;
   for (int r = 0; r < rows_here; ++r) {
     const int eb = rp[r], ee = rp[r + 1];
-    if (ee - eb < p.long_row) continue;
+    if (ee - eb < p.long_row || ((tcmask >> (r / BLK_H)) & 1u)) continue;
     Vec<VW> acc[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) acc[i].zero();
@@ -435,7 +544,9 @@ static cudaError_t launch_hybrid(const SpmmParams &p, dim3 grid, size_t smem, cu
   cudaError_t err = cudaFuncSetAttribute(spmm_hybrid_kernel<LPE, NV, VW>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
-  spmm_hybrid_kernel<LPE, NV, VW><<<grid, CTA_THREADS, smem, stream>>>(p);
+  SpmmParams q = p;
+  q.short_row = p.short_row * (32 / LPE);   // "fewer than short_row steps of a whole warp"
+  spmm_hybrid_kernel<LPE, NV, VW><<<grid, CTA_THREADS, smem, stream>>>(q);
   return cudaGetLastError();
 }
 
@@ -473,6 +584,9 @@ int launch_spmm(const float *x, int64_t ldx, int32_t x_rows, const int32_t *rowp
   p.precision = precision; p.accumulate = accumulate;
   p.y = y; p.ldy = ldy;
   p.long_row = tuning().long_row > 0 ? tuning().long_row : 0x7fffffff;
+  p.short_row = tuning().short_row;   // multiplied by G inside the launcher below
+  p.wpc = 1;
+  p.n_windows = (n_rows + BLK_H - 1) / BLK_H;
 
   const int n_windows = (n_rows + BLK_H - 1) / BLK_H;
   const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0 &&
@@ -487,7 +601,17 @@ int launch_spmm(const float *x, int64_t ldx, int32_t x_rows, const int32_t *rowp
     if (slab > 512) slab = 512;
     if (slab > dim) slab = dim;
     p.slab = slab;
-    dim3 grid(n_windows, (dim + slab - 1) / slab, 1);
+    // low-degree graphs: several windows per CTA so that a CTA has a few hundred edges to chew on
+    const long long per_window = n_windows > 0 ? (long long)(nnz / n_windows) : 0;
+    int wpc = tuning().wpc;
+    if (wpc <= 0) {
+      wpc = 1;
+      while (wpc < MAX_WPC && per_window * wpc < 384) wpc <<= 1;
+    }
+    if (wpc > MAX_WPC) wpc = MAX_WPC;
+    p.wpc = wpc;
+    p.n_windows = n_windows;
+    dim3 grid((n_windows + wpc - 1) / wpc, (dim + slab - 1) / slab, 1);
     const bool tc = labels && (slab % 8 == 0);
     const size_t smem = hybrid_smem_bytes(slab, tc);
     // 256-bit loads need 32-byte aligned rows in every slab

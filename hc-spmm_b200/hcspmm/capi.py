@@ -20,7 +20,7 @@ PRECISIONS = {"tf32": 0, "tf32x2": 1, "fp32": 2}
 EXPORTS = [
     "hcspmm_version", "hcspmm_last_error", "hcspmm_set_tuning",
     "hcspmm_preprocess_workspace_bytes", "hcspmm_preprocess", "hcspmm_spmm", "hcspmm_spmm_gemm",
-    "hcspmm_gemm_tf32", "hcspmm_graph_create", "hcspmm_graph_spmm_host",
+    "hcspmm_gemm_tf32", "hcspmm_loa_workspace_bytes", "hcspmm_loa_reorder", "hcspmm_graph_create", "hcspmm_graph_spmm_host",
     "hcspmm_graph_get_preprocess", "hcspmm_graph_destroy",
 ]
 
@@ -51,6 +51,9 @@ def lib() -> ctypes.CDLL:
         L.hcspmm_spmm_gemm.argtypes = [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32,
                                        _int, _vp, _i64, _i32, _vp, _i64, _vp, _i64, _vp]
         L.hcspmm_gemm_tf32.argtypes = [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _i64, _vp]
+        L.hcspmm_loa_workspace_bytes.restype = _sz
+        L.hcspmm_loa_workspace_bytes.argtypes = [_i32, _i64, _i32]
+        L.hcspmm_loa_reorder.argtypes = [_vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]
         L.hcspmm_graph_create.argtypes = [_vp, _vp, _i32, _i64, _i32, _int, ctypes.POINTER(_vp)]
         L.hcspmm_graph_spmm_host.argtypes = [_vp, _vp, _i32, _int, _vp]
         L.hcspmm_graph_get_preprocess.argtypes = [_vp, _vp, _vp, _vp, _vp]
@@ -141,6 +144,49 @@ def gemm_tf32(a: torch.Tensor, b: torch.Tensor):
                                       b.shape[1], _ptr(out), out.stride(0), _stream(a)),
                "hcspmm_gemm_tf32")
     return out
+
+
+def csc_of(rowptr: torch.Tensor, colidx: torch.Tensor):
+    """CSC of a device CSR with ascending row lists -- what LOI.cpp's main builds (:826-841)."""
+    n = rowptr.numel() - 1
+    rows = torch.repeat_interleave(torch.arange(n, device=rowptr.device), (rowptr[1:] - rowptr[:-1]).long())
+    key = torch.sort(colidx.long() * n + rows).values
+    cnt = torch.bincount(torch.div(key, n, rounding_mode="floor"), minlength=n)
+    rp_in = torch.zeros(n + 1, dtype=torch.int64, device=rowptr.device)
+    rp_in[1:] = torch.cumsum(cnt, 0)
+    return rp_in.to(torch.int32), (key % n).to(torch.int32)
+
+
+def loa_reorder(rowptr: torch.Tensor, colidx: torch.Tensor):
+    """hcspmm_loa_reorder on a device CSR -> (perm int32[n], block_sizes int32[n_blocks], n_full)."""
+    assert rowptr.is_cuda and colidx.is_cuda and rowptr.dtype == torch.int32 and colidx.dtype == torch.int32
+    n, nnz = rowptr.numel() - 1, colidx.numel()
+    if n == 0:
+        return torch.zeros(0, dtype=torch.int32, device=rowptr.device), torch.zeros(0, dtype=torch.int32), 0
+    rp_in, ci_in = csc_of(rowptr, colidx)
+    maxdeg = int((rowptr[1:] - rowptr[:-1]).max())
+    with torch.cuda.device(rowptr.device):
+        o = dict(dtype=torch.int32, device=rowptr.device)
+        perm, bstart, counts = torch.empty(n, **o), torch.zeros(n + 1, **o), torch.zeros(2, **o)
+        nbytes = lib().hcspmm_loa_workspace_bytes(n, nnz, maxdeg)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=rowptr.device)
+        _check(lib().hcspmm_loa_reorder(_ptr(rowptr), _ptr(colidx), _ptr(rp_in), _ptr(ci_in), n, nnz, maxdeg,
+                                        _ptr(perm), _ptr(bstart), _ptr(counts), _ptr(ws), nbytes, _stream(rowptr)),
+               "hcspmm_loa_reorder")
+        nb, nf = (int(v) for v in counts.cpu())
+        sizes = (bstart[1:nb + 1] - bstart[:nb]).cpu()
+    return perm, sizes, nf
+
+
+def relabel(rowptr: torch.Tensor, colidx: torch.Tensor, perm: torch.Tensor):
+    """Apply an LOA permutation (perm[new] = old) symmetrically to rows and columns and re-canonicalise
+    the CSR -- the 'Reorder G using NRW' step the reference never shipped."""
+    from . import graphs
+    n = rowptr.numel() - 1
+    inv = torch.empty(n, dtype=torch.int64, device=rowptr.device)
+    inv[perm.long()] = torch.arange(n, device=rowptr.device)
+    rows = torch.repeat_interleave(torch.arange(n, device=rowptr.device), (rowptr[1:] - rowptr[:-1]).long())
+    return graphs.csr_from_pairs(inv[rows], inv[colidx.long()], n, symmetrize=False)
 
 
 class HostGraph:

@@ -67,6 +67,9 @@ const char *hcspmm_last_error(void);
  *   "slab"       feature-slab width in floats (0 = whole row); slabs are scheduled
  *                slab-major so that one slab of X stays L2-resident
  *   "vec8"       1 (default): 256-bit gathers when rows are 32-byte aligned; 0: 128-bit
+ *   "short_row"  rows with fewer than short_row * G entries (G = rows a warp can advance at once,
+ *                32 / lanes-per-row) are processed one lane group per row; 0 disables
+ *   "wpc"        16-row windows per CTA (1..8); 0 = chosen from nnz / windows
  * Returns the previous value, or -1 for an unknown key.                          */
 int hcspmm_set_tuning(const char *key, int value);
 
@@ -117,6 +120,24 @@ int hcspmm_spmm_gemm(const float *d_x, int64_t ldx, int32_t x_rows, const int32_
 int hcspmm_gemm_tf32(const float *d_a, int64_t lda, const float *d_b, int64_t ldb,
                      int32_t m, int32_t k, int32_t n, float *d_out, int64_t ldo,
                      void *stream);
+
+/* ---- A9: LOA vertex reordering ------------------------------------------------------
+ * Replaces reorder_plus_new_direct + the output loop of main, /root/reference/LOI.cpp:660-805,
+ * 873-891 (the reference runs it offline on the CPU).  Inputs: the CSR and the CSC of the same
+ * graph (the reference function takes both: row_id/col_id and row_id_in/col_id_in, :660); the
+ * CSC lists must be ascending, as main builds them (:826-841); CSR rows must be sorted.
+ * max_degree = largest CSR row length (sizes the scratch).  Outputs, bit-exact with the reference:
+ *   d_perm[n]         vertex ids in the order main writes reorder_direct.txt: full 16-blocks in
+ *                     creation order, then partial blocks, then never-visited vertices ascending
+ *   d_block_start[n+1] (optional) prefix offsets of the blocks in creation order
+ *   d_counts[2]       {number of blocks, number of full blocks (what main prints)}
+ * The greedy is sequential across blocks by definition; the kernel is one persistent CTA that
+ * parallelises the scan / arg-max / set-merge inside each of the 15 steps of a block.          */
+size_t hcspmm_loa_workspace_bytes(int32_t n, int64_t nnz, int32_t max_degree);
+int hcspmm_loa_reorder(const int32_t *d_rowptr, const int32_t *d_colidx, const int32_t *d_rowptr_in,
+                       const int32_t *d_colidx_in, int32_t n, int64_t nnz, int32_t max_degree,
+                       int32_t *d_perm, int32_t *d_block_start, int32_t *d_counts, void *d_workspace,
+                       size_t workspace_bytes, void *stream);
 
 /* ---- host-buffer convenience (what a non-torch caller binds) ----------------------
  * A graph handle owns device copies of the CSR and of the preprocessing products.

@@ -113,6 +113,30 @@ def test_spmm_feature_slabs(capi, slab):
         assert rel_fro(got, want) <= 2e-5
 
 
+@pytest.mark.parametrize("wpc", [1, 2, 8])
+@pytest.mark.parametrize("short_row", [0, 8, 100000])
+def test_spmm_windows_per_cta_and_group_rows(capi, wpc, short_row):
+    """Low-degree machinery: several windows per CTA, one lane group per short row; mixed labels."""
+    for name in ("ring3_256", "rmat_1000", "holes_777", "sbm_1024"):
+        rp, ci = GRAPHS[name]
+        n = rp.size - 1
+        bp, etc, etr, _ = oracle.preprocess(ci, rp, 0)
+        ht = np.zeros(oracle.num_windows(n), np.int32)
+        ht[2::5] = 1
+        for dim in (8, 32, 64, 128, 256):
+            x = xmat(n, dim, seed=dim + wpc)
+            want = oracle.spmm(rp, ci, x, hybrid_type=ht, precision=0)
+            o1, o2 = capi.set_tuning("wpc", wpc), capi.set_tuning("short_row", short_row)
+            try:
+                got = capi.spmm(dev(x), dev(rp), dev(ci), dev(bp), dev(etc), dev(etr), dev(ht)).cpu().numpy()
+                acc = dev(np.ones_like(want))
+                capi.spmm(dev(x), dev(rp), dev(ci), dev(bp), dev(etc), dev(etr), dev(ht), out=acc, accumulate=True)
+            finally:
+                capi.set_tuning("wpc", o1), capi.set_tuning("short_row", o2)
+            assert rel_fro(got, want) <= 2e-5, (name, dim)
+            assert rel_fro(acc.cpu().numpy(), want + 1.0) <= 2e-5, (name, dim)
+
+
 def test_spmm_strided_and_unaligned(capi):
     rp, ci = GRAPHS["rmat_1000"]
     big = dev(xmat(1000, 80, seed=9))
