@@ -17,7 +17,7 @@ void set_error(const char *fmt, ...) {
 }
 
 Tuning &tuning() {
-  static Tuning t = {1024, 0, 1, 1, 0};
+  static Tuning t = {1024, 0, 1, 1, 0, 0, 1};
   return t;
 }
 
@@ -30,6 +30,9 @@ int launch_spmm(const float *, int64_t, int32_t, const int32_t *, const int32_t 
 int launch_gemm_tf32(const float *, int64_t, const float *, int64_t, int32_t, int32_t, int32_t,
                      float *, int64_t, cudaStream_t);
 
+bool umma_gemm_supported(const float *, int64_t, const float *, int64_t, int32_t, int32_t);
+int launch_umma_gemm(const float *, int64_t, const float *, int64_t, int32_t, int32_t, int32_t, float *, int64_t,
+                     int *, cudaStream_t);
 size_t loa_workspace_bytes(int32_t n, int64_t nnz, int32_t max_degree);
 int launch_loa(const int32_t *, const int32_t *, const int32_t *, const int32_t *, int32_t, int64_t, int32_t,
                int32_t *, int32_t *, int32_t *, void *, size_t, cudaStream_t);
@@ -69,6 +72,8 @@ int hcspmm_set_tuning(const char *key, int value) {
   else if (key && !strcmp(key, "vec8")) slot = &tuning().vec8;
   else if (key && !strcmp(key, "short_row")) slot = &tuning().short_row;
   else if (key && !strcmp(key, "wpc")) slot = &tuning().wpc;
+  else if (key && !strcmp(key, "umma")) slot = &tuning().umma;
+  else if (key && !strcmp(key, "pad_odd")) slot = &tuning().pad_odd;
   if (!slot) return -1;
   int old = *slot;
   *slot = value;
@@ -98,9 +103,33 @@ int hcspmm_spmm(const float *d_x, int64_t ldx, int32_t x_rows, const int32_t *d_
                      ldy, (cudaStream_t)stream);
 }
 
+static int *umma_error_flag() {
+  static thread_local int *flag[16] = {nullptr};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 16) return nullptr;
+  if (!flag[dev]) {
+    if (cudaMalloc(&flag[dev], sizeof(int)) != cudaSuccess) return nullptr;
+    cudaMemset(flag[dev], 0, sizeof(int));
+  }
+  return flag[dev];
+}
+
 int hcspmm_gemm_tf32(const float *d_a, int64_t lda, const float *d_b, int64_t ldb, int32_t m,
                      int32_t k, int32_t n, float *d_out, int64_t ldo, void *stream) {
+  if (tuning().umma && d_a && d_b && d_out && m > 0 && n > 0 && lda >= k && ldb >= n && ldo >= n &&
+      umma_gemm_supported(d_a, lda, d_b, ldb, k, n))
+    return launch_umma_gemm(d_a, lda, d_b, ldb, m, k, n, d_out, ldo, umma_error_flag(), (cudaStream_t)stream);
   return launch_gemm_tf32(d_a, lda, d_b, ldb, m, k, n, d_out, ldo, (cudaStream_t)stream);
+}
+
+int hcspmm_debug_umma_error(void) {
+  int *f = umma_error_flag();
+  if (!f) return -1;
+  int v = 0;
+  if (cudaMemcpy(&v, f, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  if (v) cudaMemset(f, 0, sizeof(int));
+  return v;
 }
 
 int hcspmm_spmm_gemm(const float *d_x, int64_t ldx, int32_t x_rows, const int32_t *d_rowptr,
@@ -117,8 +146,7 @@ int hcspmm_spmm_gemm(const float *d_x, int64_t ldx, int32_t x_rows, const int32_
                        d_edge_to_row, d_hybrid_type, n_rows, nnz, dim, precision, 0, d_z, ldz,
                        (cudaStream_t)stream);
   if (rc) return rc;
-  return launch_gemm_tf32(d_z, ldz, d_w, ldw, n_rows, dim, hidden, d_out, ldo,
-                          (cudaStream_t)stream);
+  return hcspmm_gemm_tf32(d_z, ldz, d_w, ldw, n_rows, dim, hidden, d_out, ldo, stream);
 }
 
 size_t hcspmm_loa_workspace_bytes(int32_t n, int64_t nnz, int32_t max_degree) {

@@ -21,6 +21,8 @@ struct Tuning {
   int vec8;      // use 256-bit gathers when alignment allows (1) or always 128-bit (0)
   int short_row; // rows shorter than short_row * (32 / lanes-per-row) go one lane group per row
   int wpc;       // windows per CTA, 0 = automatic from the mean window population
+  int umma;      // 1: tcgen05/TMEM kernels (Update GEMM, dense super-windows) where applicable
+  int pad_odd;   // 1: large operands with odd width / unaligned rows run on padded copies
 };
 Tuning &tuning();
 

@@ -71,17 +71,21 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *warp_buf, int &t
   return wexc + inc - v;
 }
 
-// row of edge e inside the window: largest r in [0,15] with rp[r] <= e
+// row of edge e inside the window: largest r in [0,H) with rp[r] <= e   (H a power of two)
+template <int H>
 __device__ __forceinline__ int row_of_edge(const int *rp, int e) {
-  int lo = 0, hi = BLK_H;
+  int lo = 0, hi = H;
 #pragma unroll
-  for (int s = 0; s < 4; ++s) {
+  for (int s = 1; s < H; s <<= 1) {
     int mid = (lo + hi) >> 1;
     if (rp[mid] <= e) lo = mid; else hi = mid;
   }
   return lo;
 }
 
+// H = rows per window: 16 for the reference's row windows (BLK_H); 128 for the super-windows of the
+// tcgen05 dense plan, where only the ranks and the distinct-column counts are used.
+template <int H>
 __global__ void __launch_bounds__(SMALL_THREADS)
 preprocess_small_kernel(const int *__restrict__ colidx, const int *__restrict__ rowptr,
                         int n_rows, int n_windows, int mode, int *__restrict__ block_partition,
@@ -89,19 +93,20 @@ preprocess_small_kernel(const int *__restrict__ colidx, const int *__restrict__ 
                         int *__restrict__ hybrid_type, int *__restrict__ large_list,
                         int *__restrict__ large_count) {
   __shared__ unsigned long long keys[SORT_CAP];
-  __shared__ int rp[BLK_H + 1];
+  __shared__ int rp[H + 1];
   __shared__ int warp_buf[32];
   const int w = blockIdx.x, tid = threadIdx.x;
-  const int r0 = w * BLK_H;
-  if (tid <= BLK_H) rp[tid] = (r0 < n_rows) ? rowptr[min(r0 + tid, n_rows)] : 0;
+  const int r0 = w * H;
+  if (tid <= H) rp[tid] = (r0 < n_rows) ? rowptr[min(r0 + tid, n_rows)] : 0;
   __syncthreads();
-  const int e0 = rp[0], e1 = rp[BLK_H];
+  const int e0 = rp[0], e1 = rp[H];
   const int ne = e1 - e0;
   if (ne <= 0) {  // reference returns before writing (:252-253); defined as 0 here
     if (tid == 0) { block_partition[w] = 0; hybrid_type[w] = 0; }
     return;
   }
-  for (int e = e0 + tid; e < e1; e += SMALL_THREADS) edge_to_row[e] = r0 + row_of_edge(rp, e);
+  if (edge_to_row != nullptr)
+    for (int e = e0 + tid; e < e1; e += SMALL_THREADS) edge_to_row[e] = r0 + row_of_edge<H>(rp, e);
   if (ne > SORT_CAP) {
     if (tid == 0) large_list[atomicAdd(large_count, 1)] = w;
     return;
@@ -146,6 +151,7 @@ preprocess_small_kernel(const int *__restrict__ colidx, const int *__restrict__ 
 
 // Persistent CTAs over the work list of windows with more than SORT_CAP edges.
 // Dynamic shared memory: bitmap[chunk_words] + prefix[chunk_words].
+template <int H>
 __global__ void __launch_bounds__(LARGE_THREADS)
 preprocess_large_kernel(const int *__restrict__ colidx, const int *__restrict__ rowptr,
                         int n_rows, int mode, int chunk_words, int *__restrict__ block_partition,
@@ -161,8 +167,8 @@ preprocess_large_kernel(const int *__restrict__ colidx, const int *__restrict__ 
   const int chunk_bits = chunk_words * 32;
   for (int li = blockIdx.x; li < n_large; li += gridDim.x) {
     const int w = large_list[li];
-    const int r0 = w * BLK_H;
-    const int e0 = rowptr[r0], e1 = rowptr[min(r0 + BLK_H, n_rows)];
+    const int r0 = w * H;
+    const int e0 = rowptr[r0], e1 = rowptr[min(r0 + H, n_rows)];
     if (tid == 0) { s_min = 0x7fffffff; s_max = -1; }
     __syncthreads();
     int mn = 0x7fffffff, mx = -1;
@@ -220,6 +226,11 @@ preprocess_large_kernel(const int *__restrict__ colidx, const int *__restrict__ 
   }
 }
 
+template <int H>
+static int launch_preprocess_h(const int32_t *colidx, const int32_t *rowptr, int32_t n_rows, int32_t n_windows,
+                               int mode, int32_t *bp, int32_t *etc, int32_t *etr, int32_t *ht, void *ws,
+                               cudaStream_t stream);
+
 size_t preprocess_workspace_bytes(int32_t n_rows, int64_t /*nnz*/) {
   size_t w = ((size_t)n_rows + BLK_H - 1) / BLK_H;
   return (w + 64) * sizeof(int);  // [0] = work-list counter, [16..] = work list
@@ -248,11 +259,18 @@ int launch_preprocess(const int32_t *colidx, const int32_t *rowptr, int32_t n_ro
               preprocess_workspace_bytes(n_rows, nnz));
     return HCSPMM_E_WORKSPACE;
   }
+  return launch_preprocess_h<BLK_H>(colidx, rowptr, n_rows, n_windows, mode, bp, etc, etr, ht, ws, stream);
+}
+
+template <int H>
+static int launch_preprocess_h(const int32_t *colidx, const int32_t *rowptr, int32_t n_rows, int32_t n_windows,
+                               int mode, int32_t *bp, int32_t *etc, int32_t *etr, int32_t *ht, void *ws,
+                               cudaStream_t stream) {
   int *counter = reinterpret_cast<int *>(ws);
   int *list = counter + 16;
   cudaError_t err = cudaMemsetAsync(counter, 0, 16 * sizeof(int), stream);
   if (err != cudaSuccess) { set_error("preprocess: memset: %s", cudaGetErrorString(err)); return (int)err; }
-  preprocess_small_kernel<<<n_windows, SMALL_THREADS, 0, stream>>>(
+  preprocess_small_kernel<H><<<n_windows, SMALL_THREADS, 0, stream>>>(
       colidx, rowptr, n_rows, n_windows, mode, bp, etc, etr, ht, list, counter);
   err = cudaGetLastError();
   if (err != cudaSuccess) { set_error("preprocess_small launch: %s", cudaGetErrorString(err)); return (int)err; }
@@ -261,19 +279,25 @@ int launch_preprocess(const int32_t *colidx, const int32_t *rowptr, int32_t n_ro
   chunk_words = ((chunk_words + 511) / 512) * 512;
   if (chunk_words > 16384) chunk_words = 16384;
   size_t smem = (size_t)chunk_words * 8;
-  cudaFuncSetAttribute(preprocess_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       16384 * 8);
+  cudaFuncSetAttribute(preprocess_large_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int per_sm = smem > 96 * 1024 ? 1 : (smem > 64 * 1024 ? 2 : 3);
   int grid = sms * per_sm;
   if (grid > n_windows) grid = n_windows;
-  preprocess_large_kernel<<<grid, LARGE_THREADS, smem, stream>>>(
+  preprocess_large_kernel<H><<<grid, LARGE_THREADS, smem, stream>>>(
       colidx, rowptr, n_rows, mode, chunk_words, bp, etc, ht, list, counter);
   err = cudaGetLastError();
   if (err != cudaSuccess) { set_error("preprocess_large launch: %s", cudaGetErrorString(err)); return (int)err; }
   return 0;
+}
+
+// ranks and ceil(U/8) per 128-row super-window (dense plan, dense.cu)
+int launch_preprocess_super(const int32_t *colidx, const int32_t *rowptr, int32_t n_rows, int32_t n_super,
+                            int32_t *bp128, int32_t *etc128, int32_t *ht_scratch, void *ws, cudaStream_t stream) {
+  return launch_preprocess_h<128>(colidx, rowptr, n_rows, n_super, HCSPMM_CLASSIFIER_ALL_CUDA, bp128, etc128,
+                                  nullptr, ht_scratch, ws, stream);
 }
 
 }  // namespace hcspmm

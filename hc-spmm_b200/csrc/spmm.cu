@@ -397,7 +397,12 @@ __global__ void __launch_bounds__(CTA_THREADS, HCSPMM_MIN_CTAS) spmm_hybrid_kern
   for (int i = 0; i < NV; ++i) active[i] = (g + i * LPE) < nvec;
   const bool all_active = nvec == LPE * NV;
   const float *xlane = p.x + feat0 + g * VW;
-  const int short_row = G > 1 ? p.short_row : 0;
+  // phase A is for CTAs made of short rows only (mean population below p.short_row = knob * G);
+  // in a mixed CTA the idle lane groups would cost more than the one-warp-per-row bookkeeping
+  const int e_cta = rp[rows_here] - rp[0];
+  const int short_row = (G > 1 && p.short_row > 0 && e_cta < rows_here * p.short_row &&
+                         2 * rows_here >= CTA_WARPS * G)   // enough rows to occupy the lane groups
+                            ? 4 * p.short_row : 0;
 
   // phase A: short rows, one lane group per row, static round-robin over the CTA's rows
   if (short_row > 0) {
@@ -533,6 +538,24 @@ __global__ void __launch_bounds__(CTA_THREADS) spmm_scalar_kernel(const SpmmPara
   }
 }
 
+// dst[r, 0..dpad) = src[r, 0..dim) zero-extended (dst dense with leading dim dpad)
+__global__ void pad_rows_kernel(const float *__restrict__ src, long long lds, int dim, float *__restrict__ dst,
+                                int dpad, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long r = i / dpad;
+  const int c = (int)(i - r * dpad);
+  dst[i] = c < dim ? __ldg(src + r * lds + c) : 0.f;
+}
+__global__ void unpad_rows_kernel(const float *__restrict__ src, int dpad, int dim, float *__restrict__ dst,
+                                  long long ldd, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long r = i / dim;
+  const int c = (int)(i - r * dim);
+  dst[r * ldd + c] = src[r * dpad + c];
+}
+
 static size_t hybrid_smem_bytes(int S, bool tc) {
   size_t cuda_path = (size_t)CTA_WARPS * S * sizeof(float);
   size_t tc_path = tc ? (size_t)(2 * (UCAP + KC) + NSTAGE * KC * (S + 8)) * sizeof(float) : 0;
@@ -592,6 +615,49 @@ int launch_spmm(const float *x, int64_t ldx, int32_t x_rows, const int32_t *rowp
   const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0 &&
                    (ldx & 3) == 0 && (ldy & 3) == 0 && (dim & 3) == 0;
   cudaError_t err;
+  if (!vec && (long long)n_rows * dim >= (1 << 20) && tuning().pad_odd) {
+    // Large operand with an odd width / unaligned rows (e.g. dim = 47 classes): run the vector
+    // kernel on 32-byte-aligned padded copies instead of the one-warp-per-row scalar kernel.
+    // Two streaming copies cost 2 * (x_rows + n_rows) * dim * 4 bytes -- small next to the gather.
+    const int dpad = (dim + 7) / 8 * 8;
+    float *xp = nullptr, *yp = nullptr;
+    {
+      // keep freed blocks in the stream-ordered pool (the default threshold returns them to the
+      // driver at every synchronisation, which makes the next call pay for a fresh allocation)
+      static bool pool_tuned[64] = {false};
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (dev >= 0 && dev < 64 && !pool_tuned[dev]) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+          unsigned long long keep = ~0ull;
+          cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        pool_tuned[dev] = true;
+      }
+    }
+    err = cudaMallocAsync(&xp, sizeof(float) * (size_t)x_rows * dpad, stream);
+    if (err == cudaSuccess) err = cudaMallocAsync(&yp, sizeof(float) * (size_t)n_rows * dpad, stream);
+    if (err != cudaSuccess) {
+      if (xp) cudaFreeAsync(xp, stream);
+      set_error("spmm: cudaMallocAsync: %s", cudaGetErrorString(err));
+      return (int)err;
+    }
+    const long long nx = (long long)x_rows * dpad, ny = (long long)n_rows * dpad;
+    pad_rows_kernel<<<(unsigned)((nx + 255) / 256), 256, 0, stream>>>(x, ldx, dim, xp, dpad, nx);
+    if (accumulate) pad_rows_kernel<<<(unsigned)((ny + 255) / 256), 256, 0, stream>>>(y, ldy, dim, yp, dpad, ny);
+    int rc = launch_spmm(xp, dpad, x_rows, rowptr, colidx, bp, etc, etr, ht, n_rows, nnz, dpad, precision,
+                         accumulate, yp, dpad, stream);
+    if (rc == 0) {
+      unpad_rows_kernel<<<(unsigned)(((long long)n_rows * dim + 255) / 256), 256, 0, stream>>>(
+          yp, dpad, dim, y, ldy, (long long)n_rows * dim);
+      err = cudaGetLastError();
+      if (err != cudaSuccess) { set_error("spmm pad path: %s", cudaGetErrorString(err)); rc = (int)err; }
+    }
+    cudaFreeAsync(xp, stream);
+    cudaFreeAsync(yp, stream);
+    return rc;
+  }
   if (!vec) {
     p.slab = dim;
     spmm_scalar_kernel<<<(n_rows + CTA_WARPS - 1) / CTA_WARPS, CTA_THREADS, 0, stream>>>(p);

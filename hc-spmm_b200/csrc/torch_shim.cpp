@@ -247,7 +247,7 @@ bool set_bug_compat(bool on) {
 
 int64_t set_tuning(const std::string &key, int64_t value) {
   int old = hcspmm_set_tuning(key.c_str(), (int)value);
-  TORCH_CHECK(old != -1 || key == "slab" || key == "long_row" || key == "vec8" || key == "short_row" || key == "wpc",
+  TORCH_CHECK(old != -1 || key == "slab" || key == "long_row" || key == "vec8" || key == "short_row" || key == "wpc" || key == "umma" || key == "pad_odd",
               "unknown tuning key '", key, "'");
   return old;
 }

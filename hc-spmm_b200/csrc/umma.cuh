@@ -81,14 +81,22 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 //   [0,14)  start address >> 4        [16,30) leading-dimension byte offset >> 4
 //   [32,46) stride-dimension byte offset >> 4        [46,48) version = 1 (Blackwell)
 //   [49,52) base offset = 0 (atoms are 1024-byte aligned)   [61,64) layout: 2 = SWIZZLE_128B
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//           1 = SWIZZLE_128B_BASE32B -- the ONLY layout the hardware accepts for an MN-major
+//           operand with 32-bit (TF32) elements (measured: a plain SWIZZLE_128B MN-major TF32
+//           operand multiplies as all-zero; scripts/debug/umma_probe.cu)
+constexpr uint32_t LAYOUT_SW128 = 2, LAYOUT_SW128_BASE32B = 1;
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout_type << 61;
   return d;
+}
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return make_desc(smem_addr, lbo_bytes, sbo_bytes, LAYOUT_SW128);
 }
 // Instruction descriptor, kind::tf32, FP32 accumulate:
 //   [4,6) D format: 1 = F32   [7,10) A format: 2 = TF32   [10,13) B format: 2 = TF32
@@ -123,12 +131,17 @@ __device__ __forceinline__ void mma_commit(uint64_t *bar) {
 __device__ __forceinline__ uint32_t kmajor_off(int r, int k /* 0..31 */) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((k >> 2) ^ (r & 7)) & 7) << 4) + ((k & 3) << 2));
 }
-// MN-major operand (B, rows = k, contiguous along n): element (k, n): n-atom = n / 32 at stride LBO,
-// k-group = k / 8 at stride SBO, inside the atom row = k % 8, 16-byte chunk = (n % 32) / 4.
+// MN-major TF32 operand (B: rows = k, contiguous along n -- how X / W rows lie in memory), layout
+// SWIZZLE_128B_BASE32B: atom = 4 k-rows x 128 B (32 floats along n), Swizzle<2,5,2>: the 32-byte
+// chunk index inside a row is XORed with the row index (k % 4).  n-atoms at stride LBO, k-atoms
+// (4 rows) at stride SBO; one K = 8 MMA consumes two k-atoms.  Atoms start on 512-byte boundaries.
+// Offset of the 16-byte piece holding features [4*chunk, 4*chunk + 4) of row k:
 __device__ __forceinline__ uint32_t mnmajor_chunk_off(int k, int chunk /* 16-byte chunk along n */,
                                                       uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  const int natom = chunk >> 3, c = chunk & 7, kr = k & 7;
-  return (uint32_t)(k >> 3) * sbo_bytes + (uint32_t)natom * lbo_bytes + (uint32_t)(kr * 128 + ((c ^ kr) << 4));
+  const int natom = chunk >> 3, kr = k & 3;
+  const uint32_t b = (uint32_t)(chunk & 7) << 4;          // byte offset inside the 128-byte row
+  return (uint32_t)(k >> 2) * sbo_bytes + (uint32_t)natom * lbo_bytes + (uint32_t)(kr * 128) +
+         ((((b >> 5) ^ (uint32_t)kr) & 3u) << 5) + (b & 31u);
 }
 
 }  // namespace umma

@@ -20,7 +20,7 @@ PRECISIONS = {"tf32": 0, "tf32x2": 1, "fp32": 2}
 EXPORTS = [
     "hcspmm_version", "hcspmm_last_error", "hcspmm_set_tuning",
     "hcspmm_preprocess_workspace_bytes", "hcspmm_preprocess", "hcspmm_spmm", "hcspmm_spmm_gemm",
-    "hcspmm_gemm_tf32", "hcspmm_loa_workspace_bytes", "hcspmm_loa_reorder", "hcspmm_graph_create", "hcspmm_graph_spmm_host",
+    "hcspmm_gemm_tf32", "hcspmm_debug_umma_error", "hcspmm_loa_workspace_bytes", "hcspmm_loa_reorder", "hcspmm_graph_create", "hcspmm_graph_spmm_host",
     "hcspmm_graph_get_preprocess", "hcspmm_graph_destroy",
 ]
 

@@ -70,6 +70,9 @@ const char *hcspmm_last_error(void);
  *   "short_row"  rows with fewer than short_row * G entries (G = rows a warp can advance at once,
  *                32 / lanes-per-row) are processed one lane group per row; 0 disables
  *   "wpc"        16-row windows per CTA (1..8); 0 = chosen from nnz / windows
+ *   "pad_odd"    1 (default): large operands whose width is not a multiple of 4 (or whose rows
+ *                are unaligned) run through zero-padded aligned copies; 0: scalar kernel
+ *   "umma"       1: tcgen05 / TMEM kernels where applicable (Update GEMM); 0: mma.sync kernels
  * Returns the previous value, or -1 for an unknown key.                          */
 int hcspmm_set_tuning(const char *key, int value);
 
@@ -120,6 +123,10 @@ int hcspmm_spmm_gemm(const float *d_x, int64_t ldx, int32_t x_rows, const int32_
 int hcspmm_gemm_tf32(const float *d_a, int64_t lda, const float *d_b, int64_t ldb,
                      int32_t m, int32_t k, int32_t n, float *d_out, int64_t ldo,
                      void *stream);
+
+/* 1 if a tcgen05 kernel reported a barrier timeout since the last call (synchronises the device),
+ * 0 if not, -1 on error.  Debug / test aid.                                              */
+int hcspmm_debug_umma_error(void);
 
 /* ---- A9: LOA vertex reordering ------------------------------------------------------
  * Replaces reorder_plus_new_direct + the output loop of main, /root/reference/LOI.cpp:660-805,

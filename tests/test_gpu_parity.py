@@ -262,3 +262,39 @@ def test_host_graph_roundtrip(capi):
     y = g.spmm(x)
     assert rel_fro(y.numpy(), oracle.spmm(rp, ci, x.numpy(), hybrid_type=want_pre[3], precision=0)) <= 2e-5
     g.close()
+
+
+# ---- tcgen05 / TMEM Update GEMM ---------------------------------------------------------------
+@pytest.mark.parametrize("m,k,n", [(128, 32, 32), (128, 64, 256), (1000, 128, 128), (513, 100, 48), (4096, 256, 256),
+                                   (300, 36, 16), (2000, 128, 320), (77, 8, 4)])
+def test_gemm_tcgen05(capi, m, k, n):
+    a, b = xmat(m, k, 1), xmat(k, n, 2)
+    old = capi.set_tuning("umma", 1)
+    try:
+        got = capi.gemm_tf32(dev(a), dev(b)).cpu().numpy()
+        assert capi.lib().hcspmm_debug_umma_error() == 0, "tcgen05 kernel reported a barrier timeout"
+    finally:
+        capi.set_tuning("umma", old)
+    assert rel_fro(got, oracle.gemm(a, b, tf32=True)) <= 1e-4
+
+
+def test_spmm_odd_width_large_uses_padded_copies(capi):
+    """dim = 47 on a graph large enough for the pad path (n_rows * dim >= 2^20), with a hub row."""
+    from hcspmm import graphs as G
+    rp, ci = G.rmat(40000, 600000, seed=9)
+    rp, ci = rp.numpy(), ci.numpy()
+    for dim in (47, 30):
+        x = xmat(40000, dim, seed=dim)
+        want = oracle.spmm(rp, ci, x, precision=1)
+        got = capi.spmm(dev(x), dev(rp), dev(ci), precision="fp32").cpu().numpy()
+        assert rel_fro(got, want) <= TOL_FP32
+        y0 = xmat(40000, dim, seed=1)
+        out = dev(y0)
+        capi.spmm(dev(x), dev(rp), dev(ci), out=out, accumulate=True, precision="fp32")
+        assert rel_fro(out.cpu().numpy(), want + y0) <= TOL_FP32
+        old = capi.set_tuning("pad_odd", 0)
+        try:
+            got = capi.spmm(dev(x), dev(rp), dev(ci), precision="fp32").cpu().numpy()
+        finally:
+            capi.set_tuning("pad_odd", old)
+        assert rel_fro(got, want) <= TOL_FP32
