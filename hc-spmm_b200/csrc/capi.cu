@@ -33,6 +33,16 @@ int launch_gemm_tf32(const float *, int64_t, const float *, int64_t, int32_t, in
 bool umma_gemm_supported(const float *, int64_t, const float *, int64_t, int32_t, int32_t);
 int launch_umma_gemm(const float *, int64_t, const float *, int64_t, int32_t, int32_t, int32_t, float *, int64_t,
                      int *, cudaStream_t);
+size_t dense_plan_workspace_bytes(int32_t n_rows, int64_t nnz);
+int dense_plan_count(const int32_t *, const int32_t *, const int32_t *, int32_t, int64_t, int, void *, size_t, int32_t *,
+                     cudaStream_t);
+size_t dense_plan_words(int32_t n_rows, int32_t n_dense, int64_t total_cols);
+int dense_plan_fill(const int32_t *, const int32_t *, int32_t, int64_t, void *, int32_t, int64_t, int32_t *, size_t,
+                    cudaStream_t);
+bool dense_supported(const float *, const float *, int64_t, int32_t);
+int launch_spmm_dense(const float *, int64_t, int32_t, int32_t, int32_t, const int32_t *, int32_t, int64_t, int, float *,
+                      int64_t, float *, int *, cudaStream_t);
+const int32_t *dense_plan_labels(const int32_t *, int32_t, int32_t, int64_t);
 size_t loa_workspace_bytes(int32_t n, int64_t nnz, int32_t max_degree);
 int launch_loa(const int32_t *, const int32_t *, const int32_t *, const int32_t *, int32_t, int64_t, int32_t,
                int32_t *, int32_t *, int32_t *, void *, size_t, cudaStream_t);
@@ -121,6 +131,52 @@ int hcspmm_gemm_tf32(const float *d_a, int64_t lda, const float *d_b, int64_t ld
       umma_gemm_supported(d_a, lda, d_b, ldb, k, n))
     return launch_umma_gemm(d_a, lda, d_b, ldb, m, k, n, d_out, ldo, umma_error_flag(), (cudaStream_t)stream);
   return launch_gemm_tf32(d_a, lda, d_b, ldb, m, k, n, d_out, ldo, (cudaStream_t)stream);
+}
+
+size_t hcspmm_dense_plan_workspace_bytes(int32_t n_rows, int64_t nnz) { return dense_plan_workspace_bytes(n_rows, nnz); }
+
+int hcspmm_dense_plan_count(const int32_t *d_colidx, const int32_t *d_rowptr, const int32_t *d_hybrid_type,
+                            int32_t n_rows, int64_t nnz, int min_reuse_x2, void *d_workspace, size_t workspace_bytes,
+                            int32_t *h_counts, void *stream) {
+  if (!h_counts) { set_error("dense_plan_count: null h_counts"); return HCSPMM_E_INVALID; }
+  return dense_plan_count(d_colidx, d_rowptr, d_hybrid_type, n_rows, nnz, min_reuse_x2, d_workspace, workspace_bytes,
+                          h_counts, (cudaStream_t)stream);
+}
+
+size_t hcspmm_dense_plan_words(int32_t n_rows, int32_t n_dense, int64_t total_cols) {
+  return dense_plan_words(n_rows, n_dense, total_cols);
+}
+
+int hcspmm_dense_plan_fill(const int32_t *d_colidx, const int32_t *d_edge_to_row, int32_t n_rows, int64_t nnz,
+                           void *d_workspace, int32_t n_dense, int64_t total_cols, int32_t *d_plan, size_t plan_words,
+                           void *stream) {
+  if (!d_colidx || !d_edge_to_row || !d_workspace || !d_plan) { set_error("dense_plan_fill: null pointer argument"); return HCSPMM_E_INVALID; }
+  return dense_plan_fill(d_colidx, d_edge_to_row, n_rows, nnz, d_workspace, n_dense, total_cols, d_plan, plan_words,
+                         (cudaStream_t)stream);
+}
+
+int hcspmm_spmm_plan(const float *d_x, int64_t ldx, int32_t x_rows, const int32_t *d_rowptr,
+                     const int32_t *d_colidx, const int32_t *d_block_partition,
+                     const int32_t *d_edge_to_column, const int32_t *d_edge_to_row,
+                     const int32_t *d_hybrid_type, int32_t n_rows, int64_t nnz, int32_t dim,
+                     int precision, int accumulate, float *d_y, int64_t ldy, const int32_t *d_plan,
+                     int32_t n_dense, int64_t total_cols, void *stream) {
+  const bool dense = d_plan && n_dense > 0 && tuning().umma && precision == HCSPMM_PRECISION_TF32 && d_x && d_y &&
+                     (ldx & 3) == 0 && dense_supported(d_x, d_y, ldy, dim);
+  if (!dense)
+    return launch_spmm(d_x, ldx, x_rows, d_rowptr, d_colidx, d_block_partition, d_edge_to_column, d_edge_to_row,
+                       d_hybrid_type, n_rows, nnz, dim, precision, accumulate, d_y, ldy, (cudaStream_t)stream);
+  float *xr = nullptr;
+  cudaError_t err = cudaMallocAsync(&xr, sizeof(float) * (size_t)x_rows * dim, (cudaStream_t)stream);
+  if (err != cudaSuccess) { set_error("spmm_plan: cudaMallocAsync: %s", cudaGetErrorString(err)); return (int)err; }
+  int rc = launch_spmm_dense(d_x, ldx, x_rows, n_rows, dim, d_plan, n_dense, total_cols, accumulate, d_y, ldy, xr,
+                             umma_error_flag(), (cudaStream_t)stream);
+  if (rc == 0)
+    rc = launch_spmm(d_x, ldx, x_rows, d_rowptr, d_colidx, d_block_partition, d_edge_to_column, d_edge_to_row,
+                     dense_plan_labels(d_plan, n_rows, n_dense, total_cols), n_rows, nnz, dim, precision, accumulate,
+                     d_y, ldy, (cudaStream_t)stream);
+  cudaFreeAsync(xr, (cudaStream_t)stream);
+  return rc;
 }
 
 int hcspmm_debug_umma_error(void) {

@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(CTA_THREADS, HCSPMM_MIN_CTAS) spmm_hybrid_kern
   extern __shared__ __align__(16) float smem[];
   __shared__ int rp[BLK_H * MAX_WPC + 1];
   __shared__ int s_next;
-  __shared__ unsigned s_tcmask;
+  __shared__ unsigned s_tcmask, s_skipmask;
   constexpr int G = 32 / LPE;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int w0 = blockIdx.x * p.wpc;
@@ -361,19 +361,27 @@ __global__ void __launch_bounds__(CTA_THREADS, HCSPMM_MIN_CTAS) spmm_hybrid_kern
   for (int i = tid; i <= rows_here; i += CTA_THREADS) rp[i] = __ldg(p.rowptr + r0 + i);
   if (tid == 0) {
     s_next = 0;
-    unsigned m = 0;
-    if (p.ht != nullptr && p.precision != HCSPMM_PRECISION_FP32 && (S & 7) == 0)
-      for (int i = 0; i < nwin; ++i)
-        if (__ldg(p.ht + w0 + i) != 0) m |= 1u << i;
+    // label 1: tensor-core window (mma.sync path below); label 2: the window belongs to a dense
+    // super-window that the tcgen05 kernel (dense.cu) computes -- nothing to do here
+    unsigned m = 0, sk = 0;
+    if (p.ht != nullptr)
+      for (int i = 0; i < nwin; ++i) {
+        const int l = __ldg(p.ht + w0 + i);
+        if (l == 2) sk |= 1u << i;
+        else if (l != 0 && p.precision != HCSPMM_PRECISION_FP32 && (S & 7) == 0) m |= 1u << i;
+      }
     s_tcmask = m;
+    s_skipmask = sk;
   }
   __syncthreads();
-  const unsigned tcmask = s_tcmask;
+  const unsigned tcmask0 = s_tcmask;
+  const unsigned skipmask = s_skipmask;
+  if (skipmask == (nwin >= 32 ? 0xffffffffu : ((1u << nwin) - 1u))) return;
 
   // tensor-core windows of this CTA, one after another (CTA-wide)
-  if (tcmask != 0u) {
+  if (tcmask0 != 0u) {
     for (int i = 0; i < nwin; ++i) {
-      if (!((tcmask >> i) & 1u)) continue;
+      if (!((tcmask0 >> i) & 1u)) continue;
       const int e0 = rp[i * BLK_H], e1 = rp[min((i + 1) * BLK_H, rows_here)];
       if (e1 > e0) {
         tc_window<(LPE * NV * VW + 63) / 64>(p, w0 + i, e0, e1, feat0, S, smem);
@@ -388,8 +396,9 @@ __global__ void __launch_bounds__(CTA_THREADS, HCSPMM_MIN_CTAS) spmm_hybrid_kern
       }
       __syncthreads();
     }
-    if (tcmask == (nwin >= 32 ? 0xffffffffu : ((1u << nwin) - 1u))) return;
+    if ((tcmask0 | skipmask) == (nwin >= 32 ? 0xffffffffu : ((1u << nwin) - 1u))) return;
   }
+  const unsigned tcmask = tcmask0 | skipmask;   // windows the CUDA-core phases must not touch
 
   const int q = lane / LPE, g = lane % LPE;
   bool active[NV];

@@ -40,7 +40,7 @@ __device__ __forceinline__ float4 round_tf32x4(float4 v) {
   return v;
 }
 
-__global__ void __launch_bounds__(UG_THREADS, 1) umma_gemm_kernel(const UmmaGemmParams p) {
+__global__ void __launch_bounds__(UG_THREADS, 3) umma_gemm_kernel(const UmmaGemmParams p) {
   extern __shared__ __align__(1024) uint8_t ug_smem[];
   __shared__ __align__(8) uint64_t bar_empty[UG_STAGES];
   __shared__ __align__(8) uint64_t bar_done;
@@ -63,7 +63,9 @@ __global__ void __launch_bounds__(UG_THREADS, 1) umma_gemm_kernel(const UmmaGemm
     umma::mbar_init(&bar_done, 1);
     umma::fence_barrier_init();
   }
-  if (wid == 0) umma::tmem_alloc(&tmem_slot, 256);
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < bn) tmem_cols <<= 1;   // power of two >= the N tile: several CTAs share the SM's 512 columns
+  if (wid == 0) umma::tmem_alloc(&tmem_slot, tmem_cols);
   umma::tc_fence_before_sync();
   __syncthreads();
   umma::tc_fence_after_sync();
@@ -183,7 +185,7 @@ __global__ void __launch_bounds__(UG_THREADS, 1) umma_gemm_kernel(const UmmaGemm
   if (!ok && p.err) atomicExch(p.err, 1);
   umma::tc_fence_before_sync();
   __syncthreads();
-  if (wid == 0) umma::tmem_dealloc(tmem_d, 256);
+  if (wid == 0) umma::tmem_dealloc(tmem_d, tmem_cols);
 }
 
 bool umma_gemm_supported(const float *a, int64_t lda, const float *b, int64_t ldb, int32_t k, int32_t n) {

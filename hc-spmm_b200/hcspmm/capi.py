@@ -20,7 +20,8 @@ PRECISIONS = {"tf32": 0, "tf32x2": 1, "fp32": 2}
 EXPORTS = [
     "hcspmm_version", "hcspmm_last_error", "hcspmm_set_tuning",
     "hcspmm_preprocess_workspace_bytes", "hcspmm_preprocess", "hcspmm_spmm", "hcspmm_spmm_gemm",
-    "hcspmm_gemm_tf32", "hcspmm_debug_umma_error", "hcspmm_loa_workspace_bytes", "hcspmm_loa_reorder", "hcspmm_graph_create", "hcspmm_graph_spmm_host",
+    "hcspmm_gemm_tf32", "hcspmm_dense_plan_workspace_bytes", "hcspmm_dense_plan_count", "hcspmm_dense_plan_words",
+    "hcspmm_dense_plan_fill", "hcspmm_spmm_plan", "hcspmm_debug_umma_error", "hcspmm_loa_workspace_bytes", "hcspmm_loa_reorder", "hcspmm_graph_create", "hcspmm_graph_spmm_host",
     "hcspmm_graph_get_preprocess", "hcspmm_graph_destroy",
 ]
 
@@ -51,6 +52,14 @@ def lib() -> ctypes.CDLL:
         L.hcspmm_spmm_gemm.argtypes = [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32,
                                        _int, _vp, _i64, _i32, _vp, _i64, _vp, _i64, _vp]
         L.hcspmm_gemm_tf32.argtypes = [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _i64, _vp]
+        L.hcspmm_dense_plan_workspace_bytes.restype = _sz
+        L.hcspmm_dense_plan_workspace_bytes.argtypes = [_i32, _i64]
+        L.hcspmm_dense_plan_count.argtypes = [_vp, _vp, _vp, _i32, _i64, _int, _vp, _sz, _vp, _vp]
+        L.hcspmm_dense_plan_words.restype = _sz
+        L.hcspmm_dense_plan_words.argtypes = [_i32, _i32, _i64]
+        L.hcspmm_dense_plan_fill.argtypes = [_vp, _vp, _i32, _i64, _vp, _i32, _i64, _vp, _sz, _vp]
+        L.hcspmm_spmm_plan.argtypes = [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _int, _int,
+                                       _vp, _i64, _vp, _i32, _i64, _vp]
         L.hcspmm_loa_workspace_bytes.restype = _sz
         L.hcspmm_loa_workspace_bytes.argtypes = [_i32, _i64, _i32]
         L.hcspmm_loa_reorder.argtypes = [_vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]
@@ -118,6 +127,41 @@ def spmm(x: torch.Tensor, rowptr, colidx, bp=None, etc=None, etr=None, ht=None, 
                                  _ptr(etc), _ptr(etr), _ptr(ht), n, colidx.numel(), d, prec,
                                  1 if accumulate else 0, _ptr(out), out.stride(0), _stream(x)),
                "hcspmm_spmm")
+    return out
+
+
+class DensePlan:
+    """hcspmm_dense_plan_*: the tcgen05 dense super-window plan of a preprocessed graph."""
+
+    def __init__(self, rowptr: torch.Tensor, colidx: torch.Tensor, etr: torch.Tensor, ht: torch.Tensor,
+                 min_reuse: float = 2.0):
+        n, nnz = rowptr.numel() - 1, colidx.numel()
+        self.n_rows = n
+        with torch.cuda.device(rowptr.device):
+            nbytes = lib().hcspmm_dense_plan_workspace_bytes(n, nnz)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=rowptr.device)
+            counts = (ctypes.c_int32 * 2)()
+            _check(lib().hcspmm_dense_plan_count(_ptr(colidx), _ptr(rowptr), _ptr(ht), n, nnz, int(round(min_reuse * 2)),
+                                                 _ptr(ws), nbytes, ctypes.addressof(counts), _stream(rowptr)),
+                   "hcspmm_dense_plan_count")
+            self.n_dense, self.total_cols = int(counts[0]), int(counts[1])
+            words = lib().hcspmm_dense_plan_words(n, self.n_dense, self.total_cols)
+            self.plan = torch.zeros(words, dtype=torch.int32, device=rowptr.device)
+            _check(lib().hcspmm_dense_plan_fill(_ptr(colidx), _ptr(etr), n, nnz, _ptr(ws), self.n_dense, self.total_cols,
+                                                _ptr(self.plan), words, _stream(rowptr)), "hcspmm_dense_plan_fill")
+
+
+def spmm_plan(x, rowptr, colidx, bp, etc, etr, ht, plan: DensePlan, precision="tf32", out=None, accumulate=False):
+    """hcspmm_spmm_plan on device tensors."""
+    n, d = rowptr.numel() - 1, x.shape[1]
+    if out is None:
+        out = torch.empty((n, d), dtype=torch.float32, device=x.device)
+    prec = PRECISIONS[precision] if isinstance(precision, str) else int(precision)
+    with torch.cuda.device(x.device):
+        _check(lib().hcspmm_spmm_plan(_ptr(x), x.stride(0), x.shape[0], _ptr(rowptr), _ptr(colidx), _ptr(bp), _ptr(etc),
+                                      _ptr(etr), _ptr(ht), n, colidx.numel(), d, prec, 1 if accumulate else 0, _ptr(out),
+                                      out.stride(0), _ptr(plan.plan), plan.n_dense, plan.total_cols, _stream(x)),
+               "hcspmm_spmm_plan")
     return out
 
 

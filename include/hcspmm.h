@@ -124,6 +124,33 @@ int hcspmm_gemm_tf32(const float *d_a, int64_t lda, const float *d_b, int64_t ld
                      int32_t m, int32_t k, int32_t n, float *d_out, int64_t ldo,
                      void *stream);
 
+/* ---- dense super-window plan (tcgen05 / TMEM path) ----------------------------------------
+ * Groups of eight 16-row windows (128 rows) whose windows are all labelled tensor-core are
+ * multiplied as one dense contraction per group with tcgen05.mma.  The plan is
+ * derived from the CSR and the window labels (it does not change any reference array):
+ *   1. hcspmm_dense_plan_count   ranks columns per 128-row group, selects the dense groups
+ *                                (mean column reuse >= min_reuse_x2 / 2), synchronises, and
+ *                                returns h_counts = {n_dense, total condensed columns} on the host
+ *   2. hcspmm_dense_plan_fill    writes the plan (hcspmm_dense_plan_words() int32 words)
+ *   3. hcspmm_spmm_plan          hcspmm_spmm + plan: dense groups on the tcgen05 kernel, every other
+ *                                window on the hybrid kernel.  Falls back to hcspmm_spmm when the
+ *                                plan is empty, dim is not a multiple of 16 in [16, 256], precision
+ *                                is not TF32, or the "umma" knob is 0.                            */
+size_t hcspmm_dense_plan_workspace_bytes(int32_t n_rows, int64_t nnz);
+int hcspmm_dense_plan_count(const int32_t *d_colidx, const int32_t *d_rowptr, const int32_t *d_hybrid_type,
+                            int32_t n_rows, int64_t nnz, int min_reuse_x2, void *d_workspace,
+                            size_t workspace_bytes, int32_t *h_counts, void *stream);
+size_t hcspmm_dense_plan_words(int32_t n_rows, int32_t n_dense, int64_t total_cols);
+int hcspmm_dense_plan_fill(const int32_t *d_colidx, const int32_t *d_edge_to_row, int32_t n_rows, int64_t nnz,
+                           void *d_workspace, int32_t n_dense, int64_t total_cols, int32_t *d_plan,
+                           size_t plan_words, void *stream);
+int hcspmm_spmm_plan(const float *d_x, int64_t ldx, int32_t x_rows, const int32_t *d_rowptr,
+                     const int32_t *d_colidx, const int32_t *d_block_partition,
+                     const int32_t *d_edge_to_column, const int32_t *d_edge_to_row,
+                     const int32_t *d_hybrid_type, int32_t n_rows, int64_t nnz, int32_t dim,
+                     int precision, int accumulate, float *d_y, int64_t ldy, const int32_t *d_plan,
+                     int32_t n_dense, int64_t total_cols, void *stream);
+
 /* 1 if a tcgen05 kernel reported a barrier timeout since the last call (synchronises the device),
  * 0 if not, -1 on error.  Debug / test aid.                                              */
 int hcspmm_debug_umma_error(void);

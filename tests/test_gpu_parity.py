@@ -298,3 +298,56 @@ def test_spmm_odd_width_large_uses_padded_copies(capi):
         finally:
             capi.set_tuning("pad_odd", old)
         assert rel_fro(got, want) <= TOL_FP32
+
+
+# ---- tcgen05 dense super-window path -----------------------------------------------------------
+@pytest.mark.parametrize("name", ["sbm_1024", "rmat_1000", "band2_320", "holes_777", "dense_2048"])
+def test_spmm_dense_superwindows_tcgen05(capi, name):
+    rp, ci = GRAPHS[name]
+    n = rp.size - 1
+    d_rp, d_ci = dev(rp), dev(ci)
+    bp, etc, etr, ht = capi.preprocess(d_ci, d_rp, "all_tc")
+    old = capi.set_tuning("umma", 1)
+    try:
+        plan = capi.DensePlan(d_rp, d_ci, etr, ht, min_reuse=0.0)
+        assert plan.n_dense == sum(1 for s in range((n + 127) // 128) if rp[min(128 * s + 128, n)] > rp[128 * s])
+        for dim in (16, 32, 64, 128, 256, 48):
+            x = xmat(x_rows_for(rp, ci), dim, seed=dim + 3)
+            fp32 = oracle.spmm(rp, ci, x, precision=1)
+            tf32 = oracle.spmm(rp, ci, oracle.tf32_round(x), precision=1)
+            got = capi.spmm_plan(dev(x), d_rp, d_ci, bp, etc, etr, ht, plan).cpu().numpy()
+            assert capi.lib().hcspmm_debug_umma_error() == 0
+            assert rel_fro(got, fp32) <= TOL_TF32, (name, dim)
+            assert rel_fro(got, tf32) <= 2e-5, (name, dim)
+            acc = dev(np.ones_like(fp32))
+            capi.spmm_plan(dev(x), d_rp, d_ci, bp, etc, etr, ht, plan, out=acc, accumulate=True)
+            assert rel_fro(acc.cpu().numpy(), tf32 + 1.0) <= 2e-5, (name, dim)
+        # widths the dense kernel does not take fall back to the per-window paths
+        x = xmat(x_rows_for(rp, ci), 40, seed=1)
+        got = capi.spmm_plan(dev(x), d_rp, d_ci, bp, etc, etr, ht, plan).cpu().numpy()
+        assert rel_fro(got, oracle.spmm(rp, ci, x, precision=1)) <= TOL_TF32
+    finally:
+        capi.set_tuning("umma", old)
+
+
+def test_spmm_dense_plan_mixed_labels(capi):
+    """Only super-windows whose eight windows are ALL tensor-core go dense; the rest stay hybrid."""
+    rp, ci = GRAPHS["sbm_1024"]
+    d_rp, d_ci = dev(rp), dev(ci)
+    bp, etc, etr, _ = capi.preprocess(d_ci, d_rp, "all_tc")
+    ht = np.ones(64, np.int32)
+    ht[3] = 0            # super-window 0 has a CUDA-core window
+    ht[40:48] = 0        # super-window 5 entirely CUDA-core
+    old = capi.set_tuning("umma", 1)
+    try:
+        plan = capi.DensePlan(d_rp, d_ci, etr, dev(ht), min_reuse=0.0)
+        assert plan.n_dense == 6
+        x = xmat(1024, 64, seed=5)
+        got = capi.spmm_plan(dev(x), d_rp, d_ci, bp, etc, etr, dev(ht), plan).cpu().numpy()
+        want = oracle.spmm(rp, ci, x, hybrid_type=ht, precision=0)
+        assert rel_fro(got, want) <= 2e-5
+        assert capi.lib().hcspmm_debug_umma_error() == 0
+        # b200-style reuse threshold: a huge threshold selects nothing
+        assert capi.DensePlan(d_rp, d_ci, etr, dev(ht), min_reuse=1e6).n_dense == 0
+    finally:
+        capi.set_tuning("umma", old)
