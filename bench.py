@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--slab", type=int, default=-1, help="feature-slab width (-1 = library default)")
     ap.add_argument("--long-row", type=int, default=-1)
     ap.add_argument("--vec8", type=int, default=-1, help="256-bit gathers: 1 on, 0 off (-1 = library default)")
+    ap.add_argument("--dense", action="store_true", help="tcgen05 dense super-window plan (with --classifier b200|all_tc)")
     ap.add_argument("--tune", action="append", default=[], help="library tuning knob key=value (repeatable)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -261,6 +262,7 @@ def main():
     for kv in args.tune:
         k, v = kv.split("=")
         HCSPMM.set_tuning(k, int(v))
+    HCSPMM.set_dense(bool(args.dense))
     HCSPMM.set_classifier(args.classifier)
     HCSPMM.set_precision(args.precision)
 
@@ -274,6 +276,7 @@ def main():
     torch.cuda.synchronize()
     prep_ms = ev0.elapsed_time(ev1)
     tc_windows = int((pre[3] != 0).sum())
+    dense_groups = int(pre[4][1]) if (pre[4].device.type == "cpu" and pre[4].numel() >= 4) else 0
 
     g = torch.Generator(device=dev)
     g.manual_seed(1234)
@@ -433,7 +436,7 @@ def main():
                 "config": {"workload": f"{args.shape}-shape power-law graph, single-kernel SpMM Y=A*X "
                                        f"(BASELINE.json configs[1])" if args.shape == "reddit" else f"{args.shape}-shape SpMM",
                            "nodes": n, "stored_entries": nnz, "dim": dim, "classifier": args.classifier,
-                           "precision_tc_windows": args.precision, "tc_windows": tc_windows,
+                           "precision_tc_windows": args.precision, "tc_windows": tc_windows, "dense_groups_tcgen05": dense_groups,
                            "windows": (n_l + 15) // 16, "partition": f"row windows, nnz-balanced, {world} shard(s)",
                            "exchange": "NCCL all_gather_into_tensor of row-sharded X per step" if world > 1 else "none",
                            "l2": "inputs larger than L2 (X %.0f MB + CSR %.0f MB vs 126 MB), no flush" %

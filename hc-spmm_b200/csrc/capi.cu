@@ -17,7 +17,7 @@ void set_error(const char *fmt, ...) {
 }
 
 Tuning &tuning() {
-  static Tuning t = {1024, 0, 1, 1, 0, 0, 1};
+  static Tuning t = {1024, 0, 1, 1, 0, 0, 1, 0};
   return t;
 }
 
@@ -33,6 +33,7 @@ int launch_gemm_tf32(const float *, int64_t, const float *, int64_t, int32_t, in
 bool umma_gemm_supported(const float *, int64_t, const float *, int64_t, int32_t, int32_t);
 int launch_umma_gemm(const float *, int64_t, const float *, int64_t, int32_t, int32_t, int32_t, float *, int64_t,
                      int *, cudaStream_t);
+void keep_mempool_blocks();
 size_t dense_plan_workspace_bytes(int32_t n_rows, int64_t nnz);
 int dense_plan_count(const int32_t *, const int32_t *, const int32_t *, int32_t, int64_t, int, void *, size_t, int32_t *,
                      cudaStream_t);
@@ -84,6 +85,7 @@ int hcspmm_set_tuning(const char *key, int value) {
   else if (key && !strcmp(key, "wpc")) slot = &tuning().wpc;
   else if (key && !strcmp(key, "umma")) slot = &tuning().umma;
   else if (key && !strcmp(key, "pad_odd")) slot = &tuning().pad_odd;
+  else if (key && !strcmp(key, "umma_gemm")) slot = &tuning().umma_gemm;
   if (!slot) return -1;
   int old = *slot;
   *slot = value;
@@ -127,7 +129,7 @@ static int *umma_error_flag() {
 
 int hcspmm_gemm_tf32(const float *d_a, int64_t lda, const float *d_b, int64_t ldb, int32_t m,
                      int32_t k, int32_t n, float *d_out, int64_t ldo, void *stream) {
-  if (tuning().umma && d_a && d_b && d_out && m > 0 && n > 0 && lda >= k && ldb >= n && ldo >= n &&
+  if (tuning().umma_gemm && d_a && d_b && d_out && m > 0 && n > 0 && lda >= k && ldb >= n && ldo >= n &&
       umma_gemm_supported(d_a, lda, d_b, ldb, k, n))
     return launch_umma_gemm(d_a, lda, d_b, ldb, m, k, n, d_out, ldo, umma_error_flag(), (cudaStream_t)stream);
   return launch_gemm_tf32(d_a, lda, d_b, ldb, m, k, n, d_out, ldo, (cudaStream_t)stream);
@@ -167,6 +169,7 @@ int hcspmm_spmm_plan(const float *d_x, int64_t ldx, int32_t x_rows, const int32_
     return launch_spmm(d_x, ldx, x_rows, d_rowptr, d_colidx, d_block_partition, d_edge_to_column, d_edge_to_row,
                        d_hybrid_type, n_rows, nnz, dim, precision, accumulate, d_y, ldy, (cudaStream_t)stream);
   float *xr = nullptr;
+  keep_mempool_blocks();
   cudaError_t err = cudaMallocAsync(&xr, sizeof(float) * (size_t)x_rows * dim, (cudaStream_t)stream);
   if (err != cudaSuccess) { set_error("spmm_plan: cudaMallocAsync: %s", cudaGetErrorString(err)); return (int)err; }
   int rc = launch_spmm_dense(d_x, ldx, x_rows, n_rows, dim, d_plan, n_dense, total_cols, accumulate, d_y, ldy, xr,

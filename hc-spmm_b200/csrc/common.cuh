@@ -23,6 +23,7 @@ struct Tuning {
   int wpc;       // windows per CTA, 0 = automatic from the mean window population
   int umma;      // 1: tcgen05/TMEM kernels (Update GEMM, dense super-windows) where applicable
   int pad_odd;   // 1: large operands with odd width / unaligned rows run on padded copies
+  int umma_gemm; // 1: the Update GEMM uses the tcgen05 kernel (default: mma.sync kernel, still faster)
 };
 Tuning &tuning();
 

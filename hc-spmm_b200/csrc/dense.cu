@@ -270,6 +270,26 @@ __global__ void __launch_bounds__(DN_THREADS, 1) spmm_dense_kernel(const DensePa
   const uint32_t idesc = umma::make_idesc_tf32(SW_H, D, 0, 1);
   const int row_pieces = D / 4;              // 16-byte pieces per X row
   bool ok = true;
+  // per-thread piece map (depends on tid and D only): B pieces tid + i * 256 -> (k-row, 16-byte chunk)
+  constexpr int B_PER = DN_KC * 64 / DN_THREADS;   // 8 pieces per thread at D = 256
+  int b_kr[B_PER], b_ch[B_PER], rc[B_PER];
+  uint32_t b_off[B_PER], a_off[4], rm[16];
+#pragma unroll
+  for (int i = 0; i < B_PER; ++i) {
+    const int pid = tid + i * DN_THREADS;
+    if (pid < DN_KC * row_pieces) {
+      b_kr[i] = pid / row_pieces;
+      b_ch[i] = pid - b_kr[i] * row_pieces;
+      b_off[i] = umma::mnmajor_chunk_off(b_kr[i], b_ch[i], b_lbo, b_sbo);
+    } else {
+      b_kr[i] = -1; b_ch[i] = 0; b_off[i] = 0;
+    }
+    rc[i] = -1;
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) a_off[c] = umma::kmajor_off(tid & (SW_H - 1), (tid >> 7) * 16 + c * 4);
+#pragma unroll
+  for (int k = 0; k < 16; ++k) rm[k] = 0u;
   uint32_t g = 0;                            // global stage counter (drives buffer index and barrier parity)
   uint32_t tile_iter = 0;
 
@@ -279,38 +299,44 @@ __global__ void __launch_bounds__(DN_THREADS, 1) spmm_dense_kernel(const DensePa
     const int nst = (__ldg(p.sw_off + ti + 1) - c0) / DN_KC;
     const uint32_t g0 = g;
 
-    auto fill = [&](int s, uint32_t buf) {
-      uint8_t *sa = gen + buf * stage_bytes, *sb = sa + a_bytes;
+    // Index prefetch: the column ids and row masks of the NEXT stage to be filled are loaded into
+    // registers one pipeline step ahead, so their L2 latency is off the critical path.
+    auto load_idx = [&](int s) {
       const int cbase = c0 + s * DN_KC;
-      // B: 32 gathered rows, 16-byte cp.async pieces into the swizzled MN-major tile
-      for (int pid = tid; pid < DN_KC * row_pieces; pid += DN_THREADS) {
-        const int kr = pid / row_pieces, ch = pid - kr * row_pieces;
-        const int col = __ldg(p.cols + cbase + kr);
-        const bool valid = (unsigned)col < (unsigned)p.x_rows;
-        const float *src = valid ? p.xr + (long long)col * D + ch * 4 : p.xr;
-        cp_async_16(sb + umma::mnmajor_chunk_off(kr, ch, b_lbo, b_sbo), src, valid ? 16 : 0);
+#pragma unroll
+      for (int i = 0; i < B_PER; ++i) rc[i] = (b_kr[i] >= 0) ? __ldg(p.cols + cbase + b_kr[i]) : -1;
+      const int word = (tid & (SW_H - 1)) >> 5, kh = (tid >> 7) * 16;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) rm[k] = __ldg(p.masks + 4 * (long long)(cbase + kh + k) + word);
+    };
+    auto fill = [&](uint32_t buf) {
+      uint8_t *sa = gen + buf * stage_bytes, *sb = sa + a_bytes;
+      // B: gathered rows, 16-byte cp.async pieces into the swizzled MN-major tile
+#pragma unroll
+      for (int i = 0; i < B_PER; ++i) {
+        if (b_kr[i] >= 0) {
+          const bool valid = (unsigned)rc[i] < (unsigned)p.x_rows;
+          const float *src = valid ? p.xr + (long long)rc[i] * D + b_ch[i] * 4 : p.xr;
+          cp_async_16(sb + b_off[i], src, valid ? 16 : 0);
+        }
       }
       // A: thread (row r, half h) expands 16 condensed columns of its row from the bit masks
-      {
-        const int r = tid & (SW_H - 1), h = tid >> 7;
-        const int word = r >> 5, bit = r & 31;
+      const int bit = tid & 31;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int k = h * 16 + c * 4;
-          const unsigned m0 = __ldg(p.masks + 4 * (long long)(cbase + k) + word);
-          const unsigned m1 = __ldg(p.masks + 4 * (long long)(cbase + k + 1) + word);
-          const unsigned m2 = __ldg(p.masks + 4 * (long long)(cbase + k + 2) + word);
-          const unsigned m3 = __ldg(p.masks + 4 * (long long)(cbase + k + 3) + word);
-          const float4 v = make_float4((float)((m0 >> bit) & 1u), (float)((m1 >> bit) & 1u),
-                                       (float)((m2 >> bit) & 1u), (float)((m3 >> bit) & 1u));
-          *reinterpret_cast<float4 *>(sa + umma::kmajor_off(r, k)) = v;
-        }
+      for (int c = 0; c < 4; ++c) {
+        const float4 v = make_float4((float)((rm[4 * c] >> bit) & 1u), (float)((rm[4 * c + 1] >> bit) & 1u),
+                                     (float)((rm[4 * c + 2] >> bit) & 1u), (float)((rm[4 * c + 3] >> bit) & 1u));
+        *reinterpret_cast<float4 *>(sa + a_off[c]) = v;
       }
     };
 
+    load_idx(0);
 #pragma unroll
     for (int s0 = 0; s0 < DN_STAGES - 1; ++s0) {
-      if (s0 < nst) fill(s0, (g0 + s0) % DN_STAGES);
+      if (s0 < nst) {
+        fill((g0 + s0) % DN_STAGES);
+        if (s0 + 1 < nst) load_idx(s0 + 1);
+      }
       cp_async_commit();
     }
     for (int s = 0; s < nst; ++s) {
@@ -337,7 +363,8 @@ __global__ void __launch_bounds__(DN_THREADS, 1) spmm_dense_kernel(const DensePa
           const uint32_t gp = gs - 1;
           ok = umma::mbar_wait(&bar_empty[gp % DN_STAGES], (gp / DN_STAGES) & 1) && ok;
         }
-        fill(nxt, (g0 + nxt) % DN_STAGES);
+        fill((g0 + nxt) % DN_STAGES);
+        if (nxt + 1 < nst) load_idx(nxt + 1);
       }
       cp_async_commit();
     }

@@ -35,7 +35,9 @@ __device__ __forceinline__ int classify(int size, unsigned n_edges, int num, int
     // B200 re-fit (DESIGN.md "selector"): the dense path gathers each distinct column once
     // per window, so it wins as soon as the mean column reuse E_w / U covers its fixed cost.
     int upad = num * BLK_W;
-    return (n_edges >= 24u && 2u * n_edges >= 3u * (unsigned)upad) ? 1 : 0;
+    // ... and the window must fit the per-window path's residency (<= 1024 condensed columns):
+    // hub windows with tens of thousands of distinct columns belong to the CUDA-core path.
+    return (n_edges >= 24u && 2u * n_edges >= 3u * (unsigned)upad && upad <= 1024) ? 1 : 0;
   }
   float sf = (float)size;
   float df = __fdiv_rn((float)n_edges, (float)(int)((unsigned)num << 7));

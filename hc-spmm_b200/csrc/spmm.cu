@@ -123,6 +123,9 @@ __device__ __forceinline__ void gather_accumulate(Vec<VW> (&acc)[NV], const floa
   constexpr int STEPS = 32 / G;       // gather steps per full 32-edge chunk
   constexpr int U0 = HCSPMM_INFLIGHT_BYTES / (NV * VW * 4);
   constexpr int U = U0 < 1 ? 1 : (U0 > STEPS ? STEPS : U0);   // ring depth
+  int voff[NV];   // float offset of vector i from xlane; inactive lanes point at the slab's first vector
+#pragma unroll
+  for (int i = 0; i < NV; ++i) voff[i] = active[i] ? i * LPE * VW : -(lane % LPE) * VW;
   int base = eb + chunk0 * 32;
   int c_next = (base + lane < ee) ? __ldg(colidx + base + lane) : -1;
   for (; base < ee; base += chunk_stride * 32) {
@@ -130,18 +133,19 @@ __device__ __forceinline__ void gather_accumulate(Vec<VW> (&acc)[NV], const floa
     const int c = c_next;
     const int nb = base + chunk_stride * 32;
     c_next = (nb + lane < ee) ? __ldg(colidx + nb + lane) : -1;  // next chunk's ids, early
-    const bool fast = all_active && n == 32 &&
-                      __all_sync(0xffffffffu, (unsigned)c < (unsigned)x_rows);
+    (void)all_active;
+    const bool fast = n == 32 && __all_sync(0xffffffffu, (unsigned)c < (unsigned)x_rows);
     if (fast) {
-      // full chunk, every id valid, every lane active: unpredicated ring of U loads in flight --
-      // slot s % U is consumed and immediately refilled with step s + U
+      // full chunk, every id valid: unpredicated ring of U loads in flight -- slot s % U is consumed
+      // and immediately refilled with step s + U.  Lanes beyond the slab width (voff < 0) re-read
+      // the row's first vector (same cache line as lane 0) and never store their sums.
       Vec<VW> v[U][NV];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int cu = __shfl_sync(0xffffffffu, c, u * G + q);
         const float *src = xlane + (long long)cu * ldx;
 #pragma unroll
-        for (int i = 0; i < NV; ++i) v[u][i].load(src + i * LPE * VW);
+        for (int i = 0; i < NV; ++i) v[u][i].load(src + voff[i]);
       }
 #pragma unroll
       for (int s = 0; s < STEPS; ++s) {
@@ -151,7 +155,7 @@ __device__ __forceinline__ void gather_accumulate(Vec<VW> (&acc)[NV], const floa
           const int cu = __shfl_sync(0xffffffffu, c, (s + U) * G + q);
           const float *src = xlane + (long long)cu * ldx;
 #pragma unroll
-          for (int i = 0; i < NV; ++i) v[s % U][i].load(src + i * LPE * VW);
+          for (int i = 0; i < NV; ++i) v[s % U][i].load(src + voff[i]);
         }
       }
     } else {
@@ -565,6 +569,21 @@ __global__ void unpad_rows_kernel(const float *__restrict__ src, int dpad, int d
   dst[r * ldd + c] = src[r * dpad + c];
 }
 
+// Keep freed blocks in the stream-ordered pool: the default release threshold (0) hands them back to
+// the driver at every synchronisation, which makes the next cudaMallocAsync pay for a fresh mapping.
+void keep_mempool_blocks() {
+  static bool tuned[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || tuned[dev]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  tuned[dev] = true;
+}
+
 static size_t hybrid_smem_bytes(int S, bool tc) {
   size_t cuda_path = (size_t)CTA_WARPS * S * sizeof(float);
   size_t tc_path = tc ? (size_t)(2 * (UCAP + KC) + NSTAGE * KC * (S + 8)) * sizeof(float) : 0;
@@ -630,21 +649,7 @@ int launch_spmm(const float *x, int64_t ldx, int32_t x_rows, const int32_t *rowp
     // Two streaming copies cost 2 * (x_rows + n_rows) * dim * 4 bytes -- small next to the gather.
     const int dpad = (dim + 7) / 8 * 8;
     float *xp = nullptr, *yp = nullptr;
-    {
-      // keep freed blocks in the stream-ordered pool (the default threshold returns them to the
-      // driver at every synchronisation, which makes the next call pay for a fresh allocation)
-      static bool pool_tuned[64] = {false};
-      int dev = 0;
-      cudaGetDevice(&dev);
-      if (dev >= 0 && dev < 64 && !pool_tuned[dev]) {
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-          unsigned long long keep = ~0ull;
-          cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
-        pool_tuned[dev] = true;
-      }
-    }
+    keep_mempool_blocks();
     err = cudaMallocAsync(&xp, sizeof(float) * (size_t)x_rows * dpad, stream);
     if (err == cudaSuccess) err = cudaMallocAsync(&yp, sizeof(float) * (size_t)n_rows * dpad, stream);
     if (err != cudaSuccess) {

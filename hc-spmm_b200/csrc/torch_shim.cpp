@@ -25,6 +25,8 @@
 
 namespace {
 
+constexpr int32_t kPlanMagic = 0x48435044;   // row_nzr[0] when col_nzr carries a dense plan
+bool g_dense = false;                        // build / use tcgen05 dense super-window plans
 int g_classifier = HCSPMM_CLASSIFIER_SHIPPED;
 int g_precision = HCSPMM_PRECISION_TF32;
 bool g_bug_compat = false;
@@ -107,9 +109,51 @@ std::vector<torch::Tensor> preprocess(torch::Tensor edgeList, torch::Tensor node
                              ht.data_ptr<int32_t>(), ws.data_ptr(), ws_bytes,
                              at::cuda::getCurrentCUDAStream().stream()),
            "preprocess");
-  // row_nzr / col_nzr are one-element placeholders in the reference too (:405)
+  // row_nzr / col_nzr are one-element placeholders in the reference (:405) -- opaque to the caller,
+  // who only passes them back.  With set_dense(True) and a selector that labels tensor-core windows
+  // they carry the tcgen05 dense plan instead: col_nzr = the plan (device), row_nzr = its sizes (HOST
+  // int32 tensor, so that forward() needs no device synchronisation to read them).
   auto row_nzr = torch::zeros({1}, opts), col_nzr = torch::zeros({1}, opts);
+  if (g_dense && edge_num > 0 && g_classifier != HCSPMM_CLASSIFIER_SHIPPED && g_classifier != HCSPMM_CLASSIFIER_ALL_CUDA) {
+    auto stream = at::cuda::getCurrentCUDAStream().stream();
+    const size_t pws = hcspmm_dense_plan_workspace_bytes((int32_t)num_nodes, edge_num);
+    auto pw = torch::empty({(int64_t)pws}, opts.dtype(torch::kUInt8));
+    int32_t counts[2] = {0, 0};
+    const int min_reuse_x2 = g_classifier == HCSPMM_CLASSIFIER_ALL_TC ? 0 : 4;
+    check_rc(hcspmm_dense_plan_count(edgeList.data_ptr<int32_t>(), nodePointer.data_ptr<int32_t>(), ht.data_ptr<int32_t>(),
+                                     (int32_t)num_nodes, edge_num, min_reuse_x2, pw.data_ptr(), pws, counts, stream),
+             "dense_plan_count");
+    if (counts[0] > 0) {
+      const size_t words = hcspmm_dense_plan_words((int32_t)num_nodes, counts[0], counts[1]);
+      col_nzr = torch::zeros({(int64_t)words}, opts);
+      check_rc(hcspmm_dense_plan_fill(edgeList.data_ptr<int32_t>(), etr.data_ptr<int32_t>(), (int32_t)num_nodes, edge_num,
+                                      pw.data_ptr(), counts[0], counts[1], col_nzr.data_ptr<int32_t>(), words, stream),
+               "dense_plan_fill");
+      row_nzr = torch::tensor({kPlanMagic, counts[0], counts[1], (int32_t)num_nodes},
+                              torch::TensorOptions().dtype(torch::kInt32));
+    }
+  }
   return {bp, etc, etr, ht, row_nzr, col_nzr};
+}
+
+// one aggregation through the C ABI: with a dense plan when row_nzr / col_nzr carry one
+void run_spmm(const torch::Tensor &input, const Graph &g, const torch::Tensor &row_nzr, const torch::Tensor &col_nzr,
+              float *out, int64_t ldy, int accumulate, const char *what) {
+  const int64_t dim = input.size(1);
+  auto stream = at::cuda::getCurrentCUDAStream().stream();
+  if (g_dense && row_nzr.defined() && row_nzr.device().is_cpu() && row_nzr.scalar_type() == torch::kInt32 &&
+      row_nzr.numel() >= 4 && row_nzr.data_ptr<int32_t>()[0] == kPlanMagic && col_nzr.is_cuda() &&
+      col_nzr.scalar_type() == torch::kInt32 && row_nzr.data_ptr<int32_t>()[3] == g.n_rows) {
+    const int32_t *h = row_nzr.data_ptr<int32_t>();
+    check_rc(hcspmm_spmm_plan(input.data_ptr<float>(), input.stride(0), (int32_t)input.size(0), g.rowptr, g.colidx, g.bp,
+                              g.etc, g.etr, g.ht, g.n_rows, g.nnz, (int32_t)dim, g_precision, accumulate, out, ldy,
+                              col_nzr.data_ptr<int32_t>(), h[1], h[2], stream),
+             what);
+    return;
+  }
+  check_rc(hcspmm_spmm(input.data_ptr<float>(), input.stride(0), (int32_t)input.size(0), g.rowptr, g.colidx, g.bp, g.etc,
+                       g.etr, g.ht, g.n_rows, g.nnz, (int32_t)dim, g_precision, accumulate, out, ldy, stream),
+           what);
 }
 
 // forward / forward_more / forward_fixed32 / forward_fixed64 and their backward_* aliases,
@@ -119,15 +163,11 @@ std::vector<torch::Tensor> spmm_forward(torch::Tensor input, torch::Tensor nodeP
                                         torch::Tensor edgeToColumn, torch::Tensor edgeToRow,
                                         torch::Tensor hybrid_type, torch::Tensor row_nzr,
                                         torch::Tensor col_nzr) {
-  (void)row_nzr; (void)col_nzr;
   Graph g = check_graph(input, nodePointer, edgeList, blockPartition, edgeToColumn, edgeToRow, hybrid_type);
   c10::cuda::CUDAGuard guard(input.device());
   const int64_t dim = input.size(1);
   auto out = torch::empty({g.n_rows, dim}, input.options());
-  check_rc(hcspmm_spmm(input.data_ptr<float>(), dim, (int32_t)input.size(0), g.rowptr, g.colidx, g.bp,
-                       g.etc, g.etr, g.ht, g.n_rows, g.nnz, (int32_t)dim, g_precision, 0,
-                       out.data_ptr<float>(), dim, at::cuda::getCurrentCUDAStream().stream()),
-           "forward");
+  run_spmm(input, g, row_nzr, col_nzr, out.data_ptr<float>(), dim, 0, "forward");
   return {out};
 }
 
@@ -164,16 +204,17 @@ torch::Tensor dense_weights(const torch::Tensor &weights, const torch::Tensor &i
   return weights.contiguous();
 }
 
-std::vector<torch::Tensor> fused_impl(const torch::Tensor &input, const Graph &g,
-                                      const torch::Tensor &weights, torch::Tensor out, const char *what) {
+std::vector<torch::Tensor> fused_impl(const torch::Tensor &input, const Graph &g, const torch::Tensor &row_nzr,
+                                      const torch::Tensor &col_nzr, const torch::Tensor &weights, torch::Tensor out,
+                                      const char *what) {
   c10::cuda::CUDAGuard guard(input.device());
   auto w = dense_weights(weights, input);
   const int64_t dim = input.size(1), hidden = w.size(1);
   auto z = torch::empty({g.n_rows, dim}, input.options());
-  check_rc(hcspmm_spmm_gemm(input.data_ptr<float>(), dim, (int32_t)input.size(0), g.rowptr, g.colidx, g.bp,
-                            g.etc, g.etr, g.ht, g.n_rows, g.nnz, (int32_t)dim, g_precision,
-                            w.data_ptr<float>(), hidden, (int32_t)hidden, out.data_ptr<float>(), hidden,
-                            z.data_ptr<float>(), dim, at::cuda::getCurrentCUDAStream().stream()),
+  // Z = A X, then out = Z W: exactly what hcspmm_spmm_gemm does, with the plan-aware aggregation
+  run_spmm(input, g, row_nzr, col_nzr, z.data_ptr<float>(), dim, 0, what);
+  check_rc(hcspmm_gemm_tf32(z.data_ptr<float>(), dim, w.data_ptr<float>(), hidden, g.n_rows, (int32_t)dim,
+                            (int32_t)hidden, out.data_ptr<float>(), hidden, at::cuda::getCurrentCUDAStream().stream()),
            what);
   return {out, z};
 }
@@ -185,11 +226,10 @@ std::vector<torch::Tensor> spmm_forward_fused(torch::Tensor input, torch::Tensor
                                               torch::Tensor edgeToColumn, torch::Tensor edgeToRow,
                                               torch::Tensor hybrid_type, torch::Tensor row_nzr,
                                               torch::Tensor col_nzr, torch::Tensor weights) {
-  (void)row_nzr; (void)col_nzr;
   Graph g = check_graph(input, nodePointer, edgeList, blockPartition, edgeToColumn, edgeToRow, hybrid_type);
   TORCH_CHECK(weights.dim() == 2, "weights must be 2-D");
   auto out = torch::empty({g.n_rows, weights.size(1)}, input.options());
-  return fused_impl(input, g, weights, out, "forward_fused");
+  return fused_impl(input, g, row_nzr, col_nzr, weights, out, "forward_fused");
 }
 
 // forward_final_fused / forward_final_fused_64 (+ backward_*): writes the caller's `output`,
@@ -200,14 +240,13 @@ std::vector<torch::Tensor> spmm_forward_final_fused(torch::Tensor input, torch::
                                                     torch::Tensor hybrid_type, torch::Tensor row_nzr,
                                                     torch::Tensor col_nzr, torch::Tensor weights,
                                                     torch::Tensor output) {
-  (void)row_nzr; (void)col_nzr;
   Graph g = check_graph(input, nodePointer, edgeList, blockPartition, edgeToColumn, edgeToRow, hybrid_type);
   check_f32_2d(output, "output");
   TORCH_CHECK(weights.dim() == 2, "weights must be 2-D");
   TORCH_CHECK(output.device() == input.device(), "output must be on the input's device");
   TORCH_CHECK(output.size(0) == g.n_rows && output.size(1) == weights.size(1),
               "output must be [num_nodes, hidden] = [", g.n_rows, ", ", weights.size(1), "]");
-  return fused_impl(input, g, weights, output, "forward_final_fused");
+  return fused_impl(input, g, row_nzr, col_nzr, weights, output, "forward_final_fused");
 }
 
 torch::Tensor gemm_tf32(torch::Tensor a, torch::Tensor b) {
@@ -239,6 +278,13 @@ std::string set_precision(const std::string &mode) {
   TORCH_CHECK(false, "unknown precision '", mode, "' (tf32|tf32x2|fp32)");
 }
 
+bool set_dense(bool on) {
+  bool old = g_dense;
+  g_dense = on;
+  hcspmm_set_tuning("umma", on ? 1 : 0);
+  return old;
+}
+
 bool set_bug_compat(bool on) {
   bool old = g_bug_compat;
   g_bug_compat = on;
@@ -247,7 +293,7 @@ bool set_bug_compat(bool on) {
 
 int64_t set_tuning(const std::string &key, int64_t value) {
   int old = hcspmm_set_tuning(key.c_str(), (int)value);
-  TORCH_CHECK(old != -1 || key == "slab" || key == "long_row" || key == "vec8" || key == "short_row" || key == "wpc" || key == "umma" || key == "pad_odd",
+  TORCH_CHECK(old != -1 || key == "slab" || key == "long_row" || key == "vec8" || key == "short_row" || key == "wpc" || key == "umma" || key == "pad_odd" || key == "umma_gemm",
               "unknown tuning key '", key, "'");
   return old;
 }
@@ -282,6 +328,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm_tf32", &gemm_tf32, "a @ b with TF32 tensor-core product");
   m.def("set_classifier", &set_classifier, "shipped | intended | b200 | all_cuda | all_tc; returns the previous mode");
   m.def("set_precision", &set_precision, "tf32 | tf32x2 | fp32; returns the previous mode");
+  m.def("set_dense", &set_dense, "tcgen05 kernels: dense super-window plans in preprocess()/forward*(), Update GEMM");
   m.def("set_bug_compat", &set_bug_compat, "read strided `weights` as raw memory like the reference");
   m.def("set_tuning", &set_tuning, "kernel tuning knob (long_row, slab); returns the previous value");
 }

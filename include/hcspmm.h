@@ -72,7 +72,8 @@ const char *hcspmm_last_error(void);
  *   "wpc"        16-row windows per CTA (1..8); 0 = chosen from nnz / windows
  *   "pad_odd"    1 (default): large operands whose width is not a multiple of 4 (or whose rows
  *                are unaligned) run through zero-padded aligned copies; 0: scalar kernel
- *   "umma"       1: tcgen05 / TMEM kernels where applicable (Update GEMM); 0: mma.sync kernels
+ *   "umma"       1: tcgen05 / TMEM dense super-window kernel (hcspmm_spmm_plan); 0: per-window paths
+ *   "umma_gemm"  1: tcgen05 / TMEM Update GEMM; 0 (default): mma.sync GEMM
  * Returns the previous value, or -1 for an unknown key.                          */
 int hcspmm_set_tuning(const char *key, int value);
 

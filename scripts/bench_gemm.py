@@ -14,7 +14,7 @@ for (m, k, n) in [(2449029, 128, 128), (2449029, 100, 128), (232965, 256, 256), 
     a = torch.randn(m, k, device="cuda"); b = torch.randn(k, n, device="cuda")
     res = {}
     for umma in (0, 1):
-        capi.set_tuning("umma", umma)
+        capi.set_tuning("umma_gemm", umma)
         res[umma] = t(lambda: capi.gemm_tf32(a, b))
     torch.backends.cuda.matmul.allow_tf32 = True
     tt = t(lambda: torch.mm(a, b))

@@ -4,7 +4,7 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "hc-spmm_b200")]
 import torch, numpy as np
 from hcspmm import capi
 torch.manual_seed(0)
-capi.set_tuning("umma", 1)
+capi.set_tuning("umma_gemm", 1)
 def run(m, k, n, a=None, b=None, tag=""):
     a = torch.randn(m, k, device="cuda") if a is None else a
     b = torch.randn(k, n, device="cuda") if b is None else b

@@ -211,3 +211,29 @@ def test_reference_fused_matches(H, REF):
     torch.cuda.synchronize()
     assert rel_fro(o_z.cpu().numpy(), r_z.cpu().numpy()) <= 1e-6
     assert rel_fro(o_out.cpu().numpy(), r_out.cpu().numpy()) <= 1e-4
+
+
+def test_dense_plan_travels_in_row_nzr_col_nzr(H):
+    """set_dense(True): preprocess() returns the tcgen05 dense plan in the two opaque tensors, forward*()
+    picks it up; with set_dense(False) the same tensors are ignored (per-window paths)."""
+    rp, ci = GRAPHS["sbm_1024"]
+    n = 1024
+    H.set_dense(True)
+    try:
+        pre = prep(H, rp, ci, "all_tc")
+        assert pre[4].device.type == "cpu" and int(pre[4][1]) == 8 and pre[5].numel() > 16
+        g = torch.Generator().manual_seed(7)
+        x, w = torch.randn(n, 64, generator=g), torch.randn(64, 32, generator=g)
+        tf32 = oracle.spmm(rp, ci, oracle.tf32_round(x.numpy()), precision=1)
+        out = H.forward(x.cuda(), dev(rp), dev(ci), *pre)[0]
+        assert rel_fro(out.cpu().numpy(), tf32) <= 2e-5
+        o2, z = H.forward_fixed32_fused(x.cuda(), dev(rp), dev(ci), *pre, w.cuda())
+        assert rel_fro(z.cpu().numpy(), tf32) <= 2e-5
+        assert rel_fro(o2.cpu().numpy(), oracle.gemm(tf32, w.numpy(), tf32=True)) <= 1e-4
+        # shipped selector: no tensor-core windows, hence no plan
+        pre0 = prep(H, rp, ci, "shipped")
+        assert pre0[4].is_cuda and pre0[5].numel() == 1
+    finally:
+        H.set_dense(False)
+    out = H.forward(x.cuda(), dev(rp), dev(ci), *pre)[0]      # plan present but the path is switched off
+    assert rel_fro(out.cpu().numpy(), tf32) <= 2e-5

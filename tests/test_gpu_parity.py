@@ -269,12 +269,12 @@ def test_host_graph_roundtrip(capi):
                                    (300, 36, 16), (2000, 128, 320), (77, 8, 4)])
 def test_gemm_tcgen05(capi, m, k, n):
     a, b = xmat(m, k, 1), xmat(k, n, 2)
-    old = capi.set_tuning("umma", 1)
+    old = capi.set_tuning("umma_gemm", 1)
     try:
         got = capi.gemm_tf32(dev(a), dev(b)).cpu().numpy()
         assert capi.lib().hcspmm_debug_umma_error() == 0, "tcgen05 kernel reported a barrier timeout"
     finally:
-        capi.set_tuning("umma", old)
+        capi.set_tuning("umma_gemm", old)
     assert rel_fro(got, oracle.gemm(a, b, tf32=True)) <= 1e-4
 
 
