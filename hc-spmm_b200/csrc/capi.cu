@@ -17,7 +17,7 @@ void set_error(const char *fmt, ...) {
 }
 
 Tuning &tuning() {
-  static Tuning t = {1024, 0, 1, 1, 0, 0, 1, 0};
+  static Tuning t = {1024, 0, 1, 1, 0, 0, 1, 0, 1, 1};
   return t;
 }
 
@@ -86,6 +86,8 @@ int hcspmm_set_tuning(const char *key, int value) {
   else if (key && !strcmp(key, "umma")) slot = &tuning().umma;
   else if (key && !strcmp(key, "pad_odd")) slot = &tuning().pad_odd;
   else if (key && !strcmp(key, "umma_gemm")) slot = &tuning().umma_gemm;
+  else if (key && !strcmp(key, "dense_ws")) slot = &tuning().dense_ws;
+  else if (key && !strcmp(key, "occupancy3")) slot = &tuning().occupancy3;
   if (!slot) return -1;
   int old = *slot;
   *slot = value;

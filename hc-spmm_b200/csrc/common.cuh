@@ -24,6 +24,8 @@ struct Tuning {
   int umma;      // 1: tcgen05/TMEM kernels (Update GEMM, dense super-windows) where applicable
   int pad_odd;   // 1: large operands with odd width / unaligned rows run on padded copies
   int umma_gemm; // 1: the Update GEMM uses the tcgen05 kernel (default: mma.sync kernel, still faster)
+  int dense_ws;  // 1: warp-specialised dense kernel (producers / MMA issuer / double-buffered TMEM)
+  int occupancy3; // 1: low-degree graphs use the 3-CTAs-per-SM build of the hybrid kernel
 };
 Tuning &tuning();
 

@@ -408,6 +408,209 @@ __global__ void __launch_bounds__(DN_THREADS, 1) spmm_dense_kernel(const DensePa
   if (wid == 0) umma::tmem_dealloc(tmem_d, 256);
 }
 
+// ---- warp-specialised version ---------------------------------------------------------------------
+// 9 warps: warps 0-7 (256 threads) PRODUCE stages (cp.async gathers + mask expansion) and drain the
+// accumulator; warp 8 ISSUES the MMAs.  No block barrier in the steady state -- four kinds of mbarrier:
+//   full[s]       256 producer arrivals (cp.async.mbarrier.arrive.noinc: fires when the thread's copies
+//                 have landed)                                   producer -> issuer
+//   empty[s]      tcgen05.commit of the stage's MMAs            issuer  -> producer
+//   tmem_full[a]  tcgen05.commit after a super-window's last MMA issuer  -> epilogue
+//   tmem_empty[a] 256 arrivals after the accumulator was read    epilogue -> issuer
+// The accumulator is double buffered in TMEM (2 x 256 columns), so the issuer starts the next
+// super-window while the previous one is being written out.
+#ifndef HCSPMM_DW_PRODUCERS
+#define HCSPMM_DW_PRODUCERS 512
+#endif
+constexpr int DW_PRODUCERS = HCSPMM_DW_PRODUCERS;
+constexpr int DW_THREADS = DW_PRODUCERS + 32;
+constexpr int DW_STAGES = 3;
+constexpr int DW_IDX = 1024;   // condensed columns per shared-memory index chunk (20 KB, double buffered)
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(umma::smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(DW_THREADS, 1) spmm_dense_ws_kernel(const DenseParams p) {
+  extern __shared__ __align__(1024) uint8_t dn_smem[];
+  __shared__ __align__(8) uint64_t bar_full[DW_STAGES], bar_empty[DW_STAGES], bar_tfull[2], bar_tempty[2];
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int D = p.dim;
+  const int natoms = (D + 31) / 32;
+  const uint32_t a_bytes = SW_H * 128;
+  const uint32_t b_lbo = 512, b_sbo = natoms * 512;
+  const uint32_t b_bytes = (DN_KC / 4) * b_sbo;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const uint32_t smem_base = (umma::smem_u32(dn_smem) + 1023u) & ~1023u;
+  uint8_t *gen = dn_smem + (smem_base - umma::smem_u32(dn_smem));
+
+  if (tid == 0) {
+    for (int s = 0; s < DW_STAGES; ++s) { umma::mbar_init(&bar_full[s], 2 * DW_PRODUCERS); umma::mbar_init(&bar_empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { umma::mbar_init(&bar_tfull[a], 1); umma::mbar_init(&bar_tempty[a], DW_PRODUCERS); }
+    umma::fence_barrier_init();
+  }
+  if (wid == 0) umma::tmem_alloc(&tmem_slot, 512);
+  for (uint32_t o = tid * 16; o < DW_STAGES * stage_bytes; o += DW_THREADS * 16)
+    *reinterpret_cast<float4 *>(gen + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  umma::tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_slot;
+  bool ok = true;
+
+  if (wid == DW_PRODUCERS / 32) {
+    // ================= MMA issuer (one thread) =================
+    if (lane == 0) {
+      const uint32_t idesc = umma::make_idesc_tf32(SW_H, D, 0, 1);
+      uint32_t g = 0, it = 0;
+      for (int ti = blockIdx.x; ti < p.n_dense; ti += gridDim.x, ++it) {
+        const int nst = (__ldg(p.sw_off + ti + 1) - __ldg(p.sw_off + ti)) / DN_KC;
+        const uint32_t acc = it & 1, use = it >> 1;
+        ok = umma::mbar_wait(&bar_tempty[acc], (use & 1) ^ 1) && ok;      // accumulator drained (first use: free)
+        umma::tc_fence_after_sync();
+        const uint32_t tmem_d = tmem_base + acc * 256;
+        for (int s = 0; s < nst; ++s) {
+          const uint32_t gs = g + s, buf = gs % DW_STAGES;
+          ok = umma::mbar_wait(&bar_full[buf], (gs / DW_STAGES) & 1) && ok;
+          // consumer-side proxy fence: the producers' generic-proxy writes (st.shared, cp.async), made
+          // visible to this thread by the mbarrier, are ordered before the tensor core's async-proxy reads
+          umma::fence_proxy_async_smem();
+          umma::tc_fence_after_sync();
+          const uint32_t sa = smem_base + buf * stage_bytes, sb = sa + a_bytes;
+#pragma unroll
+          for (int j = 0; j < DN_KC / 8; ++j) {
+            const uint64_t da = umma::make_desc_sw128(sa + j * 32, 16, 1024);
+            const uint64_t db = umma::make_desc(sb + 2 * j * b_sbo, b_lbo, b_sbo, umma::LAYOUT_SW128_BASE32B);
+            umma::mma_tf32_ss(tmem_d, da, db, idesc, (s > 0 || j > 0) ? 1u : 0u);
+          }
+          umma::mma_commit(&bar_empty[buf]);
+        }
+        umma::mma_commit(&bar_tfull[acc]);
+        g += nst;
+      }
+    }
+    __syncwarp();   // lanes 1..31 wait here, so the whole warp reaches the final block barrier together
+  } else {
+    // ================= producers + epilogue (256 threads) =================
+    const int row_pieces = D / 4;
+    constexpr int B_PER = DN_KC * 64 / DW_PRODUCERS;       // 16-byte B pieces per thread at D = 256
+    constexpr int A_KS = DN_KC * SW_H / DW_PRODUCERS;      // condensed columns of its row a thread expands
+    constexpr int A_PER = A_KS / 4;
+    int b_kr[B_PER], b_ch[B_PER];
+    uint32_t b_off[B_PER], a_off[A_PER];
+#pragma unroll
+    for (int i = 0; i < B_PER; ++i) {
+      const int pid = tid + i * DW_PRODUCERS;
+      if (pid < DN_KC * row_pieces) {
+        b_kr[i] = pid / row_pieces;
+        b_ch[i] = pid - b_kr[i] * row_pieces;
+        b_off[i] = umma::mnmajor_chunk_off(b_kr[i], b_ch[i], b_lbo, b_sbo);
+      } else {
+        b_kr[i] = -1; b_ch[i] = 0; b_off[i] = 0;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < A_PER; ++c) a_off[c] = umma::kmajor_off(tid & (SW_H - 1), (tid >> 7) * A_KS + c * 4);
+    const int word = (tid & (SW_H - 1)) >> 5, kh = (tid >> 7) * A_KS, bit = tid & 31;
+
+    // Column ids and row masks are staged in shared memory in chunks of DW_IDX condensed columns
+    // (double buffered, cp.async): the stage loop below never waits on a global index load.
+    int *cols_s = reinterpret_cast<int *>(gen + DW_STAGES * stage_bytes);
+    unsigned *masks_s = reinterpret_cast<unsigned *>(cols_s + 2 * DW_IDX);
+    auto load_chunk = [&](int cbase, int ncols, int slot) {
+      // ncols is a multiple of 32: cols = ncols / 4 pieces of 16 B, masks = ncols pieces of 16 B
+      for (int i = tid; i < ncols / 4; i += DW_PRODUCERS) cp_async_16(cols_s + slot * DW_IDX + i * 4, p.cols + cbase + i * 4, 16);
+      for (int i = tid; i < ncols; i += DW_PRODUCERS)
+        cp_async_16(masks_s + (size_t)(slot * DW_IDX + i) * 4, p.masks + 4 * (long long)(cbase + i), 16);
+    };
+    auto producers_sync = [&]() {
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(DW_PRODUCERS) : "memory");
+    };
+
+    uint32_t g = 0, it = 0;
+    for (int ti = blockIdx.x; ti < p.n_dense; ti += gridDim.x, ++it) {
+      const int sw = __ldg(p.sw_ids + ti);
+      const int c0 = __ldg(p.sw_off + ti);
+      const int ucols = __ldg(p.sw_off + ti + 1) - c0;
+      const int nst = ucols / DN_KC;
+      const int nchunks = (ucols + DW_IDX - 1) / DW_IDX;
+      producers_sync();                       // previous super-window's index buffers are no longer read
+      load_chunk(c0, min(DW_IDX, ucols), 0);
+      for (int ch = 0; ch < nchunks; ++ch) {
+        const int slot = ch & 1;
+        producers_sync();                     // chunk ch has landed (and chunk ch-1 is fully consumed)
+        if (ch + 1 < nchunks) load_chunk(c0 + (ch + 1) * DW_IDX, min(DW_IDX, ucols - (ch + 1) * DW_IDX), slot ^ 1);
+        const int f0 = ch * (DW_IDX / DN_KC), f1 = min(nst, f0 + DW_IDX / DN_KC);
+        for (int f = f0; f < f1; ++f) {
+          const uint32_t gf = g + f, buf = gf % DW_STAGES;
+          const int kb = slot * DW_IDX + (f - f0) * DN_KC;
+          ok = umma::mbar_wait(&bar_empty[buf], ((gf / DW_STAGES) & 1) ^ 1) && ok;   // first round: buffers are free
+          uint8_t *sa = gen + buf * stage_bytes, *sb = sa + a_bytes;
+#pragma unroll
+          for (int c = 0; c < A_PER; ++c) {
+            const unsigned m0 = masks_s[(kb + kh + 4 * c) * 4 + word], m1 = masks_s[(kb + kh + 4 * c + 1) * 4 + word];
+            const unsigned m2 = masks_s[(kb + kh + 4 * c + 2) * 4 + word], m3 = masks_s[(kb + kh + 4 * c + 3) * 4 + word];
+            const float4 v = make_float4(((m0 >> bit) & 1u) ? 1.f : 0.f, ((m1 >> bit) & 1u) ? 1.f : 0.f,
+                                         ((m2 >> bit) & 1u) ? 1.f : 0.f, ((m3 >> bit) & 1u) ? 1.f : 0.f);
+            *reinterpret_cast<float4 *>(sa + a_off[c]) = v;
+          }
+          mbar_arrive(&bar_full[buf]);                   // release: this thread's part of the A tile is written
+#pragma unroll
+          for (int i = 0; i < B_PER; ++i) {
+            if (b_kr[i] >= 0) {
+              const int col = cols_s[kb + b_kr[i]];
+              const bool valid = (unsigned)col < (unsigned)p.x_rows;
+              const float *src = valid ? p.xr + (long long)col * D + b_ch[i] * 4 : p.xr;
+              cp_async_16(sb + b_off[i], src, valid ? 16 : 0);
+            }
+          }
+          cp_async_mbar_arrive_noinc(&bar_full[buf]);    // second arrival: when this thread's copies have landed
+        }
+      }
+      g += nst;
+
+      // ---- epilogue of this super-window
+      const uint32_t acc = it & 1, use = it >> 1;
+      ok = umma::mbar_wait(&bar_tfull[acc], use & 1) && ok;
+      umma::tc_fence_after_sync();
+      {
+        constexpr int CW = 256 / (DW_PRODUCERS / 128);     // accumulator columns per warp group of four
+        const int lq = wid & 3, part = wid >> 2;
+        const int row = sw * SW_H + lq * 32 + lane;
+        for (int cc = part * CW; cc < part * CW + CW && cc < D; cc += 32) {
+          uint32_t v[32];
+          umma::tmem_ld_32x32(tmem_base + acc * 256 + ((uint32_t)(lq * 32) << 16) + (uint32_t)cc, v);
+          umma::tmem_ld_wait();
+          if (row < p.n_rows) {
+            float *dst = p.y + (long long)row * p.ldy + cc;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (cc + j < D) {
+                float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                       __uint_as_float(v[j + 3]));
+                float4 *d4 = reinterpret_cast<float4 *>(dst + j);
+                if (p.accumulate) add4(o, *d4);
+                *d4 = o;
+              }
+            }
+          }
+        }
+      }
+      umma::tc_fence_before_sync();
+      mbar_arrive(&bar_tempty[acc]);
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  }
+  if (!ok && p.err) atomicExch(p.err, 1);
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  if (wid == 0) umma::tmem_dealloc(tmem_base, 512);
+}
+
 bool dense_supported(const float *x, const float *y, int64_t ldy, int32_t dim) {
   return dim >= 16 && dim <= 256 && (dim % 16) == 0 && (ldy % 4) == 0 &&
          ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
@@ -432,7 +635,14 @@ int launch_spmm_dense(const float *x, int64_t ldx, int32_t x_rows, int32_t n_row
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = n_dense < sms ? n_dense : sms;
-  spmm_dense_kernel<<<grid, DN_THREADS, smem, stream>>>(p);
+  if (tuning().dense_ws) {
+    const size_t smem_ws = (size_t)DW_STAGES * (SW_H * 128 + (DN_KC / 4) * natoms * 512) + 2 * DW_IDX * 20 + 1024;
+    err = cudaFuncSetAttribute(spmm_dense_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws);
+    if (err != cudaSuccess) { set_error("spmm_dense_ws attr: %s", cudaGetErrorString(err)); return (int)err; }
+    spmm_dense_ws_kernel<<<grid, DW_THREADS, smem_ws, stream>>>(p);
+  } else {
+    spmm_dense_kernel<<<grid, DN_THREADS, smem, stream>>>(p);
+  }
   err = cudaGetLastError();
   if (err != cudaSuccess) { set_error("spmm_dense launch: %s", cudaGetErrorString(err)); return (int)err; }
   return 0;

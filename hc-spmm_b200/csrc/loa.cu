@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(LOA_THREADS, 1) loa_kernel(const LoaParams p) 
   __shared__ float red_p[32];
   __shared__ unsigned long long red_k[32];
   __shared__ int red_i[32];
-  __shared__ int s_cur, s_npro, s_nresi, s_winner;
+  __shared__ int s_cur, s_npro, s_winner;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int n = p.n;
   int *cols = p.cols_a, *cols_next = p.cols_b;
@@ -197,7 +197,6 @@ __global__ void __launch_bounds__(LOA_THREADS, 1) loa_kernel(const LoaParams p) 
       if (tid == 0) {
         __stcg(p.visit + win, (unsigned char)1);
         p.blk_vert[nvert + bsz] = win;
-        s_nresi = 0;
       }
       ++bsz;
       if (bsz == 16) break;                     // 1 seed + 15 picks; no further scan is needed

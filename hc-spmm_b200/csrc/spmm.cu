@@ -347,8 +347,10 @@ __device__ __forceinline__ void tc_window(const SpmmParams &p, int w, int e0, in
 // ---------------------------------------------------------------------------------------
 // The hybrid kernel.  Slab width S <= LPE * NV * 4 floats; X/Y 16-byte aligned, ldx/ldy % 4 == 0.
 // ---------------------------------------------------------------------------------------
-template <int LPE, int NV, int VW>
-__global__ void __launch_bounds__(CTA_THREADS, HCSPMM_MIN_CTAS) spmm_hybrid_kernel(const SpmmParams p) {
+// MINB = minimum resident CTAs per SM the register allocation must allow: 2 for high-degree graphs
+// (the gather ring wants registers), 3 for low-degree graphs (latency hiding wants warps).
+template <int LPE, int NV, int VW, int MINB>
+__global__ void __launch_bounds__(CTA_THREADS, MINB) spmm_hybrid_kernel(const SpmmParams p) {
   extern __shared__ __align__(16) float smem[];
   __shared__ int rp[BLK_H * MAX_WPC + 1];
   __shared__ int s_next;
@@ -590,15 +592,21 @@ static size_t hybrid_smem_bytes(int S, bool tc) {
   return cuda_path > tc_path ? cuda_path : tc_path;
 }
 
-template <int LPE, int NV, int VW>
-static cudaError_t launch_hybrid(const SpmmParams &p, dim3 grid, size_t smem, cudaStream_t stream) {
-  cudaError_t err = cudaFuncSetAttribute(spmm_hybrid_kernel<LPE, NV, VW>,
+template <int LPE, int NV, int VW, int MINB>
+static cudaError_t launch_hybrid_b(const SpmmParams &p, dim3 grid, size_t smem, cudaStream_t stream) {
+  cudaError_t err = cudaFuncSetAttribute(spmm_hybrid_kernel<LPE, NV, VW, MINB>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
   SpmmParams q = p;
   q.short_row = p.short_row * (32 / LPE);   // "fewer than short_row steps of a whole warp"
-  spmm_hybrid_kernel<LPE, NV, VW><<<grid, CTA_THREADS, smem, stream>>>(q);
+  spmm_hybrid_kernel<LPE, NV, VW, MINB><<<grid, CTA_THREADS, smem, stream>>>(q);
   return cudaGetLastError();
+}
+template <int LPE, int NV, int VW>
+static cudaError_t launch_hybrid(const SpmmParams &p, dim3 grid, size_t smem, cudaStream_t stream) {
+  // p.wpc > 1 <=> low-degree graph (few hundred entries per window)
+  if (p.wpc > 1 && tuning().occupancy3) return launch_hybrid_b<LPE, NV, VW, 3>(p, grid, smem, stream);
+  return launch_hybrid_b<LPE, NV, VW, HCSPMM_MIN_CTAS>(p, grid, smem, stream);
 }
 
 int launch_spmm(const float *x, int64_t ldx, int32_t x_rows, const int32_t *rowptr,
@@ -681,12 +689,13 @@ int launch_spmm(const float *x, int64_t ldx, int32_t x_rows, const int32_t *rowp
     if (slab > 512) slab = 512;
     if (slab > dim) slab = dim;
     p.slab = slab;
-    // low-degree graphs: several windows per CTA so that a CTA has a few hundred edges to chew on
+    // low-degree graphs: several windows per CTA so that a CTA has a few thousand entries to chew on
+    // (measured on the products shape, 405 entries / window: 1 -> 4 windows per CTA = -28 % time)
     const long long per_window = n_windows > 0 ? (long long)(nnz / n_windows) : 0;
     int wpc = tuning().wpc;
     if (wpc <= 0) {
       wpc = 1;
-      while (wpc < MAX_WPC && per_window * wpc < 384) wpc <<= 1;
+      while (wpc < MAX_WPC && per_window * wpc < 4096) wpc <<= 1;
     }
     if (wpc > MAX_WPC) wpc = MAX_WPC;
     p.wpc = wpc;

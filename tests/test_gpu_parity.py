@@ -301,13 +301,15 @@ def test_spmm_odd_width_large_uses_padded_copies(capi):
 
 
 # ---- tcgen05 dense super-window path -----------------------------------------------------------
+@pytest.mark.parametrize("warp_specialised", [0, 1])
 @pytest.mark.parametrize("name", ["sbm_1024", "rmat_1000", "band2_320", "holes_777", "dense_2048"])
-def test_spmm_dense_superwindows_tcgen05(capi, name):
+def test_spmm_dense_superwindows_tcgen05(capi, name, warp_specialised):
     rp, ci = GRAPHS[name]
     n = rp.size - 1
     d_rp, d_ci = dev(rp), dev(ci)
     bp, etc, etr, ht = capi.preprocess(d_ci, d_rp, "all_tc")
     old = capi.set_tuning("umma", 1)
+    old_ws = capi.set_tuning("dense_ws", warp_specialised)
     try:
         plan = capi.DensePlan(d_rp, d_ci, etr, ht, min_reuse=0.0)
         assert plan.n_dense == sum(1 for s in range((n + 127) // 128) if rp[min(128 * s + 128, n)] > rp[128 * s])
@@ -328,6 +330,7 @@ def test_spmm_dense_superwindows_tcgen05(capi, name):
         assert rel_fro(got, oracle.spmm(rp, ci, x, precision=1)) <= TOL_TF32
     finally:
         capi.set_tuning("umma", old)
+        capi.set_tuning("dense_ws", old_ws)
 
 
 def test_spmm_dense_plan_mixed_labels(capi):
