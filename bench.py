@@ -45,10 +45,13 @@ def parse():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink N and nnz (smoke runs only)")
     ap.add_argument("--classifier", default="shipped",
                     help="core selector: shipped (reference, all CUDA-core) | intended | b200 | all_tc")
-    ap.add_argument("--precision", default="tf32", choices=["tf32", "tf32x2", "fp32"])
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "tf32x2", "fp32", "bf16"])
     ap.add_argument("--slab", type=int, default=-1, help="feature-slab width (-1 = library default)")
     ap.add_argument("--long-row", type=int, default=-1)
     ap.add_argument("--vec8", type=int, default=-1, help="256-bit gathers: 1 on, 0 off (-1 = library default)")
+    ap.add_argument("--exchange-slabs", type=int, default=1,
+                    help="N > 1: all-gather X in this many feature slabs, slab k+1 in flight while the SpMM of slab k runs "
+                         "(1 = one all-gather, then one SpMM)")
     ap.add_argument("--dense", action="store_true", help="tcgen05 dense super-window plan (with --classifier b200|all_tc)")
     ap.add_argument("--tune", action="append", default=[], help="library tuning knob key=value (repeatable)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -296,7 +299,34 @@ def main():
     else:
         ci_run, x_rows_run = ci_l, n
 
+    n_slabs = max(1, args.exchange_slabs) if world > 1 else 1
+    if world > 1 and n_slabs > 1:
+        width = (dim // n_slabs + 7) // 8 * 8
+        edges = list(range(0, dim, width)) + [dim]
+        comm_stream = torch.cuda.Stream(device=dev)
+        pads = [torch.zeros(max_rows, edges[k + 1] - edges[k], device=dev) for k in range(len(edges) - 1)]
+        gats = [torch.empty(world * max_rows, edges[k + 1] - edges[k], device=dev) for k in range(len(edges) - 1)]
+        y_out = torch.empty(n_l, dim, device=dev)
+
     def step():
+        if world > 1 and n_slabs > 1:
+            # exchange pipelined in feature slabs: slab k+1 travels on the communication stream while the
+            # hybrid kernel works on slab k (the kernel takes row-strided views: ldx / ldy)
+            cur = torch.cuda.current_stream(dev)
+            comm_stream.wait_stream(cur)
+            evs = []
+            for k in range(len(edges) - 1):
+                with torch.cuda.stream(comm_stream):
+                    pads[k][:n_l].copy_(x_loc[:, edges[k]:edges[k + 1]])
+                    dist.all_gather_into_tensor(gats[k], pads[k])
+                    e = torch.cuda.Event()
+                    e.record(comm_stream)
+                evs.append(e)
+            for k in range(len(edges) - 1):
+                cur.wait_event(evs[k])
+                HCSPMM.spmm_strided(gats[k], rp_l, ci_run, *pre[:4], y_out[:, edges[k]:edges[k + 1]], False)
+            comm_stream.wait_stream(cur)
+            return y_out
         if world > 1:
             dist.all_gather_into_tensor(gathered, x_pad)
             return HCSPMM.forward(gathered, rp_l, ci_run, *pre)[0]
@@ -337,6 +367,24 @@ def main():
     ms_per_step = total_ms / args.steps
     flops = 2.0 * nnz * dim
     value = flops / (ms_per_step * 1e-3) / 1e9
+
+    phases = None
+    if world > 1:
+        def tm(fn, k=5):
+            fn()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(k):
+                fn()
+            b.record()
+            barrier()
+            t = torch.tensor([a.elapsed_time(b) / k], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t)
+        phases = {"exchange_only_ms": tm(lambda: dist.all_gather_into_tensor(gathered, x_pad)),
+                  "kernel_only_ms": tm(lambda: HCSPMM.forward(gathered, rp_l, ci_run, *pre)),
+                  "exchange_bytes_per_rank": int((world - 1) * max_rows * dim * 4)}
 
     # quick full-size sanity inside the bench (not timed): X = 1 gives the row degrees exactly
     ones = torch.ones(x_rows_run, 8, device=dev)
@@ -438,7 +486,9 @@ def main():
                            "nodes": n, "stored_entries": nnz, "dim": dim, "classifier": args.classifier,
                            "precision_tc_windows": args.precision, "tc_windows": tc_windows, "dense_groups_tcgen05": dense_groups,
                            "windows": (n_l + 15) // 16, "partition": f"row windows, nnz-balanced, {world} shard(s)",
-                           "exchange": "NCCL all_gather_into_tensor of row-sharded X per step" if world > 1 else "none",
+                           "exchange": ("NCCL all_gather_into_tensor of row-sharded X per step, %d feature slab(s) pipelined with the SpMM"
+                                        % n_slabs) if world > 1 else "none",
+                           "phases": phases,
                            "l2": "inputs larger than L2 (X %.0f MB + CSR %.0f MB vs 126 MB), no flush" %
                                  (n * dim * 4 / 1e6, nnz * 4 / 1e6),
                            "preprocess_ms": prep_ms, "graph_gen_s": t_gen,

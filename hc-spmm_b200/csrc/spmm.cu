@@ -60,8 +60,8 @@ constexpr int MAX_WPC = 8;
 // The 256-bit form also carries an L2 eviction priority: X rows are loaded evict_last so the
 // streamed column ids / Y writes do not push the gathered matrix out of the 126 MB L2.
 // ---------------------------------------------------------------------------------------
-template <int VW> struct Vec;
-template <> struct Vec<4> {
+template <int VW, bool B16 = false> struct Vec;
+template <> struct Vec<4, false> {
   float4 a;
   __device__ __forceinline__ void zero() { a = make_float4(0.f, 0.f, 0.f, 0.f); }
   __device__ __forceinline__ void load(const float *p) { a = ldg_f4(p); }
@@ -75,7 +75,7 @@ template <> struct Vec<4> {
   __device__ __forceinline__ void load_plain(const float *p) { a = *reinterpret_cast<const float4 *>(p); }
   __device__ __forceinline__ void store(float *p) const { *reinterpret_cast<float4 *>(p) = a; }
 };
-template <> struct Vec<8> {
+template <> struct Vec<8, false> {
   float4 a, b;
   __device__ __forceinline__ void zero() { a = b = make_float4(0.f, 0.f, 0.f, 0.f); }
   __device__ __forceinline__ void load(const float *p) {
@@ -104,6 +104,42 @@ template <> struct Vec<8> {
   }
 };
 
+// BF16-stored X (precision = BF16): 8 features arrive as one 128-bit load of eight bfloat16 and are
+// widened to FP32 (a shift / mask each) before the FP32 accumulation.  Pointers and offsets into X
+// are kept in float units, i.e. halved (XDIV = 2).
+template <> struct Vec<8, true> {
+  float4 a, b;
+  __device__ __forceinline__ void zero() { a = b = make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ void load(const float *p) {
+    const float4 raw = ldg_f4(p);
+    const uint32_t w0 = __float_as_uint(raw.x), w1 = __float_as_uint(raw.y), w2 = __float_as_uint(raw.z),
+                   w3 = __float_as_uint(raw.w);
+    a = make_float4(__uint_as_float(w0 << 16), __uint_as_float(w0 & 0xffff0000u), __uint_as_float(w1 << 16),
+                    __uint_as_float(w1 & 0xffff0000u));
+    b = make_float4(__uint_as_float(w2 << 16), __uint_as_float(w2 & 0xffff0000u), __uint_as_float(w3 << 16),
+                    __uint_as_float(w3 & 0xffff0000u));
+  }
+  __device__ __forceinline__ void add(const Vec &o) { add4(a, o.a); add4(b, o.b); }
+  __device__ __forceinline__ void xor_reduce(int off) {
+    a.x += __shfl_xor_sync(0xffffffffu, a.x, off);
+    a.y += __shfl_xor_sync(0xffffffffu, a.y, off);
+    a.z += __shfl_xor_sync(0xffffffffu, a.z, off);
+    a.w += __shfl_xor_sync(0xffffffffu, a.w, off);
+    b.x += __shfl_xor_sync(0xffffffffu, b.x, off);
+    b.y += __shfl_xor_sync(0xffffffffu, b.y, off);
+    b.z += __shfl_xor_sync(0xffffffffu, b.z, off);
+    b.w += __shfl_xor_sync(0xffffffffu, b.w, off);
+  }
+  __device__ __forceinline__ void load_plain(const float *p) {   // FP32 side (Y)
+    a = *reinterpret_cast<const float4 *>(p);
+    b = *reinterpret_cast<const float4 *>(p + 4);
+  }
+  __device__ __forceinline__ void store(float *p) const {
+    *reinterpret_cast<float4 *>(p) = a;
+    *reinterpret_cast<float4 *>(p + 4) = b;
+  }
+};
+
 #ifndef HCSPMM_INFLIGHT_BYTES
 #define HCSPMM_INFLIGHT_BYTES 128  // gathered bytes kept in flight per lane (ring depth x vector bytes)
 #endif
@@ -113,19 +149,20 @@ template <> struct Vec<8> {
 // chunk0, chunk0 + chunk_stride, ...   A group of LPE lanes reads one X row, lane g of the group
 // owning vectors g, g + LPE, ... (NV of them, VW floats each).
 // ---------------------------------------------------------------------------------------
-template <int LPE, int NV, int VW>
-__device__ __forceinline__ void gather_accumulate(Vec<VW> (&acc)[NV], const float *__restrict__ xlane,
+template <int LPE, int NV, int VW, bool B16>
+__device__ __forceinline__ void gather_accumulate(Vec<VW, B16> (&acc)[NV], const float *__restrict__ xlane,
                                                   long long ldx, int x_rows,
                                                   const int *__restrict__ colidx, int eb, int ee,
                                                   int chunk0, int chunk_stride, int lane, int q,
                                                   const bool (&active)[NV], bool all_active) {
   constexpr int G = 32 / LPE;         // edges handled concurrently by one warp
   constexpr int STEPS = 32 / G;       // gather steps per full 32-edge chunk
-  constexpr int U0 = HCSPMM_INFLIGHT_BYTES / (NV * VW * 4);
+  constexpr int XDIV = B16 ? 2 : 1;      // X offsets in float units: a BF16 row is half as long
+  constexpr int U0 = HCSPMM_INFLIGHT_BYTES * XDIV / (NV * VW * 4);
   constexpr int U = U0 < 1 ? 1 : (U0 > STEPS ? STEPS : U0);   // ring depth
   int voff[NV];   // float offset of vector i from xlane; inactive lanes point at the slab's first vector
 #pragma unroll
-  for (int i = 0; i < NV; ++i) voff[i] = active[i] ? i * LPE * VW : -(lane % LPE) * VW;
+  for (int i = 0; i < NV; ++i) voff[i] = (active[i] ? i * LPE * VW : -(lane % LPE) * VW) / XDIV;
   int base = eb + chunk0 * 32;
   int c_next = (base + lane < ee) ? __ldg(colidx + base + lane) : -1;
   for (; base < ee; base += chunk_stride * 32) {
@@ -139,7 +176,7 @@ __device__ __forceinline__ void gather_accumulate(Vec<VW> (&acc)[NV], const floa
       // full chunk, every id valid: unpredicated ring of U loads in flight -- slot s % U is consumed
       // and immediately refilled with step s + U.  Lanes beyond the slab width (voff < 0) re-read
       // the row's first vector (same cache line as lane 0) and never store their sums.
-      Vec<VW> v[U][NV];
+      Vec<VW, B16> v[U][NV];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int cu = __shfl_sync(0xffffffffu, c, u * G + q);
@@ -161,7 +198,7 @@ __device__ __forceinline__ void gather_accumulate(Vec<VW> (&acc)[NV], const floa
     } else {
 #pragma unroll 1
       for (int t = 0; t * G < n; t += U) {
-        Vec<VW> v[U][NV];
+        Vec<VW, B16> v[U][NV];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int j = (t + u) * G + q;
@@ -170,7 +207,7 @@ __device__ __forceinline__ void gather_accumulate(Vec<VW> (&acc)[NV], const floa
           const float *src = xlane + (long long)cu * ldx;
 #pragma unroll
           for (int i = 0; i < NV; ++i) {
-            if (ok && active[i]) v[u][i].load(src + i * LPE * VW);
+            if (ok && active[i]) v[u][i].load(src + i * LPE * VW / XDIV);
             else v[u][i].zero();
           }
         }
@@ -188,12 +225,13 @@ __device__ __forceinline__ void gather_accumulate(Vec<VW> (&acc)[NV], const floa
 // once and nothing is reduced across lanes.  The group fetches LPE column ids with one load and
 // broadcasts them inside the group (sub-warp shuffle masks: groups may run different trip counts).
 // ---------------------------------------------------------------------------------------
-template <int LPE, int NV, int VW>
-__device__ __forceinline__ void gather_group_row(Vec<VW> (&acc)[NV], const float *__restrict__ xlane,
+template <int LPE, int NV, int VW, bool B16>
+__device__ __forceinline__ void gather_group_row(Vec<VW, B16> (&acc)[NV], const float *__restrict__ xlane,
                                                  long long ldx, int x_rows,
                                                  const int *__restrict__ colidx, int eb, int ee, int lane,
                                                  int q, int g, const bool (&active)[NV]) {
-  constexpr int UB0 = HCSPMM_INFLIGHT_BYTES / (NV * VW * 4);
+  constexpr int XDIV = B16 ? 2 : 1;
+  constexpr int UB0 = HCSPMM_INFLIGHT_BYTES * XDIV / (NV * VW * 4);
   constexpr int UB = UB0 < 1 ? 1 : (UB0 > LPE ? LPE : UB0);
   const unsigned gmask = LPE == 32 ? 0xffffffffu : (((1u << LPE) - 1u) << (q * LPE));
   (void)lane;
@@ -202,7 +240,7 @@ __device__ __forceinline__ void gather_group_row(Vec<VW> (&acc)[NV], const float
     const int cnt = min(LPE, ee - e);
 #pragma unroll 1
     for (int j0 = 0; j0 < cnt; j0 += UB) {
-      Vec<VW> v[UB][NV];
+      Vec<VW, B16> v[UB][NV];
 #pragma unroll
       for (int u = 0; u < UB; ++u) {
         const int cu = __shfl_sync(gmask, my, q * LPE + ((j0 + u) & (LPE - 1)));
@@ -210,7 +248,7 @@ __device__ __forceinline__ void gather_group_row(Vec<VW> (&acc)[NV], const float
         const float *src = xlane + (long long)cu * ldx;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
-          if (ok && active[i]) v[u][i].load(src + i * LPE * VW);
+          if (ok && active[i]) v[u][i].load(src + i * LPE * VW / XDIV);
           else v[u][i].zero();
         }
       }
@@ -222,8 +260,8 @@ __device__ __forceinline__ void gather_group_row(Vec<VW> (&acc)[NV], const float
   }
 }
 
-template <int LPE, int NV, int VW>
-__device__ __forceinline__ void group_reduce(Vec<VW> (&acc)[NV]) {
+template <int LPE, int NV, int VW, bool B16>
+__device__ __forceinline__ void group_reduce(Vec<VW, B16> (&acc)[NV]) {
 #pragma unroll
   for (int o = LPE; o < 32; o <<= 1)
 #pragma unroll
@@ -349,7 +387,7 @@ __device__ __forceinline__ void tc_window(const SpmmParams &p, int w, int e0, in
 // ---------------------------------------------------------------------------------------
 // MINB = minimum resident CTAs per SM the register allocation must allow: 2 for high-degree graphs
 // (the gather ring wants registers), 3 for low-degree graphs (latency hiding wants warps).
-template <int LPE, int NV, int VW, int MINB>
+template <int LPE, int NV, int VW, int MINB, bool B16 = false>
 __global__ void __launch_bounds__(CTA_THREADS, MINB) spmm_hybrid_kernel(const SpmmParams p) {
   extern __shared__ __align__(16) float smem[];
   __shared__ int rp[BLK_H * MAX_WPC + 1];
@@ -411,7 +449,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) spmm_hybrid_kernel(const Sp
 #pragma unroll
   for (int i = 0; i < NV; ++i) active[i] = (g + i * LPE) < nvec;
   const bool all_active = nvec == LPE * NV;
-  const float *xlane = p.x + feat0 + g * VW;
+  const float *xlane = p.x + (feat0 + g * VW) / (B16 ? 2 : 1);   // BF16 rows: float units are halved
   // phase A is for CTAs made of short rows only (mean population below p.short_row = knob * G);
   // in a mixed CTA the idle lane groups would cost more than the one-warp-per-row bookkeeping
   const int e_cta = rp[rows_here] - rp[0];
@@ -424,16 +462,16 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) spmm_hybrid_kernel(const Sp
     for (int r = wid * G + q; r < rows_here; r += CTA_WARPS * G) {
       const int eb = rp[r], ee = rp[r + 1];
       if (ee - eb >= short_row || ((tcmask >> (r / BLK_H)) & 1u)) continue;
-      Vec<VW> acc[NV];
+      Vec<VW, B16> acc[NV];
 #pragma unroll
       for (int i = 0; i < NV; ++i) acc[i].zero();
-      gather_group_row<LPE, NV, VW>(acc, xlane, p.ldx, p.x_rows, p.colidx, eb, ee, lane, q, g, active);
+      gather_group_row<LPE, NV, VW, B16>(acc, xlane, p.ldx, p.x_rows, p.colidx, eb, ee, lane, q, g, active);
       float *yrow = p.y + (long long)(r0 + r) * p.ldy + feat0 + g * VW;
 #pragma unroll
       for (int i = 0; i < NV; ++i)
         if (active[i]) {
           if (p.accumulate) {
-            Vec<VW> o;
+            Vec<VW, B16> o;
             o.load_plain(yrow + i * LPE * VW);
             acc[i].add(o);
           }
@@ -469,19 +507,19 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) spmm_hybrid_kernel(const Sp
     if (r >= rows_here) break;
     const int eb = rp[r], ee = rp[r + 1];
     if (ee - eb >= p.long_row || ee - eb < short_row || ee == eb || ((tcmask >> (r / BLK_H)) & 1u)) continue;
-    Vec<VW> acc[NV];
+    Vec<VW, B16> acc[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) acc[i].zero();
-    gather_accumulate<LPE, NV, VW>(acc, xlane, p.ldx, p.x_rows, p.colidx, eb, ee, 0, 1, lane, q, active,
+    gather_accumulate<LPE, NV, VW, B16>(acc, xlane, p.ldx, p.x_rows, p.colidx, eb, ee, 0, 1, lane, q, active,
                                    all_active);
-    group_reduce<LPE, NV, VW>(acc);
+    group_reduce<LPE, NV, VW, B16>(acc);
     if (q == 0) {
       float *yrow = p.y + (long long)(r0 + r) * p.ldy + feat0 + g * VW;
 #pragma unroll
       for (int i = 0; i < NV; ++i)
         if (active[i]) {
           if (p.accumulate) {
-            Vec<VW> o;
+            Vec<VW, B16> o;
             o.load_plain(yrow + i * LPE * VW);
             acc[i].add(o);
           }
@@ -496,12 +534,12 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) spmm_hybrid_kernel(const Sp
   for (int r = 0; r < rows_here; ++r) {
     const int eb = rp[r], ee = rp[r + 1];
     if (ee - eb < p.long_row || ((tcmask >> (r / BLK_H)) & 1u)) continue;
-    Vec<VW> acc[NV];
+    Vec<VW, B16> acc[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) acc[i].zero();
-    gather_accumulate<LPE, NV, VW>(acc, xlane, p.ldx, p.x_rows, p.colidx, eb, ee, wid, CTA_WARPS, lane, q,
+    gather_accumulate<LPE, NV, VW, B16>(acc, xlane, p.ldx, p.x_rows, p.colidx, eb, ee, wid, CTA_WARPS, lane, q,
                                    active, all_active);
-    group_reduce<LPE, NV, VW>(acc);
+    group_reduce<LPE, NV, VW, B16>(acc);
     if (q == 0) {
 #pragma unroll
       for (int i = 0; i < NV; ++i)
@@ -586,6 +624,21 @@ void keep_mempool_blocks() {
   tuned[dev] = true;
 }
 
+// X (FP32, leading dim ldx) -> dense BF16 copy [rows, dim], round to nearest even
+__global__ void f32_to_bf16_rows_kernel(const float *__restrict__ x, long long ldx, int dim2, uint32_t *__restrict__ xb,
+                                        long long total2) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total2; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / dim2;
+    const int c = (int)(i - r * dim2) * 2;
+    const float lo = __ldg(x + r * ldx + c), hi = __ldg(x + r * ldx + c + 1);
+    const uint32_t ulo = __float_as_uint(lo), uhi = __float_as_uint(hi);
+    // RNE on the upper 16 bits (NaN / Inf pass through the truncation unchanged enough for a gather-sum)
+    const uint32_t rlo = ((ulo & 0x7f800000u) == 0x7f800000u) ? ulo : ulo + 0x7fffu + ((ulo >> 16) & 1u);
+    const uint32_t rhi = ((uhi & 0x7f800000u) == 0x7f800000u) ? uhi : uhi + 0x7fffu + ((uhi >> 16) & 1u);
+    xb[i] = (rlo >> 16) | (rhi & 0xffff0000u);
+  }
+}
+
 static size_t hybrid_smem_bytes(int S, bool tc) {
   size_t cuda_path = (size_t)CTA_WARPS * S * sizeof(float);
   size_t tc_path = tc ? (size_t)(2 * (UCAP + KC) + NSTAGE * KC * (S + 8)) * sizeof(float) : 0;
@@ -602,6 +655,17 @@ static cudaError_t launch_hybrid_b(const SpmmParams &p, dim3 grid, size_t smem, 
   spmm_hybrid_kernel<LPE, NV, VW, MINB><<<grid, CTA_THREADS, smem, stream>>>(q);
   return cudaGetLastError();
 }
+template <int LPE, int NV>
+static cudaError_t launch_hybrid_bf16(const SpmmParams &p, dim3 grid, size_t smem, cudaStream_t stream) {
+  cudaError_t err = cudaFuncSetAttribute(spmm_hybrid_kernel<LPE, NV, 8, HCSPMM_MIN_CTAS, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  SpmmParams q = p;
+  q.short_row = p.short_row * (32 / LPE);
+  spmm_hybrid_kernel<LPE, NV, 8, HCSPMM_MIN_CTAS, true><<<grid, CTA_THREADS, smem, stream>>>(q);
+  return cudaGetLastError();
+}
+
 template <int LPE, int NV, int VW>
 static cudaError_t launch_hybrid(const SpmmParams &p, dim3 grid, size_t smem, cudaStream_t stream) {
   // p.wpc > 1 <=> low-degree graph (few hundred entries per window)
@@ -626,11 +690,16 @@ int launch_spmm(const float *x, int64_t ldx, int32_t x_rows, const int32_t *rowp
     set_error("spmm: leading dimension smaller than dim");
     return HCSPMM_E_INVALID;
   }
-  if (precision < 0 || precision > HCSPMM_PRECISION_FP32) {
+  if (precision < 0 || precision > HCSPMM_PRECISION_BF16) {
     set_error("spmm: unknown precision %d", precision);
     return HCSPMM_E_INVALID;
   }
-  const bool labels = ht != nullptr && precision != HCSPMM_PRECISION_FP32;
+  // BF16 mode: X is stored as bfloat16 for the gather (half the L2 / HBM traffic of the dominant
+  // stream), FP32 accumulate, every window on the CUDA-core path.  Needs dim % 8 == 0 and an aligned
+  // Y; anything else is computed in FP32 (which is within the BF16 tolerance a fortiori).
+  const bool y_vec = (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (ldy & 3) == 0;
+  if (precision == HCSPMM_PRECISION_BF16 && !((dim & 7) == 0 && y_vec)) precision = HCSPMM_PRECISION_FP32;
+  const bool labels = ht != nullptr && precision != HCSPMM_PRECISION_FP32 && precision != HCSPMM_PRECISION_BF16;
   if (labels && (!bp || (nnz > 0 && (!etc || !etr)))) {
     set_error("spmm: hybrid_type given without blockPartition/edgeToColumn/edgeToRow");
     return HCSPMM_E_INVALID;
@@ -651,6 +720,36 @@ int launch_spmm(const float *x, int64_t ldx, int32_t x_rows, const int32_t *rowp
   const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0 &&
                    (ldx & 3) == 0 && (ldy & 3) == 0 && (dim & 3) == 0;
   cudaError_t err;
+  if (precision == HCSPMM_PRECISION_BF16) {
+    uint32_t *xb = nullptr;
+    keep_mempool_blocks();
+    err = cudaMallocAsync(&xb, sizeof(uint16_t) * (size_t)x_rows * dim, stream);
+    if (err != cudaSuccess) { set_error("spmm bf16: cudaMallocAsync: %s", cudaGetErrorString(err)); return (int)err; }
+    const long long total2 = (long long)x_rows * (dim / 2);
+    f32_to_bf16_rows_kernel<<<1184, 256, 0, stream>>>(x, ldx, dim / 2, xb, total2);
+    p.x = reinterpret_cast<const float *>(xb);
+    p.ldx = dim / 2;
+    int slab = tuning().slab > 0 ? (tuning().slab + 31) / 32 * 32 : 512;
+    if (slab > 512) slab = 512;
+    if (slab > dim) slab = dim;
+    p.slab = slab;
+    const long long per_window = n_windows > 0 ? (long long)(nnz / n_windows) : 0;
+    int wpc = tuning().wpc;
+    if (wpc <= 0) { wpc = 1; while (wpc < MAX_WPC && per_window * wpc < 4096) wpc <<= 1; }
+    if (wpc > MAX_WPC) wpc = MAX_WPC;
+    p.wpc = wpc;
+    p.n_windows = n_windows;
+    dim3 grid((n_windows + wpc - 1) / wpc, (dim + slab - 1) / slab, 1);
+    const size_t smem = hybrid_smem_bytes(slab, false);
+    if (slab <= 32) err = launch_hybrid_bf16<4, 1>(p, grid, smem, stream);
+    else if (slab <= 64) err = launch_hybrid_bf16<8, 1>(p, grid, smem, stream);
+    else if (slab <= 128) err = launch_hybrid_bf16<16, 1>(p, grid, smem, stream);
+    else if (slab <= 256) err = launch_hybrid_bf16<32, 1>(p, grid, smem, stream);
+    else err = launch_hybrid_bf16<32, 2>(p, grid, smem, stream);
+    cudaFreeAsync(xb, stream);
+    if (err != cudaSuccess) { set_error("spmm bf16 launch: %s", cudaGetErrorString(err)); return (int)err; }
+    return 0;
+  }
   if (!vec && (long long)n_rows * dim >= (1 << 20) && tuning().pad_odd) {
     // Large operand with an odd width / unaligned rows (e.g. dim = 47 classes): run the vector
     // kernel on 32-byte-aligned padded copies instead of the one-warp-per-row scalar kernel.

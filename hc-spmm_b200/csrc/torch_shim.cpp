@@ -271,11 +271,11 @@ std::string set_classifier(const std::string &mode) {
 }
 
 std::string set_precision(const std::string &mode) {
-  static const char *names[] = {"tf32", "tf32x2", "fp32"};
+  static const char *names[] = {"tf32", "tf32x2", "fp32", "bf16"};
   std::string old = names[g_precision];
-  for (int i = 0; i < 3; ++i)
+  for (int i = 0; i < 4; ++i)
     if (mode == names[i]) { g_precision = i; return old; }
-  TORCH_CHECK(false, "unknown precision '", mode, "' (tf32|tf32x2|fp32)");
+  TORCH_CHECK(false, "unknown precision '", mode, "' (tf32|tf32x2|fp32|bf16)");
 }
 
 bool set_dense(bool on) {
@@ -327,7 +327,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("spmm_accumulate", &spmm_strided, "alias of spmm_strided");
   m.def("gemm_tf32", &gemm_tf32, "a @ b with TF32 tensor-core product");
   m.def("set_classifier", &set_classifier, "shipped | intended | b200 | all_cuda | all_tc; returns the previous mode");
-  m.def("set_precision", &set_precision, "tf32 | tf32x2 | fp32; returns the previous mode");
+  m.def("set_precision", &set_precision, "tf32 | tf32x2 | fp32 | bf16; returns the previous mode");
   m.def("set_dense", &set_dense, "tcgen05 kernels: dense super-window plans in preprocess()/forward*(), Update GEMM");
   m.def("set_bug_compat", &set_bug_compat, "read strided `weights` as raw memory like the reference");
   m.def("set_tuning", &set_tuning, "kernel tuning knob (long_row, slab); returns the previous value");

@@ -15,7 +15,7 @@ from .build import LIB_PATH
 
 BLK_H, BLK_W = 16, 8
 CLASSIFIERS = {"shipped": 0, "intended": 1, "b200": 2, "all_cuda": 3, "all_tc": 4}
-PRECISIONS = {"tf32": 0, "tf32x2": 1, "fp32": 2}
+PRECISIONS = {"tf32": 0, "tf32x2": 1, "fp32": 2, "bf16": 3}
 
 EXPORTS = [
     "hcspmm_version", "hcspmm_last_error", "hcspmm_set_tuning",

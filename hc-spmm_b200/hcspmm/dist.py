@@ -159,7 +159,12 @@ class DistGCN(torch.nn.Module):
     def forward(self, x_local):
         h = x_local
         for i, w in enumerate(self.weights):
-            h = ShardedAggregate.apply(torch.mm(h, w), self.graph, self.graph_t)
+            # A (H W) = (A H) W: exchange and aggregate at the narrower of the two widths -- the
+            # all-gather moves N * width * 4 bytes per rank and the SpMM gathers nnz * width * 4
+            if w.shape[1] <= w.shape[0]:
+                h = ShardedAggregate.apply(torch.mm(h, w), self.graph, self.graph_t)
+            else:
+                h = torch.mm(ShardedAggregate.apply(h, self.graph, self.graph_t), w)
             if i + 1 < len(self.weights):
                 h = torch.relu(h)
         return torch.nn.functional.log_softmax(h, dim=1)

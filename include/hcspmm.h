@@ -58,6 +58,10 @@ extern "C" {
 #define HCSPMM_PRECISION_TF32    0
 #define HCSPMM_PRECISION_TF32X2  1
 #define HCSPMM_PRECISION_FP32    2
+/*   BF16   : X is copied to bfloat16 (round to nearest even) for the gather -- half the bytes of the
+ *            dominant stream -- and accumulated in FP32 on the CUDA-core path for every window
+ *            (north star: 1e-2 against FP32 torch.sparse).  Needs dim % 8 == 0, else computed in FP32. */
+#define HCSPMM_PRECISION_BF16    3
 
 int hcspmm_version(void);
 const char *hcspmm_last_error(void);

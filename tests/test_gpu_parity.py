@@ -354,3 +354,19 @@ def test_spmm_dense_plan_mixed_labels(capi):
         assert capi.DensePlan(d_rp, d_ci, etr, dev(ht), min_reuse=1e6).n_dense == 0
     finally:
         capi.set_tuning("umma", old)
+
+
+# ---- BF16-stored X --------------------------------------------------------------------------------
+@pytest.mark.parametrize("dim", [8, 32, 64, 128, 256, 512, 200, 100])
+@pytest.mark.parametrize("name", ["rmat_1000", "rmat_hub_4096", "ring3_256", "holes_777"])
+def test_spmm_bf16_storage(capi, name, dim):
+    rp, ci = GRAPHS[name]
+    x = xmat(x_rows_for(rp, ci), dim, seed=dim + 11)
+    fp32 = oracle.spmm(rp, ci, x, precision=1)
+    bf16 = oracle.spmm(rp, ci, x, precision=2)          # X rounded to bfloat16 (RNE), FP32 sum
+    got = capi.spmm(dev(x), dev(rp), dev(ci), precision="bf16").cpu().numpy()
+    assert rel_fro(got, fp32) <= 1e-2                   # the north star's BF16 bar
+    if dim % 8 == 0:
+        assert rel_fro(got, bf16) <= 2e-5               # same rounding as the oracle's restatement
+    else:
+        assert rel_fro(got, fp32) <= TOL_FP32           # odd widths are computed in FP32
