@@ -32,6 +32,9 @@ def main():
     ap.add_argument("--schedule", default="gather", choices=["gather", "slabs"])
     ap.add_argument("--slabs", type=int, default=2)
     ap.add_argument("--classifier", default="shipped")
+    ap.add_argument("--model", default="gcn", choices=["gcn", "gin"],
+                    help="gcn: X' = A (X W) (GNN_model.py:61-162); gin: X' = (A X) W (GNN_model.py:166-232)")
+    ap.add_argument("--dense", action="store_true", help="tcgen05 dense super-window plans (single GPU)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -42,6 +45,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     import HCSPMM
     from hcspmm import dist as hd, graphs
+    HCSPMM.set_dense(bool(args.dense))
     HCSPMM.set_classifier(args.classifier)
     rp, ci, info = graphs.named(args.shape, device=dev, scale=args.scale)
     g = hd.ShardedGraph(rp, ci, schedule=args.schedule, n_slabs=args.slabs)
@@ -49,7 +53,8 @@ def main():
     gen = torch.Generator(device=dev).manual_seed(100 + rank)
     x = torch.randn(g.n_local, args.feat, device=dev, generator=gen)
     y = torch.randint(0, args.classes, (g.n_local,), device=dev, generator=gen)
-    model = hd.DistGCN(g, args.feat, args.hidden, args.classes, num_layers=args.layers, seed=0).to(dev)
+    model = hd.DistGCN(g, args.feat, args.hidden, args.classes, num_layers=args.layers, seed=0,
+                       order={"gcn": "auto", "gin": "aggregate_first"}[args.model]).to(dev)
     opt = torch.optim.Adam(model.parameters(), lr=0.01)
     times, losses = [], []
     for ep in range(args.warmup + args.epochs):
@@ -77,7 +82,7 @@ def main():
     if rank == 0:
         print(json.dumps({"metric": "gcn_epoch_ms", "value": times[len(times) // 2], "unit": "ms", "n_gpus": world,
                           "higher_is_better": False, "scaling": "strong", "min_ms": times[0],
-                          "config": {"workload": f"{args.layers}-layer GCN, {args.shape}-shape graph", "nodes": info["n"],
+                          "config": {"workload": f"{args.layers}-layer {args.model.upper()}, {args.shape}-shape graph", "dense": bool(args.dense), "nodes": info["n"],
                                      "stored_entries": info["nnz"], "feat": args.feat, "hidden": args.hidden,
                                      "classes": args.classes, "schedule": args.schedule, "classifier": args.classifier},
                           "loss_first": losses[0], "loss_last": losses[-1]}))

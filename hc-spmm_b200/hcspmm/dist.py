@@ -147,8 +147,11 @@ class DistGCN(torch.nn.Module):
     X and of the labels and a replica of the weights; Update GEMMs are row-local, Aggregations go
     through ShardedAggregate, weight gradients are summed with one all-reduce per step."""
 
-    def __init__(self, graph: ShardedGraph, in_dim, hidden, classes, num_layers=2, seed=0, graph_t=None):
+    def __init__(self, graph: ShardedGraph, in_dim, hidden, classes, num_layers=2, seed=0, graph_t=None,
+                 order: str = "auto"):
+        """order: "update_first" = A (H W) (GCN), "aggregate_first" = (A H) W (GIN), "auto" = the cheaper."""
         super().__init__()
+        self.order = order
         g = torch.Generator().manual_seed(seed)            # identical replicas on every rank
         dims = [in_dim] + [hidden] * (num_layers - 1) + [classes]
         self.weights = torch.nn.ParameterList(
@@ -161,7 +164,8 @@ class DistGCN(torch.nn.Module):
         for i, w in enumerate(self.weights):
             # A (H W) = (A H) W: exchange and aggregate at the narrower of the two widths -- the
             # all-gather moves N * width * 4 bytes per rank and the SpMM gathers nnz * width * 4
-            if w.shape[1] <= w.shape[0]:
+            update_first = {"update_first": True, "aggregate_first": False}.get(self.order, w.shape[1] <= w.shape[0])
+            if update_first:
                 h = ShardedAggregate.apply(torch.mm(h, w), self.graph, self.graph_t)
             else:
                 h = torch.mm(ShardedAggregate.apply(h, self.graph, self.graph_t), w)
