@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--slab", type=int, default=-1, help="feature-slab width (-1 = library default)")
     ap.add_argument("--long-row", type=int, default=-1)
     ap.add_argument("--vec8", type=int, default=-1, help="256-bit gathers: 1 on, 0 off (-1 = library default)")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "gather", "slabs", "halo", "peer"],
+                    help="N > 1: all-gather of X, all-gather pipelined in feature slabs, halo rows only (NCCL all-to-all), "
+                         "peer = halo rows pulled over NVLink peer memory by our own kernel (auto picks this)")
     ap.add_argument("--exchange-slabs", type=int, default=1,
                     help="N > 1: all-gather X in this many feature slabs, slab k+1 in flight while the SpMM of slab k runs "
                          "(1 = one all-gather, then one SpMM)")
@@ -251,11 +254,6 @@ def main():
     t_gen = time.perf_counter() - t_gen
     n, nnz = info["n"], info["nnz"]
 
-    cuts = partition.window_cuts(rp, world)
-    r0, r1 = cuts[rank], cuts[rank + 1]
-    rp_l, ci_l = partition.local_shard(rp, ci, r0, r1)
-    n_l, nnz_l = r1 - r0, ci_l.numel()
-
     if args.slab >= 0:
         HCSPMM.set_tuning("slab", args.slab)
     if args.long_row >= 0:
@@ -269,15 +267,22 @@ def main():
     HCSPMM.set_classifier(args.classifier)
     HCSPMM.set_precision(args.precision)
 
+    # row-window partition (nnz-balanced) + the exchange plan of hcspmm.dist; world == 1: the whole graph
+    from hcspmm import dist as hd
+    sg = hd.ShardedGraph(rp, ci, schedule=args.exchange, n_slabs=max(1, args.exchange_slabs))
+    cuts, r0, r1 = sg.cuts, sg.r0, sg.r1
+    rp_l, ci_run, pre = sg.rowptr, sg.colidx, sg.pre
+    n_l, nnz_l, x_rows_run = sg.n_local, sg.nnz_local, sg.x_rows
+
     # preprocessing (reported separately, like the paper: "x one SpMM")
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    pre = HCSPMM.preprocess(ci_l, rp_l, n_l, nnz_l, (n_l + 15) // 16)
     ev0.record()
-    pre = HCSPMM.preprocess(ci_l, rp_l, n_l, nnz_l, (n_l + 15) // 16)
+    pre = HCSPMM.preprocess(ci_run, rp_l, n_l, nnz_l, (n_l + 15) // 16)
     ev1.record()
     torch.cuda.synchronize()
     prep_ms = ev0.elapsed_time(ev1)
+    sg.pre = pre
     tc_windows = int((pre[3] != 0).sum())
     dense_groups = int(pre[4][1]) if (pre[4].device.type == "cpu" and pre[4].numel() >= 4) else 0
 
@@ -285,52 +290,11 @@ def main():
     g.manual_seed(1234)
     x_full = torch.randn(n, dim, device=dev, generator=g)       # same on every rank (same seed)
     x_loc = x_full[r0:r1].contiguous()
-    if world > 1:
-        # all_gather_into_tensor needs equal shards: pad every shard to the largest
-        max_rows = max(cuts[i + 1] - cuts[i] for i in range(world))
-        x_pad = torch.zeros(max_rows, dim, device=dev)
-        x_pad[:n_l] = x_loc
-        gathered = torch.empty(world * max_rows, dim, device=dev)
-        # column ids must address the padded layout: shard s starts at s * max_rows
-        bounds = torch.tensor(cuts, device=dev, dtype=torch.int32)
-        owner = torch.bucketize(ci_l, bounds[1:-1], right=True).to(torch.int32)
-        ci_run = (ci_l - bounds[owner.long()] + owner * max_rows).to(torch.int32).contiguous()
-        x_rows_run = world * max_rows
-    else:
-        ci_run, x_rows_run = ci_l, n
-
-    n_slabs = max(1, args.exchange_slabs) if world > 1 else 1
-    if world > 1 and n_slabs > 1:
-        width = (dim // n_slabs + 7) // 8 * 8
-        edges = list(range(0, dim, width)) + [dim]
-        comm_stream = torch.cuda.Stream(device=dev)
-        pads = [torch.zeros(max_rows, edges[k + 1] - edges[k], device=dev) for k in range(len(edges) - 1)]
-        gats = [torch.empty(world * max_rows, edges[k + 1] - edges[k], device=dev) for k in range(len(edges) - 1)]
-        y_out = torch.empty(n_l, dim, device=dev)
+    n_slabs = sg.n_slabs if (world > 1 and sg.schedule in ("slabs", "halo", "peer")) else 1
 
     def step():
-        if world > 1 and n_slabs > 1:
-            # exchange pipelined in feature slabs: slab k+1 travels on the communication stream while the
-            # hybrid kernel works on slab k (the kernel takes row-strided views: ldx / ldy)
-            cur = torch.cuda.current_stream(dev)
-            comm_stream.wait_stream(cur)
-            evs = []
-            for k in range(len(edges) - 1):
-                with torch.cuda.stream(comm_stream):
-                    pads[k][:n_l].copy_(x_loc[:, edges[k]:edges[k + 1]])
-                    dist.all_gather_into_tensor(gats[k], pads[k])
-                    e = torch.cuda.Event()
-                    e.record(comm_stream)
-                evs.append(e)
-            for k in range(len(edges) - 1):
-                cur.wait_event(evs[k])
-                HCSPMM.spmm_strided(gats[k], rp_l, ci_run, *pre[:4], y_out[:, edges[k]:edges[k + 1]], False)
-            comm_stream.wait_stream(cur)
-            return y_out
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, x_pad)
-            return HCSPMM.forward(gathered, rp_l, ci_run, *pre)[0]
-        return HCSPMM.forward(x_full, rp_l, ci_run, *pre)[0]
+        # N > 1: exchange of the row shards of X (all-gather or halo all-to-all), then the local SpMM
+        return sg.aggregate(x_loc if world > 1 else x_full)
 
     def barrier():
         if world > 1:
@@ -382,9 +346,11 @@ def main():
             t = torch.tensor([a.elapsed_time(b) / k], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             return float(t)
-        phases = {"exchange_only_ms": tm(lambda: dist.all_gather_into_tensor(gathered, x_pad)),
-                  "kernel_only_ms": tm(lambda: HCSPMM.forward(gathered, rp_l, ci_run, *pre)),
-                  "exchange_bytes_per_rank": int((world - 1) * max_rows * dim * 4)}
+        operand = sg.exchange(x_loc)
+        phases = {"exchange_only_ms": tm(lambda: sg.exchange(x_loc)),
+                  "kernel_only_ms": tm(lambda: HCSPMM.forward(operand, rp_l, ci_run, *pre)),
+                  "exchange_bytes_per_rank": int(sg.exchange_rows() * dim * 4),
+                  "exchange_rows_vs_allgather": sg.exchange_rows() / max(1, (world - 1) * sg.max_rows)}
 
     # quick full-size sanity inside the bench (not timed): X = 1 gives the row degrees exactly
     ones = torch.ones(x_rows_run, 8, device=dev)
@@ -393,7 +359,15 @@ def main():
     assert torch.equal(deg, want) or float((deg - want).abs().max()) <= 1e-3 * float(want.max()), \
         "degree check failed: kernel output is wrong"
 
-    # roofline of the dominant kernel (the one hybrid SpMM launch per step); single-GPU figures
+    # our kernels per step: the balanced path is merge_path_splits + spmm_balanced + fixup (library rule:
+    # mean row >= 8 entries, knob "balance"), else the one hybrid kernel; BF16 adds the X conversion kernel
+    bal_knob = HCSPMM.set_tuning("balance", 1)
+    HCSPMM.set_tuning("balance", bal_knob)
+    balanced = bal_knob >= 2 or (bal_knob == 1 and nnz_l >= 8 * n_l)
+    launches_per_step = (3 if balanced else 1) * n_slabs + (1 if args.precision == "bf16" else 0) * n_slabs
+    if world > 1 and sg.schedule == "peer":
+        launches_per_step += 1 + n_slabs          # hcspmm_peer_barrier + hcspmm_halo_pull per slab
+    # roofline of the dominant kernel (the SpMM launch of a step); single-GPU figures
     peak, peak_src = measured_peak_gbs()
     bytes_alg = nnz_l * (4 + 4 * dim) + n_l * (4 * dim + 4)
     bytes_min = 4 * nnz_l + 4 * (n_l + 1) + 4 * (n + n_l) * dim
@@ -408,7 +382,9 @@ def main():
     if kern_ms:
         ach = bytes_alg / (kern_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": traffic, "peak_source": peak_src, "kernel": "spmm_hybrid_kernel",
+                    "traffic": traffic, "peak_source": peak_src,
+                    "kernel": "spmm_balanced_kernel (+ merge_path_splits_kernel, spmm_balanced_fixup_kernel: the step)"
+                              if balanced else "spmm_hybrid_kernel",
                     "kernel_ms": kern_ms, "algorithmic_bytes": bytes_alg,
                     "compulsory_bytes": bytes_min, "compulsory_frac": bytes_min / (kern_ms * 1e-3) / 1e9 / peak,
                     "frac_of_nominal_8TBs": ach / 8000.0}
@@ -441,9 +417,7 @@ def main():
                 cur.wait_event(ev_in[b])
                 cur.wait_event(ev_out[b])                 # D2H of step i-2 has drained outs[b]
                 if world > 1:
-                    x_pad[:n_l].copy_(xd[b])
-                    dist.all_gather_into_tensor(gathered, x_pad)
-                    outs[b] = HCSPMM.forward(gathered, rp_l, ci_run, *pre)[0]
+                    outs[b] = sg.aggregate(xd[b])
                 else:
                     outs[b] = HCSPMM.forward(xd[b], rp_l, ci_run, *pre)[0]
                 ev_k[b].record(cur)
@@ -486,8 +460,12 @@ def main():
                            "nodes": n, "stored_entries": nnz, "dim": dim, "classifier": args.classifier,
                            "precision_tc_windows": args.precision, "tc_windows": tc_windows, "dense_groups_tcgen05": dense_groups,
                            "windows": (n_l + 15) // 16, "partition": f"row windows, nnz-balanced, {world} shard(s)",
-                           "exchange": ("NCCL all_gather_into_tensor of row-sharded X per step, %d feature slab(s) pipelined with the SpMM"
-                                        % n_slabs) if world > 1 else "none",
+                           "exchange": ({"gather": "NCCL all_gather_into_tensor of the row shards of X per step",
+                                         "slabs": "NCCL all_gather_into_tensor in %d feature slabs pipelined with the SpMM" % n_slabs,
+                                         "halo": "halo rows only: pack + NCCL all_to_all_single per step, %d feature slab(s)" % n_slabs,
+                                         "peer": "halo rows only, pulled from the owners' memory over NVLink by hcspmm_halo_pull "
+                                                 "after hcspmm_peer_barrier, %d feature slab(s)" % n_slabs}
+                                        [sg.schedule]) if world > 1 else "none",
                            "phases": phases,
                            "l2": "inputs larger than L2 (X %.0f MB + CSR %.0f MB vs 126 MB), no flush" %
                                  (n * dim * 4 / 1e6, nnz * 4 / 1e6),
@@ -495,10 +473,11 @@ def main():
                            "generator": "R-MAT(0.57,0.19,0.19,0.05) folded mod N, symmetrised, de-duplicated, "
                                         "ids permuted, seed %d" % shape["seed"]},
                 "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e, "clocks": clocks,
-                "gpu_launches": args.steps,
+                "gpu_launches": args.steps * launches_per_step, "launches_per_step": launches_per_step,
                 "step_ms": {"min": min(step_ms), "median": statistics.median(step_ms), "max": max(step_ms)}}
         print(json.dumps(line))
     if world > 1:
+        sg.close()
         dist.destroy_process_group()
     return 0
 

@@ -29,8 +29,8 @@ def main():
     ap.add_argument("--layers", type=int, default=2)
     ap.add_argument("--epochs", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--schedule", default="gather", choices=["gather", "slabs"])
-    ap.add_argument("--slabs", type=int, default=2)
+    ap.add_argument("--schedule", default="auto", choices=["auto", "gather", "slabs", "halo", "peer"])
+    ap.add_argument("--slabs", type=int, default=1)
     ap.add_argument("--classifier", default="shipped")
     ap.add_argument("--model", default="gcn", choices=["gcn", "gin"],
                     help="gcn: X' = A (X W) (GNN_model.py:61-162); gin: X' = (A X) W (GNN_model.py:166-232)")
@@ -50,9 +50,12 @@ def main():
     rp, ci, info = graphs.named(args.shape, device=dev, scale=args.scale)
     g = hd.ShardedGraph(rp, ci, schedule=args.schedule, n_slabs=args.slabs)
     del rp, ci
-    gen = torch.Generator(device=dev).manual_seed(100 + rank)
-    x = torch.randn(g.n_local, args.feat, device=dev, generator=gen)
-    y = torch.randint(0, args.classes, (g.n_local,), device=dev, generator=gen)
+    # the SAME problem at every N: global features / labels from one seed, then this rank's rows
+    # (A is binary and unnormalised like the reference's; features are scaled so the logits start O(1))
+    gen = torch.Generator(device=dev).manual_seed(100)
+    mean_deg = max(1.0, info["nnz"] / info["n"])
+    x = (torch.randn(info["n"], args.feat, device=dev, generator=gen) / mean_deg ** 2)[g.r0:g.r1].contiguous()
+    y = torch.randint(0, args.classes, (info["n"],), device=dev, generator=gen)[g.r0:g.r1].contiguous()
     model = hd.DistGCN(g, args.feat, args.hidden, args.classes, num_layers=args.layers, seed=0,
                        order={"gcn": "auto", "gin": "aggregate_first"}[args.model]).to(dev)
     opt = torch.optim.Adam(model.parameters(), lr=0.01)
@@ -79,14 +82,42 @@ def main():
             times.append(float(t))
             losses.append(float(l))
     times.sort()
+
+    # where an epoch goes: exchange and local SpMM of every aggregation width, timed on their own (max over ranks)
+    def tm(fn, k=5):
+        fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(k):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / k], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return round(float(t), 4)
+    phases = {}
+    with torch.no_grad():
+        for w in sorted({min(wt.shape) for wt in model.weights} if args.model == "gcn" else {wt.shape[0] for wt in model.weights}):
+            xx = torch.randn(g.n_local, w, device=dev)
+            op = g.exchange(xx).contiguous().clone()
+            phases[f"width{w}"] = {"exchange_ms": tm(lambda: g.exchange(xx)) if world > 1 else 0.0,
+                                   "spmm_ms": tm(lambda: g._spmm(op, g.rowptr, g.colidx, g.pre)),
+                                   "aggregate_ms": tm(lambda: g.aggregate(xx))}
     if rank == 0:
         print(json.dumps({"metric": "gcn_epoch_ms", "value": times[len(times) // 2], "unit": "ms", "n_gpus": world,
                           "higher_is_better": False, "scaling": "strong", "min_ms": times[0],
                           "config": {"workload": f"{args.layers}-layer {args.model.upper()}, {args.shape}-shape graph", "dense": bool(args.dense), "nodes": info["n"],
                                      "stored_entries": info["nnz"], "feat": args.feat, "hidden": args.hidden,
-                                     "classes": args.classes, "schedule": args.schedule, "classifier": args.classifier},
-                          "loss_first": losses[0], "loss_last": losses[-1]}))
+                                     "classes": args.classes, "schedule": g.schedule, "slabs": g.n_slabs,
+                                     "exchange_rows_vs_allgather": (g.exchange_rows() / max(1, (world - 1) * g.max_rows)) if world > 1 else None,
+                                     "classifier": args.classifier},
+                          "phases": phases, "loss_first": losses[0], "loss_last": losses[-1]}))
     if world > 1:
+        g.close()
         dist.destroy_process_group()
 
 

@@ -17,7 +17,7 @@ void set_error(const char *fmt, ...) {
 }
 
 Tuning &tuning() {
-  static Tuning t = {1024, 0, 1, 1, 0, 0, 1, 0, 1, 1};
+  static Tuning t = {1024, 0, 1, 1, 0, 0, 1, 0, 1, 1, 1, 0, 64};
   return t;
 }
 
@@ -88,6 +88,9 @@ int hcspmm_set_tuning(const char *key, int value) {
   else if (key && !strcmp(key, "umma_gemm")) slot = &tuning().umma_gemm;
   else if (key && !strcmp(key, "dense_ws")) slot = &tuning().dense_ws;
   else if (key && !strcmp(key, "occupancy3")) slot = &tuning().occupancy3;
+  else if (key && !strcmp(key, "balance")) slot = &tuning().balance;
+  else if (key && !strcmp(key, "chunk")) slot = &tuning().chunk;
+  else if (key && !strcmp(key, "warp_split")) slot = &tuning().warp_split;
   if (!slot) return -1;
   int old = *slot;
   *slot = value;

@@ -1,0 +1,162 @@
+// peer.cu -- the per-layer X exchange of the row-partitioned SpMM over NVLink peer memory.
+//
+// The reference has no multi-GPU code.  A row shard of A references only some rows of X ("halo":
+// 0.31 N remote rows for a 1/8 shard of the products shape, where an all-gather moves 0.875 N), so
+// instead of a collective every rank PULLS exactly the rows its shard references, straight out of
+// the owners' memory with NVLink loads:
+//   * every rank keeps its SpMM operand [halo rows of lower ranks | own rows | halo rows of higher ranks]
+//     in a cudaMalloc'ed buffer exported with CUDA IPC (hcspmm_peer_alloc / hcspmm_peer_open) -- one
+//     process per GPU, any launcher; the own rows are written in place and are what the peers read;
+//   * hcspmm_peer_barrier: one tiny kernel; thread s stores this rank's epoch into peer s's flag
+//     array (system-scope release) and spins on the local flag of peer s (acquire), so after it every
+//     peer's shard written before ITS barrier is visible.  Spins are bounded (~2 s) and report through
+//     *d_err instead of hanging the device;
+//   * hcspmm_halo_pull: operand row i (owner s = segment of i, row src_row[i] there) is copied with
+//     128-bit loads from peer_x[s]; eight rows in flight per warp cover the NVLink latency.
+// Buffers are used alternately (two per width) by the caller, so one barrier per aggregation suffices:
+// a shard buffer is rewritten only after the next barrier, which every peer enters after its pull.
+#include <string.h>
+
+#include "common.cuh"
+
+namespace hcspmm {
+
+__global__ void peer_barrier_kernel(int *const *flag_ptrs, int rank, int world, int epoch, int *err) {
+  const int s = threadIdx.x;
+  if (s >= world) return;
+  __threadfence_system();
+  int *remote = flag_ptrs[s] + rank;   // peer s's flag for me
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
+  const int *local = flag_ptrs[rank] + s;   // my flag for peer s
+  const long long t0 = clock64();
+  int v;
+  do {
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(local) : "memory");
+    if (v - epoch >= 0) break;
+    if (clock64() - t0 > 4000000000LL) {   // ~2 s at 2 GHz: a peer never arrived
+      if (err) atomicExch(err, 1);
+      break;
+    }
+    __nanosleep(64);
+  } while (true);
+  __threadfence_system();
+}
+
+constexpr int PULL_ROWS = 8;   // rows in flight per warp
+
+// dst[i, 0..width) = peer_x[owner(i)][src_row[i], c0 .. c0+width) for i in [row0, rows)   (width % 4 == 0)
+__global__ void __launch_bounds__(256) halo_pull_kernel(const float *const *__restrict__ peer_x, long long lds,
+                                                        const int *__restrict__ src_row, const int *__restrict__ seg,
+                                                        int world, int row0, int rows, int c0, int width,
+                                                        float *__restrict__ dst, long long ldd) {
+  __shared__ int s_seg[65];
+  __shared__ const float *s_base[64];
+  for (int i = threadIdx.x; i <= world; i += blockDim.x) s_seg[i] = seg[i];
+  for (int i = threadIdx.x; i < world; i += blockDim.x) s_base[i] = peer_x[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  const int nvec = width >> 2;
+  for (int r0 = row0 + warp * PULL_ROWS; r0 < rows; r0 += n_warps * PULL_ROWS) {
+    const float *src[PULL_ROWS];
+#pragma unroll
+    for (int j = 0; j < PULL_ROWS; ++j) {
+      const int i = min(r0 + j, rows - 1);
+      int s = 0;
+      while (s + 1 < world && i >= s_seg[s + 1]) ++s;
+      src[j] = s_base[s] + (long long)__ldg(src_row + i) * lds + c0;
+    }
+    for (int v = lane; v < nvec; v += 32) {
+      float4 t[PULL_ROWS];
+#pragma unroll
+      for (int j = 0; j < PULL_ROWS; ++j) t[j] = *reinterpret_cast<const float4 *>(src[j] + v * 4);
+#pragma unroll
+      for (int j = 0; j < PULL_ROWS; ++j)
+        if (r0 + j < rows) *reinterpret_cast<float4 *>(dst + (long long)(r0 + j) * ldd + c0 + v * 4) = t[j];
+    }
+  }
+}
+
+}  // namespace hcspmm
+
+using namespace hcspmm;
+
+extern "C" {
+
+int hcspmm_peer_alloc(size_t bytes, void **d_ptr, void *handle64) {
+  if (!d_ptr || !handle64 || bytes == 0) { set_error("peer_alloc: bad argument"); return HCSPMM_E_INVALID; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle is 64 bytes");
+  void *p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e == cudaSuccess) e = cudaMemset(p, 0, bytes);
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    if (p) cudaFree(p);
+    set_error("peer_alloc: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  memcpy(handle64, &h, 64);
+  *d_ptr = p;
+  return 0;
+}
+
+int hcspmm_peer_open(const void *handle64, void **d_ptr) {
+  if (!d_ptr || !handle64) { set_error("peer_open: bad argument"); return HCSPMM_E_INVALID; }
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  cudaError_t e = cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) { set_error("peer_open: %s", cudaGetErrorString(e)); return (int)e; }
+  return 0;
+}
+
+int hcspmm_peer_close(void *d_ptr) {
+  cudaError_t e = cudaIpcCloseMemHandle(d_ptr);
+  if (e != cudaSuccess) { set_error("peer_close: %s", cudaGetErrorString(e)); return (int)e; }
+  return 0;
+}
+
+int hcspmm_peer_free(void *d_ptr) {
+  cudaError_t e = cudaFree(d_ptr);
+  if (e != cudaSuccess) { set_error("peer_free: %s", cudaGetErrorString(e)); return (int)e; }
+  return 0;
+}
+
+int hcspmm_peer_barrier(int32_t *const *d_flag_ptrs, int32_t rank, int32_t world, int32_t epoch, int32_t *d_err,
+                        void *stream) {
+  if (!d_flag_ptrs || world < 1 || world > 64 || rank < 0 || rank >= world) {
+    set_error("peer_barrier: bad argument");
+    return HCSPMM_E_INVALID;
+  }
+  peer_barrier_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(reinterpret_cast<int *const *>(d_flag_ptrs), rank, world, epoch,
+                                                        d_err);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("peer_barrier: %s", cudaGetErrorString(e)); return (int)e; }
+  return 0;
+}
+
+int hcspmm_halo_pull(const float *const *d_peer_x, int64_t lds, const int32_t *d_src_row, const int32_t *d_seg,
+                     int32_t world, int32_t row_begin, int32_t row_end, int32_t col0, int32_t width, float *d_dst,
+                     int64_t ldd, void *stream) {
+  if (row_end <= row_begin || width == 0) return 0;
+  const int rows = row_end;
+  if (!d_peer_x || !d_src_row || !d_seg || !d_dst || world < 1 || world > 64 || row_begin < 0 || width < 0 || col0 < 0) {
+    set_error("halo_pull: bad argument");
+    return HCSPMM_E_INVALID;
+  }
+  if ((width & 3) || (col0 & 3) || (lds & 3) || (ldd & 3) || (reinterpret_cast<uintptr_t>(d_dst) & 15)) {
+    set_error("halo_pull: width, col0 and leading dims must be multiples of 4 floats, dst 16-byte aligned");
+    return HCSPMM_E_ALIGN;
+  }
+  const long long warps = ((long long)(row_end - row_begin) + PULL_ROWS - 1) / PULL_ROWS;
+  long long grid = (warps + 7) / 8;
+  if (grid > 148 * 8) grid = 148 * 8;
+  halo_pull_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(d_peer_x, lds, d_src_row, d_seg, world, row_begin, rows,
+                                                                     col0, width, d_dst, ldd);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("halo_pull: %s", cudaGetErrorString(e)); return (int)e; }
+  return 0;
+}
+
+}  // extern "C"

@@ -52,6 +52,21 @@ struct SpmmParams {
   int short_row;  // rows with <  short_row entries: one lane GROUP per row (G rows per warp at once)
   int wpc;        // 16-row windows per CTA (1..MAX_WPC), > 1 on low-degree graphs
   int n_windows;
+  int cuda_elsewhere;  // 1: CUDA-core windows (label 0) are computed by spmm_balanced_kernel, skip them here
+};
+
+// Work-balanced CUDA-core kernel (below): merge-path items over (rows + stored entries)
+struct BalParams {
+  SpmmParams s;
+  long long nnz;
+  int chunk;         // rows + entries per item (one CTA per item and feature slab)
+  int n_items;
+  float *partial;    // [n_items][2][dim] FP32 partial sums of rows that straddle item boundaries
+  int *split_row;    // [n_items][2]: row whose sum ENDS in this item but began earlier (slot 0) /
+                     //               row whose sum continues in the next item (slot 1); -1 = none
+  const int *splits; // [n_items + 1]: rows consumed before diagonal k * chunk (merge_path_splits_kernel)
+  int warp_split;    // > 0: items with a mean row length >= warp_split give every warp an equal run of entries;
+                     // other items (and 0) use the warp-per-row / CTA-per-long-row phases
 };
 constexpr int MAX_WPC = 8;
 
@@ -411,7 +426,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) spmm_hybrid_kernel(const Sp
     if (p.ht != nullptr)
       for (int i = 0; i < nwin; ++i) {
         const int l = __ldg(p.ht + w0 + i);
-        if (l == 2) sk |= 1u << i;
+        if (l == 2 || (l == 0 && p.cuda_elsewhere)) sk |= 1u << i;
         else if (l != 0 && p.precision != HCSPMM_PRECISION_FP32 && (S & 7) == 0) m |= 1u << i;
       }
     s_tcmask = m;
@@ -560,6 +575,326 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) spmm_hybrid_kernel(const Sp
 }
 
 // ---------------------------------------------------------------------------------------
+// Work-balanced CUDA-core kernel.  Power-law graphs put 10^5 stored entries into single rows (and
+// so into single 16-row windows): with one CTA per window the longest window bounds the kernel --
+// at the Reddit shape it is 0.29 of a CTA slot's fair share on one GPU and 2.3 x the share of a
+// 1/8 row shard.  Here the CUDA-core work is cut merge-path style instead: item k covers the
+// k-th run of `chunk` steps through the merged sequence (row ends, stored entries), so every CTA
+// gets the same rows + entries whatever the degree distribution.  A row that straddles item
+// boundaries is summed in pieces: every item writes the piece of its first / last row into
+// partial[k][0|1], and spmm_balanced_fixup_kernel adds the pieces of a row in item order -- a
+// fixed order, so results do not depend on scheduling (no atomics).
+// Rows of windows labelled tensor-core / dense are skipped (the hybrid kernel or the tcgen05
+// kernel computes them); their entries still count as item steps.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int merge_path_rows(const int *__restrict__ rowptr, int n_rows, long long nnz,
+                                               long long diag) {
+  long long lo = diag > nnz ? diag - nnz : 0;
+  long long hi = diag < n_rows ? diag : n_rows;
+  while (lo < hi) {   // first row whose end marker lies beyond the diagonal
+    const long long mid = (lo + hi) >> 1;
+    if ((long long)__ldg(rowptr + mid + 1) <= diag - 1 - mid) lo = mid + 1;
+    else hi = mid;
+  }
+  return (int)lo;
+}
+
+// All split points at once (one thread per diagonal): ~20 dependent loads each, but in parallel, so
+// the item CTAs start with two loads instead of two binary searches.
+__global__ void merge_path_splits_kernel(const int *__restrict__ rowptr, int n_rows, long long nnz, int chunk,
+                                         int n_items, int *__restrict__ splits) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n_items) return;
+  const long long total = (long long)n_rows + nnz;
+  long long diag = (long long)i * chunk;
+  if (diag > total) diag = total;
+  splits[i] = merge_path_rows(rowptr, n_rows, nnz, diag);
+}
+
+template <int LPE, int NV, int VW, int MINB, bool B16 = false>
+__global__ void __launch_bounds__(CTA_THREADS, MINB) spmm_balanced_kernel(const BalParams bp) {
+  const SpmmParams &p = bp.s;
+  extern __shared__ __align__(16) float smem[];   // [2 * CTA_WARPS * slab] row pieces | uint16 row offsets [chunk + 2]
+  __shared__ int s_next;
+  __shared__ int s_prow[CTA_WARPS][2];
+  constexpr int G = 32 / LPE;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int k = blockIdx.x;
+  const int feat0 = blockIdx.y * p.slab;
+  const int S = min(p.slab, p.dim - feat0);
+  const int nvec = S / VW;
+  const unsigned short *rp16 = reinterpret_cast<const unsigned short *>(smem + 2 * CTA_WARPS * p.slab);
+
+  // the item's two diagonals: rows consumed (precomputed) and entries consumed
+  const long long total = (long long)p.n_rows + bp.nnz;
+  const long long d0 = min(total, (long long)k * bp.chunk), d1 = min(total, (long long)(k + 1) * bp.chunk);
+  const int x0 = __ldg(bp.splits + k), x1 = __ldg(bp.splits + k + 1);
+  const int y0 = (int)(d0 - x0), y1 = (int)(d1 - x1);
+  if (tid == 0) s_next = 0;
+  // entries [y0, y1); rows x0 .. x1-1 end here, row x1 takes part through its entries below y1
+  const bool last_in = x1 < p.n_rows && __ldg(p.rowptr + x1) < y1;
+  const int rows_here = x1 - x0 + (last_in ? 1 : 0);
+  if (rows_here <= 0) {
+    if (tid == 0 && blockIdx.y == 0) bp.split_row[2 * k] = bp.split_row[2 * k + 1] = -1;
+    return;
+  }
+  // row ranges clipped to the item, as 16-bit offsets from y0 (chunk <= 16384): a small footprint
+  // leaves the shared-memory / L1 carve-out to the gathered rows
+  {
+    unsigned short *w16 = reinterpret_cast<unsigned short *>(smem + 2 * CTA_WARPS * p.slab);
+    for (int i = tid; i <= rows_here; i += CTA_THREADS)
+      w16[i] = (unsigned short)(min(max(__ldg(p.rowptr + x0 + i), y0), y1) - y0);
+  }
+  auto rp = [&](int i) -> int { return y0 + (int)rp16[i]; };
+  const int L = rows_here - 1;
+  const int s0 = __ldg(p.rowptr + x0), t0 = __ldg(p.rowptr + x0 + 1);
+  const bool lab0 = p.ht != nullptr && __ldg(p.ht + (x0 >> 4)) != 0;
+  const bool lab1 = p.ht != nullptr && last_in && __ldg(p.ht + (x1 >> 4)) != 0;
+  const bool is_tail = last_in && !lab1 && __ldg(p.rowptr + x1 + 1) > y1;     // row x1 continues in item k+1
+  const bool head_skip = s0 < y0 && t0 <= y0;                                 // row x0 was finished by item k-1
+  const bool is_head = s0 < y0 && t0 > y0 && !lab0 && !(is_tail && L == 0);   // row x0 began earlier, ends here
+  if (tid == 0 && blockIdx.y == 0) {
+    bp.split_row[2 * k] = is_head ? x0 : -1;
+    bp.split_row[2 * k + 1] = is_tail ? x1 : -1;
+  }
+  __syncthreads();
+
+  auto skip = [&](int i) -> bool {
+    return (i == 0 && head_skip) || (p.ht != nullptr && __ldg(p.ht + ((x0 + i) >> 4)) != 0);
+  };
+  auto out_row = [&](int i, int &acc_flag) -> float * {
+    if (i == 0 && is_head) { acc_flag = 0; return bp.partial + (size_t)(2 * k) * p.dim + feat0; }
+    if (i == L && is_tail) { acc_flag = 0; return bp.partial + (size_t)(2 * k + 1) * p.dim + feat0; }
+    acc_flag = p.accumulate;
+    return p.y + (long long)(x0 + i) * p.ldy + feat0;
+  };
+
+  const int q = lane / LPE, g = lane % LPE;
+  bool active[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) active[i] = (g + i * LPE) < nvec;
+  const bool all_active = nvec == LPE * NV;
+  const float *xlane = p.x + (feat0 + g * VW) / (B16 ? 2 : 1);
+  const int e_cta = y1 - y0;
+  const int short_row = (G > 1 && p.short_row > 0 && e_cta < rows_here * p.short_row &&
+                         2 * rows_here >= CTA_WARPS * G)
+                            ? 4 * p.short_row : 0;
+
+  // warp-split mode (items that are not made of short rows): every warp takes an equal, contiguous
+  // run of the item's entries and walks the rows it covers, so the eight warps finish together
+  // whatever the row lengths.  A row cut by a warp boundary is summed in pieces through shared
+  // memory, pieces added in warp order (same scheme as the item-level fix-up).
+  if (short_row == 0 && bp.warp_split > 0 && e_cta >= rows_here * bp.warp_split) {
+    float *pieces = smem;   // [CTA_WARPS][2][S]
+    const int ew = ((e_cta + CTA_WARPS - 1) / CTA_WARPS + 31) & ~31;
+    // first row with entries beyond position b (y0 <= b < y1)
+    auto row_of = [&](int b) -> int {
+      int lo = 0, hi = rows_here - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (rp(mid + 1) > b) hi = mid;
+        else lo = mid + 1;
+      }
+      return lo;
+    };
+    // run boundary w: the equal cut, moved to a row boundary when one lies within a quarter run --
+    // rows of moderate length then stay whole (no pieces, no pipeline restart inside them)
+    auto boundary = [&](int w) -> int {
+      const int b = y0 + w * ew;
+      if (w <= 0) return y0;
+      if (b >= y1) return y1;
+      const int r = row_of(b);
+      const int lo = rp(r), hi = rp(r + 1);
+      const int cand = (b - lo <= hi - b) ? lo : hi;
+      return (abs(cand - b) <= (ew >> 2)) ? cand : b;
+    };
+    const int wb = boundary(wid), we = boundary(wid + 1);
+    int head_row = -1, tail_row = -1;
+    if (wb < we) {
+      const int lo = row_of(wb);
+      for (int r = lo; r < rows_here && rp(r) < we; ++r) {
+        const int eb = max(rp(r), wb), ee = min(rp(r + 1), we);
+        if (ee <= eb || skip(r)) continue;
+        Vec<VW, B16> acc[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) acc[i].zero();
+        gather_accumulate<LPE, NV, VW, B16>(acc, xlane, p.ldx, p.x_rows, p.colidx, eb, ee, 0, 1, lane, q, active,
+                                            all_active);
+        group_reduce<LPE, NV, VW, B16>(acc);
+        int accf = 0;
+        float *dst;
+        if (rp(r + 1) > we) { dst = pieces + (wid * 2 + 1) * S; tail_row = r; }       // continues in the next warp
+        else if (rp(r) < wb) { dst = pieces + (wid * 2) * S; head_row = r; }          // began in an earlier warp
+        else dst = out_row(r, accf);
+        if (q == 0) {
+          dst += g * VW;
+#pragma unroll
+          for (int i = 0; i < NV; ++i)
+            if (active[i]) {
+              if (accf) {
+                Vec<VW, B16> o;
+                o.load_plain(dst + i * LPE * VW);
+                acc[i].add(o);
+              }
+              acc[i].store(dst + i * LPE * VW);
+            }
+        }
+      }
+    }
+    if (lane == 0) { s_prow[wid][0] = head_row; s_prow[wid][1] = tail_row; }
+    // empty rows of the item (never pieces)
+    if (!p.accumulate)
+      for (int r = tid; r < rows_here; r += CTA_THREADS)
+        if (rp(r + 1) == rp(r) && !skip(r))
+          for (int v = 0; v < (S >> 2); ++v)
+            *reinterpret_cast<float4 *>(p.y + (long long)(x0 + r) * p.ldy + feat0 + v * 4) =
+                make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    for (int b = 1; b < CTA_WARPS; ++b) {
+      const int r = s_prow[b][0];
+      if (r < 0) continue;
+      int a = b;
+      while (a > 0 && s_prow[a - 1][1] == r) --a;
+      int accf;
+      float *yrow = out_row(r, accf);
+      for (int v = tid; v < (S >> 2); v += CTA_THREADS) {
+        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int w = a; w < b; ++w) add4(sum, *reinterpret_cast<const float4 *>(pieces + (w * 2 + 1) * S + v * 4));
+        add4(sum, *reinterpret_cast<const float4 *>(pieces + (b * 2) * S + v * 4));
+        float4 *dst = reinterpret_cast<float4 *>(yrow + v * 4);
+        if (accf) add4(sum, *dst);
+        *dst = sum;
+      }
+    }
+    return;
+  }
+
+  // phase A: short rows, one lane group per row
+  if (short_row > 0) {
+    for (int r = wid * G + q; r < rows_here; r += CTA_WARPS * G) {
+      const int eb = rp(r), ee = rp(r + 1);
+      if (ee - eb >= short_row || skip(r)) continue;
+      Vec<VW, B16> acc[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) acc[i].zero();
+      gather_group_row<LPE, NV, VW, B16>(acc, xlane, p.ldx, p.x_rows, p.colidx, eb, ee, lane, q, g, active);
+      int accf;
+      float *yrow = out_row(r, accf) + g * VW;
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        if (active[i]) {
+          if (accf) {
+            Vec<VW, B16> o;
+            o.load_plain(yrow + i * LPE * VW);
+            acc[i].add(o);
+          }
+          acc[i].store(yrow + i * LPE * VW);
+        }
+    }
+    __syncwarp();
+  }
+
+  int has_medium = 0, has_long = 0;
+  for (int r = tid; r < rows_here; r += CTA_THREADS) {
+    const int d = rp(r + 1) - rp(r);
+    const bool sk = skip(r);
+    if (!sk) {
+      has_long |= d >= p.long_row;
+      has_medium |= d >= short_row && d < p.long_row && d > 0;
+    }
+    if (d == 0 && short_row == 0 && !p.accumulate && !sk) {   // empty rows (never partial)
+      for (int v = 0; v < (S >> 2); ++v)
+        *reinterpret_cast<float4 *>(p.y + (long long)(x0 + r) * p.ldy + feat0 + v * 4) =
+            make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  has_medium = __syncthreads_or(has_medium);
+  has_long = __syncthreads_or(has_long);
+
+  // phase B: medium rows, one warp per row, claimed dynamically
+  while (has_medium) {
+    int r = 0;
+    if (lane == 0) r = atomicAdd(&s_next, 1);
+    r = __shfl_sync(0xffffffffu, r, 0);
+    if (r >= rows_here) break;
+    const int eb = rp(r), ee = rp(r + 1);
+    if (ee - eb >= p.long_row || ee - eb < short_row || ee == eb || skip(r)) continue;
+    Vec<VW, B16> acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i].zero();
+    gather_accumulate<LPE, NV, VW, B16>(acc, xlane, p.ldx, p.x_rows, p.colidx, eb, ee, 0, 1, lane, q, active,
+                                        all_active);
+    group_reduce<LPE, NV, VW, B16>(acc);
+    if (q == 0) {
+      int accf;
+      float *yrow = out_row(r, accf) + g * VW;
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        if (active[i]) {
+          if (accf) {
+            Vec<VW, B16> o;
+            o.load_plain(yrow + i * LPE * VW);
+            acc[i].add(o);
+          }
+          acc[i].store(yrow + i * LPE * VW);
+        }
+    }
+  }
+
+  // phase C: long rows (or long pieces of a hub row), all warps share the row
+  if (!has_long) return;
+  const int nvec4 = S >> 2;
+  for (int r = 0; r < rows_here; ++r) {
+    const int eb = rp(r), ee = rp(r + 1);
+    if (ee - eb < p.long_row || skip(r)) continue;
+    Vec<VW, B16> acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i].zero();
+    gather_accumulate<LPE, NV, VW, B16>(acc, xlane, p.ldx, p.x_rows, p.colidx, eb, ee, wid, CTA_WARPS, lane, q,
+                                        active, all_active);
+    group_reduce<LPE, NV, VW, B16>(acc);
+    if (q == 0) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        if (active[i]) acc[i].store(smem + wid * S + (g + i * LPE) * VW);
+    }
+    __syncthreads();
+    int accf;
+    float *yrow = out_row(r, accf);
+    for (int v = tid; v < nvec4; v += CTA_THREADS) {
+      float4 s = *reinterpret_cast<const float4 *>(smem + v * 4);
+#pragma unroll
+      for (int ww = 1; ww < CTA_WARPS; ++ww)
+        add4(s, *reinterpret_cast<const float4 *>(smem + ww * S + v * 4));
+      float4 *dst = reinterpret_cast<float4 *>(yrow + v * 4);
+      if (accf) add4(s, *dst);
+      *dst = s;
+    }
+    __syncthreads();
+  }
+}
+
+// Y[r] (+)= sum of the pieces of every row that was cut by item boundaries, pieces in item order.
+__global__ void __launch_bounds__(64) spmm_balanced_fixup_kernel(const BalParams bp) {
+  const SpmmParams &p = bp.s;
+  for (int k = blockIdx.x; k < bp.n_items; k += gridDim.x) {
+    const int r = bp.split_row[2 * k];
+    if (r < 0) continue;
+    int k1 = k;
+    while (k1 > 0 && bp.split_row[2 * (k1 - 1) + 1] == r) --k1;
+    for (int f = threadIdx.x * 4; f < p.dim; f += 64 * 4) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int kk = k1; kk < k; ++kk)
+        add4(s, *reinterpret_cast<const float4 *>(bp.partial + (size_t)(2 * kk + 1) * p.dim + f));
+      add4(s, *reinterpret_cast<const float4 *>(bp.partial + (size_t)(2 * k) * p.dim + f));
+      float4 *dst = reinterpret_cast<float4 *>(p.y + (long long)r * p.ldy + f);
+      if (p.accumulate) add4(s, *dst);
+      *dst = s;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // Scalar kernel: any dim / alignment.  One warp per row, lane = feature (mod 32), FP32 sum in
 // CSR order -- bit-identical to the reference's CUDA-core arithmetic (:1003-1010).
 // ---------------------------------------------------------------------------------------
@@ -673,6 +1008,84 @@ static cudaError_t launch_hybrid(const SpmmParams &p, dim3 grid, size_t smem, cu
   return launch_hybrid_b<LPE, NV, VW, HCSPMM_MIN_CTAS>(p, grid, smem, stream);
 }
 
+template <int LPE, int NV, int VW, bool B16>
+static cudaError_t launch_balanced_t(const BalParams &bp, dim3 grid, size_t smem, cudaStream_t stream) {
+  auto kern = spmm_balanced_kernel<LPE, NV, VW, HCSPMM_MIN_CTAS, B16>;
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  BalParams q = bp;
+  q.s.short_row = bp.s.short_row * (32 / LPE);
+  kern<<<grid, CTA_THREADS, smem, stream>>>(q);
+  return cudaGetLastError();
+}
+
+// "balance" knob: 0 off, 2 always, 1 (default) when the mean row holds >= 8 entries -- below that the
+// windows-per-CTA / lane-group-per-row machinery of the hybrid kernel is faster (envelope shape: 0.113 vs 0.172 ms)
+static bool use_balanced(int n_rows, long long nnz) {
+  const int b = tuning().balance;
+  return b >= 2 || (b == 1 && nnz >= 8LL * n_rows);
+}
+
+// CUDA-core windows of p (all of them when p.ht == nullptr) on the work-balanced kernel.
+static cudaError_t run_balanced(const SpmmParams &p, long long nnz, bool v8, bool b16, cudaStream_t stream) {
+  BalParams bp;
+  bp.s = p;
+  bp.nnz = nnz;
+  // item size: about 4 MB of gathered rows, between 4096 and 8192 steps (measured: Reddit shape dim 256
+  // FP32 best at 4096, dim 64 / BF16 / products dim 128 at 8192)
+  const long long row_bytes = (long long)p.slab * (b16 ? 2 : 4);
+  int chunk = tuning().chunk > 0 ? tuning().chunk : (int)((4 << 20) / (row_bytes > 0 ? row_bytes : 4));
+  if (tuning().chunk <= 0) chunk = chunk < 4096 ? 4096 : (chunk > 8192 ? 8192 : chunk / 1024 * 1024);
+  if (chunk < 64) chunk = 64;
+  if (chunk > 16384) chunk = 16384;
+  const long long total = (long long)p.n_rows + nnz;
+  const long long n_items = total > 0 ? (total + chunk - 1) / chunk : 1;
+  if (n_items > 0x7fffffffLL / 2) return cudaErrorInvalidValue;
+  bp.chunk = chunk;
+  bp.n_items = (int)n_items;
+  keep_mempool_blocks();
+  void *ws = nullptr;
+  const size_t part_bytes = sizeof(float) * 2 * (size_t)n_items * p.dim;
+  cudaError_t err = cudaMallocAsync(&ws, part_bytes + sizeof(int) * (3 * (size_t)n_items + 1), stream);
+  if (err != cudaSuccess) return err;
+  bp.partial = reinterpret_cast<float *>(ws);
+  bp.split_row = reinterpret_cast<int *>(reinterpret_cast<char *>(ws) + part_bytes);
+  int *splits = bp.split_row + 2 * (size_t)n_items;
+  bp.splits = splits;
+  bp.warp_split = tuning().warp_split;   // mean row length from which an item is cut by warp runs
+  merge_path_splits_kernel<<<(unsigned)((n_items + 1 + 127) / 128), 128, 0, stream>>>(p.rowptr, p.n_rows, nnz, chunk,
+                                                                                    (int)n_items, splits);
+  const int slab = p.slab;
+  dim3 grid((unsigned)n_items, (p.dim + slab - 1) / slab, 1);
+  const size_t smem = (size_t)2 * CTA_WARPS * slab * sizeof(float) + (size_t)(chunk + 4) / 2 * sizeof(int);
+  if (b16) {
+    if (slab <= 32) err = launch_balanced_t<4, 1, 8, true>(bp, grid, smem, stream);
+    else if (slab <= 64) err = launch_balanced_t<8, 1, 8, true>(bp, grid, smem, stream);
+    else if (slab <= 128) err = launch_balanced_t<16, 1, 8, true>(bp, grid, smem, stream);
+    else if (slab <= 256) err = launch_balanced_t<32, 1, 8, true>(bp, grid, smem, stream);
+    else err = launch_balanced_t<32, 2, 8, true>(bp, grid, smem, stream);
+  } else if (v8) {
+    if (slab <= 32) err = launch_balanced_t<4, 1, 8, false>(bp, grid, smem, stream);
+    else if (slab <= 64) err = launch_balanced_t<8, 1, 8, false>(bp, grid, smem, stream);
+    else if (slab <= 128) err = launch_balanced_t<16, 1, 8, false>(bp, grid, smem, stream);
+    else if (slab <= 256) err = launch_balanced_t<32, 1, 8, false>(bp, grid, smem, stream);
+    else err = launch_balanced_t<32, 2, 8, false>(bp, grid, smem, stream);
+  } else {
+    if (slab <= 32) err = launch_balanced_t<8, 1, 4, false>(bp, grid, smem, stream);
+    else if (slab <= 64) err = launch_balanced_t<16, 1, 4, false>(bp, grid, smem, stream);
+    else if (slab <= 128) err = launch_balanced_t<32, 1, 4, false>(bp, grid, smem, stream);
+    else if (slab <= 256) err = launch_balanced_t<32, 2, 4, false>(bp, grid, smem, stream);
+    else err = launch_balanced_t<32, 4, 4, false>(bp, grid, smem, stream);
+  }
+  if (err == cudaSuccess && n_items > 1) {
+    const int fgrid = (int)(n_items < 148 * 32 ? n_items : 148 * 32);
+    spmm_balanced_fixup_kernel<<<fgrid, 64, 0, stream>>>(bp);
+    err = cudaGetLastError();
+  }
+  cudaFreeAsync(ws, stream);
+  return err;
+}
+
 int launch_spmm(const float *x, int64_t ldx, int32_t x_rows, const int32_t *rowptr,
                 const int32_t *colidx, const int32_t *bp, const int32_t *etc, const int32_t *etr,
                 const int32_t *ht, int32_t n_rows, int64_t nnz, int32_t dim, int precision,
@@ -715,6 +1128,7 @@ int launch_spmm(const float *x, int64_t ldx, int32_t x_rows, const int32_t *rowp
   p.short_row = tuning().short_row;   // multiplied by G inside the launcher below
   p.wpc = 1;
   p.n_windows = (n_rows + BLK_H - 1) / BLK_H;
+  p.cuda_elsewhere = 0;
 
   const int n_windows = (n_rows + BLK_H - 1) / BLK_H;
   const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0 &&
@@ -741,7 +1155,8 @@ int launch_spmm(const float *x, int64_t ldx, int32_t x_rows, const int32_t *rowp
     p.n_windows = n_windows;
     dim3 grid((n_windows + wpc - 1) / wpc, (dim + slab - 1) / slab, 1);
     const size_t smem = hybrid_smem_bytes(slab, false);
-    if (slab <= 32) err = launch_hybrid_bf16<4, 1>(p, grid, smem, stream);
+    if (use_balanced(n_rows, nnz)) err = run_balanced(p, nnz, true, true, stream);
+    else if (slab <= 32) err = launch_hybrid_bf16<4, 1>(p, grid, smem, stream);
     else if (slab <= 64) err = launch_hybrid_bf16<8, 1>(p, grid, smem, stream);
     else if (slab <= 128) err = launch_hybrid_bf16<16, 1>(p, grid, smem, stream);
     else if (slab <= 256) err = launch_hybrid_bf16<32, 1>(p, grid, smem, stream);
@@ -806,7 +1221,28 @@ int launch_spmm(const float *x, int64_t ldx, int32_t x_rows, const int32_t *rowp
     const bool v8 = tuning().vec8 != 0 &&
                     ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 31) == 0 &&
                     (ldx & 7) == 0 && (ldy & 7) == 0 && (dim & 7) == 0 && (slab & 7) == 0;
-    if (v8) {
+    if (use_balanced(n_rows, nnz)) {
+      // tensor-core windows (if any are labelled) on the per-window kernel, everything else balanced
+      err = cudaSuccess;
+      if (labels) {
+        SpmmParams pt = p;
+        pt.cuda_elsewhere = 1;
+        if (v8) {
+          if (slab <= 32) err = launch_hybrid<4, 1, 8>(pt, grid, smem, stream);
+          else if (slab <= 64) err = launch_hybrid<8, 1, 8>(pt, grid, smem, stream);
+          else if (slab <= 128) err = launch_hybrid<16, 1, 8>(pt, grid, smem, stream);
+          else if (slab <= 256) err = launch_hybrid<32, 1, 8>(pt, grid, smem, stream);
+          else err = launch_hybrid<32, 2, 8>(pt, grid, smem, stream);
+        } else {
+          if (slab <= 32) err = launch_hybrid<8, 1, 4>(pt, grid, smem, stream);
+          else if (slab <= 64) err = launch_hybrid<16, 1, 4>(pt, grid, smem, stream);
+          else if (slab <= 128) err = launch_hybrid<32, 1, 4>(pt, grid, smem, stream);
+          else if (slab <= 256) err = launch_hybrid<32, 2, 4>(pt, grid, smem, stream);
+          else err = launch_hybrid<32, 4, 4>(pt, grid, smem, stream);
+        }
+      }
+      if (err == cudaSuccess) err = run_balanced(p, nnz, v8, false, stream);
+    } else if (v8) {
       if (slab <= 32) err = launch_hybrid<4, 1, 8>(p, grid, smem, stream);
       else if (slab <= 64) err = launch_hybrid<8, 1, 8>(p, grid, smem, stream);
       else if (slab <= 128) err = launch_hybrid<16, 1, 8>(p, grid, smem, stream);

@@ -23,6 +23,8 @@ EXPORTS = [
     "hcspmm_gemm_tf32", "hcspmm_dense_plan_workspace_bytes", "hcspmm_dense_plan_count", "hcspmm_dense_plan_words",
     "hcspmm_dense_plan_fill", "hcspmm_spmm_plan", "hcspmm_debug_umma_error", "hcspmm_loa_workspace_bytes", "hcspmm_loa_reorder", "hcspmm_graph_create", "hcspmm_graph_spmm_host",
     "hcspmm_graph_get_preprocess", "hcspmm_graph_destroy",
+    "hcspmm_peer_alloc", "hcspmm_peer_open", "hcspmm_peer_close", "hcspmm_peer_free", "hcspmm_peer_barrier",
+    "hcspmm_halo_pull",
 ]
 
 _lib = None
@@ -68,6 +70,12 @@ def lib() -> ctypes.CDLL:
         L.hcspmm_graph_get_preprocess.argtypes = [_vp, _vp, _vp, _vp, _vp]
         L.hcspmm_graph_destroy.argtypes = [_vp]
         L.hcspmm_graph_destroy.restype = None
+        L.hcspmm_peer_alloc.argtypes = [_sz, ctypes.POINTER(_vp), _vp]
+        L.hcspmm_peer_open.argtypes = [_vp, ctypes.POINTER(_vp)]
+        L.hcspmm_peer_close.argtypes = [_vp]
+        L.hcspmm_peer_free.argtypes = [_vp]
+        L.hcspmm_peer_barrier.argtypes = [_vp, _i32, _i32, _i32, _vp, _vp]
+        L.hcspmm_halo_pull.argtypes = [_vp, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp]
         _lib = L
     return _lib
 

@@ -7,16 +7,32 @@ Rank r owns the 16-row windows [cuts[r], cuts[r+1]) of A (nnz-balanced, hcspmm.p
 matching rows of X / Y, and the preprocessing of its shard.  One aggregation Y_r = A_r * X is
     exchange:  all-gather of the row shards of X   (NCCL over NVLink / NVSwitch)
     compute:   local hybrid SpMM on the gathered X (rectangular: n_r x N)
-Two schedules:
+Schedules:
   * "gather":   one all_gather_into_tensor, then one SpMM launch;
   * "slabs":    X is exchanged in feature slabs; the SpMM of slab k (a strided view of the gathered
                 buffer, the kernel takes ldx/ldy) runs on the compute stream while slab k+1 is in
                 flight on the communication stream -- the exchange hides behind the gather-bound
                 kernel instead of preceding it.
-Shards are padded to the largest shard so the collective is a plain equal-size all-gather; shard
-s occupies rows [s*max_rows, s*max_rows + n_s) of the gathered buffer and the local column ids are
-remapped to that layout once.  The remap is monotone, so the window-local column ranks
-(edgeToColumn), block counts and labels are exactly those of the unpartitioned graph.
+  * "halo":     only the rows of X a shard actually references travel: at set-up every rank tells
+                every owner which of its rows it needs (the distinct remote column ids of the
+                shard); per aggregation the owners pack those rows and one all_to_all_single moves
+                them.  On power-law graphs most vertices have few neighbours, so a 1/8 row shard of
+                the products shape references 0.31 N remote rows where the all-gather moves 0.875 N.
+                `n_slabs` > 1 pipelines the halo exchange in feature slabs like "slabs".
+  * "peer":     the halo rows again, but PULLED: every rank keeps its shard of X in a CUDA-IPC buffer
+                the others have mapped, and one kernel of ours (hcspmm_halo_pull, csrc/peer.cu) copies
+                the referenced rows straight out of the owners' memory with NVLink loads, after a
+                flag barrier of ours (hcspmm_peer_barrier).  No collective, no packing pass on the
+                owner, nothing sent that is not needed.  `n_slabs` > 1 pulls feature slab k+1 on a
+                high-priority stream while the SpMM of slab k runs.
+  * "auto":     CUDA: "peer".  Otherwise "halo" when it moves <= 0.6 of the all-gather's rows
+                (decided once, collectively), else "gather".
+gather / slabs: shards are padded to the largest shard so the collective is a plain equal-size
+all-gather; shard s occupies rows [s*max_rows, s*max_rows + n_s) of the gathered buffer.  halo:
+the operand is [halo rows of rank 0 | ... | own rows | ... | halo rows of rank P-1], ascending
+global ids inside each part.  Either way the local column ids are remapped once and the remap is
+monotone, so the window-local column ranks (edgeToColumn), block counts and labels are exactly
+those of the unpartitioned graph.
 
 The aggregation operator is injectable (`spmm=`) so that the exchange / remap / autograd logic is
 testable on CPU with gloo; the default is the CUDA path (HCSPMM), which has no CPU fallback.
@@ -62,16 +78,61 @@ class ShardedGraph:
         rp_l, ci_l = partition.local_shard(rowptr, colidx, self.r0, self.r1)
         dev = colidx.device
         bounds = torch.tensor(self.cuts, device=dev, dtype=torch.int64)
-        owner = torch.bucketize(ci_l.to(torch.int64), bounds[1:-1], right=True)
-        self.colidx = (ci_l.to(torch.int64) - bounds[owner] + owner * self.max_rows).to(torch.int32).contiguous()
+        ci64 = ci_l.to(torch.int64)
         self.rowptr = rp_l
         self.nnz_local = ci_l.numel()
+        self.halo = None
+        self.peer = None
+        if self.world > 1 and schedule == "auto" and dev.type == "cuda" and spmm is None:
+            schedule = "peer"
+        if self.world > 1 and schedule in ("halo", "auto", "peer"):
+            self._setup_halo(ci64, bounds, dev, lists_only=schedule == "peer")
+            if schedule == "auto" and self.halo["ratio"] > 0.6:
+                self.halo = None
+            self.schedule = schedule if schedule == "peer" else (
+                "halo" if self.halo is not None else ("slabs" if self.n_slabs > 1 else "gather"))
+        if self.schedule == "peer":
+            from . import peer
+            self.peer = peer.PeerMemory(dev, group)
+            self._pull = peer.halo_pull
+            self._hi_stream = torch.cuda.Stream(device=dev, priority=-1)
+        if self.halo is not None:
+            self.colidx = torch.searchsorted(self.halo["ids"], ci64).to(torch.int32).contiguous()
+        else:
+            owner = torch.bucketize(ci64, bounds[1:-1], right=True)
+            self.colidx = (ci64 - bounds[owner] + owner * self.max_rows).to(torch.int32).contiguous()
+        del ci64
         if spmm is None:
             spmm, preprocess = _default_spmm()
         self._spmm = spmm
         self.pre = preprocess(self.colidx, self.rowptr) if preprocess is not None else ()
         self._bufs = {}
         self._comm_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+
+    def _setup_halo(self, ci64, bounds, dev, lists_only=False):
+        """Which rows of X this shard needs from every owner, and which of its own rows every peer needs."""
+        uniq = torch.unique(ci64)                                             # ascending global ids
+        own = torch.bucketize(uniq, bounds[1:-1], right=True)
+        mine = torch.arange(self.r0, self.r1, device=dev, dtype=torch.int64)  # own rows: all of them
+        ids = torch.cat([uniq[own < self.rank], mine, uniq[own > self.rank]])
+        own = torch.bucketize(ids, bounds[1:-1], right=True)
+        recv_counts = torch.bincount(own, minlength=self.world)               # rows arriving from each owner
+        want = (ids - bounds[own]).contiguous()                               # row index at its owner
+        moved = torch.tensor([ids.numel() - self.n_local], device=dev, dtype=torch.int64)
+        dist.all_reduce(moved, op=dist.ReduceOp.MAX, group=self.group)
+        ratio = float(moved) / max(1, (self.world - 1) * self.max_rows)
+        if lists_only:      # pull model: the owners need no send lists
+            seg = torch.zeros(self.world + 1, dtype=torch.int32, device=dev)
+            seg[1:] = torch.cumsum(recv_counts, 0).to(torch.int32)
+            self.halo = dict(ids=ids, rows=int(ids.numel()), recv=recv_counts.tolist(), ratio=ratio,
+                             src_row=want.to(torch.int32), seg=seg)
+            return
+        send_counts = torch.empty_like(recv_counts)
+        dist.all_to_all_single(send_counts, recv_counts, group=self.group)    # rows every peer wants from me
+        rc, sc = recv_counts.tolist(), send_counts.tolist()
+        send_idx = torch.empty(sum(sc), dtype=torch.int64, device=dev)
+        dist.all_to_all_single(send_idx, want, output_split_sizes=sc, input_split_sizes=rc, group=self.group)
+        self.halo = dict(ids=ids, rows=int(ids.numel()), recv=rc, send=sc, send_idx=send_idx, ratio=ratio)
 
     # ------------------------------------------------------------------------------------------
     def shard_rows(self, x_full: torch.Tensor) -> torch.Tensor:
@@ -90,12 +151,145 @@ class ShardedGraph:
         dim = x_local.shape[1]
         if self.world == 1:
             return self._spmm(x_local.contiguous(), self.rowptr, self.colidx, self.pre)
+        if self.peer is not None:
+            return self._aggregate_peer(x_local)
+        if self.halo is not None:
+            return self._aggregate_halo(x_local)
         if self.schedule == "slabs" and self.n_slabs > 1 and dim >= 8 * self.n_slabs and self._comm_stream is not None:
             return self._aggregate_slabs(x_local)
-        pad, gathered = self._buffers(dim, x_local.device, x_local.dtype)
+        return self._spmm(self.exchange(x_local), self.rowptr, self.colidx, self.pre)
+
+    @property
+    def x_rows(self) -> int:
+        """Rows of the exchanged operand the local SpMM reads (column ids address this layout)."""
+        if self.world == 1:
+            return self.n
+        return self.halo["rows"] if self.halo is not None else self.world * self.max_rows
+
+    def exchange(self, x_local: torch.Tensor) -> torch.Tensor:
+        """The exchange step on its own (one piece, not pipelined): the operand of the local SpMM."""
+        dim, dev, dt = x_local.shape[1], x_local.device, x_local.dtype
+        if self.world == 1:
+            return x_local
+        if self.peer is not None:
+            cat, dpad = self._peer_stage(x_local)
+            self._pull_halo(cat, dpad)
+            return cat if dpad == dim else cat[:, :dim]
+        if self.halo is not None:
+            h = self.halo
+            key = ("halo", dim, dev, dt)
+            if key not in self._bufs:
+                self._bufs[key] = torch.empty(h["rows"], dim, device=dev, dtype=dt)
+            cat = self._bufs[key]
+            packed = x_local.index_select(0, h["send_idx"])
+            dist.all_to_all_single(cat, packed, output_split_sizes=h["recv"], input_split_sizes=h["send"],
+                                   group=self.group)
+            return cat
+        pad, gathered = self._buffers(dim, dev, dt)
         pad[: self.n_local].copy_(x_local)
         dist.all_gather_into_tensor(gathered, pad, group=self.group)
-        return self._spmm(gathered, self.rowptr, self.colidx, self.pre)
+        return gathered
+
+    def exchange_rows(self) -> int:
+        """Rows of X this rank receives from its peers per aggregation."""
+        if self.world == 1:
+            return 0
+        return self.halo["rows"] - self.n_local if self.halo is not None else (self.world - 1) * self.max_rows
+
+    def close(self):
+        if self.peer is not None:
+            self._bufs.clear()
+            self.peer.close()
+            self.peer = None
+
+    def _peer_stage(self, x_local: torch.Tensor):
+        """Write the shard into the own-rows segment of this width's next operand buffer (peer-visible) and pass
+        the barrier: afterwards every rank's shard of this aggregation can be pulled.  -> (operand, padded width)."""
+        dim, dev = x_local.shape[1], x_local.device
+        dpad = (dim + 3) // 4 * 4
+        key = ("peer", dpad)
+        h = self.halo
+        if key not in self._bufs:
+            pm, slots = self.peer, []
+            own0 = int(h["seg"][self.rank])
+            firsts = [None] * self.world                         # every rank's own-segment offset in ITS operand
+            dist.all_gather_object(firsts, own0, group=self.group)
+            for _ in range(2):                                   # alternate: see csrc/peer.cu header
+                ptr, ptrs = pm.shared(h["rows"] * dpad * 4)
+                table = torch.tensor([p + f * dpad * 4 for p, f in zip(ptrs, firsts)], dtype=torch.int64, device=dev)
+                slots.append((pm.tensor(ptr, (h["rows"], dpad)), table))
+            self._bufs[key] = dict(slots=slots, turn=0, own0=own0)
+        b = self._bufs[key]
+        cat, self._peer_tab = b["slots"][b["turn"]]
+        b["turn"] ^= 1
+        cat[b["own0"]: b["own0"] + self.n_local, :dim].copy_(x_local)     # pad columns stay zero
+        self.peer.barrier()
+        return cat, dpad
+
+    def _pull_halo(self, cat, dpad, col0=0, width=None):
+        h, own0 = self.halo, int(self._bufs[("peer", dpad)]["own0"])
+        for lo, hi in ((0, own0), (own0 + self.n_local, h["rows"])):      # around the own rows (in place)
+            if hi > lo:
+                self._pull(self._peer_tab, dpad, h["src_row"], h["seg"], self.world, cat, col0, width, lo, hi)
+
+    def _aggregate_peer(self, x_local: torch.Tensor) -> torch.Tensor:
+        dim, dev = x_local.shape[1], x_local.device
+        cat, dpad = self._peer_stage(x_local.float())
+        n_slabs = self.n_slabs if dpad >= 32 * self.n_slabs else 1
+        if n_slabs == 1:
+            self._pull_halo(cat, dpad)
+            y = self._spmm(cat, self.rowptr, self.colidx, self.pre)
+            return y if dpad == dim else y[:, :dim]
+        step = (dpad // n_slabs + 31) // 32 * 32
+        edges = list(range(0, dpad, step)) + [dpad]
+        y = torch.empty(self.n_local, dpad, device=dev)
+        cur, comm = torch.cuda.current_stream(dev), self._hi_stream
+        comm.wait_stream(cur)
+        events = []
+        with torch.cuda.stream(comm):
+            for k in range(len(edges) - 1):
+                self._pull_halo(cat, dpad, edges[k], edges[k + 1] - edges[k])
+                ev = torch.cuda.Event()
+                ev.record(comm)
+                events.append(ev)
+        for k, ev in enumerate(events):
+            cur.wait_event(ev)
+            self._spmm(cat[:, edges[k]:edges[k + 1]], self.rowptr, self.colidx, self.pre, out=y[:, edges[k]:edges[k + 1]])
+        comm.wait_stream(cur)
+        return y if dpad == dim else y[:, :dim]
+
+    def _aggregate_halo(self, x_local: torch.Tensor) -> torch.Tensor:
+        h = self.halo
+        dim, dev, dt = x_local.shape[1], x_local.device, x_local.dtype
+        pipelined = self.n_slabs > 1 and dim >= 8 * self.n_slabs and self._comm_stream is not None
+        if not pipelined:
+            return self._spmm(self.exchange(x_local), self.rowptr, self.colidx, self.pre)
+        step = (dim // self.n_slabs + 7) // 8 * 8
+        edges = list(range(0, dim, step)) + [dim]
+        y = torch.empty(self.n_local, dim, device=dev, dtype=dt)
+        cur, comm = torch.cuda.current_stream(dev), self._comm_stream
+        comm.wait_stream(cur)
+        events, cats = [], []
+        for k in range(len(edges) - 1):
+            w = edges[k + 1] - edges[k]
+            key = ("halo_slab", k, w, dev, dt)
+            if key not in self._bufs:
+                self._bufs[key] = torch.empty(h["rows"], w, device=dev, dtype=dt)
+            cat = self._bufs[key]
+            with torch.cuda.stream(comm):
+                packed = x_local[:, edges[k]:edges[k + 1]].index_select(0, h["send_idx"])
+                dist.all_to_all_single(cat, packed, output_split_sizes=h["recv"], input_split_sizes=h["send"],
+                                       group=self.group)
+                packed.record_stream(comm)
+                ev = torch.cuda.Event()
+                ev.record(comm)
+            events.append(ev)
+            cats.append(cat)
+        for k, (ev, cat) in enumerate(zip(events, cats)):
+            cur.wait_event(ev)
+            self._spmm(cat, self.rowptr, self.colidx, self.pre, out=y[:, edges[k]:edges[k + 1]])
+        comm.wait_stream(cur)
+        return y
 
     def _aggregate_slabs(self, x_local: torch.Tensor) -> torch.Tensor:
         dim = x_local.shape[1]

@@ -1,0 +1,99 @@
+"""NVLink peer memory for the row-partitioned SpMM: IPC-shared buffers, a flag barrier and the
+halo-pull kernel of libhcspmm (csrc/peer.cu, include/hcspmm.h "multi-GPU").
+
+One process per GPU.  `torch.distributed` is used once per buffer to hand the 64-byte CUDA IPC
+handles round (all_gather_object); after that the data path is our own kernels reading the peers'
+memory -- no collective per aggregation.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import capi
+
+
+class _Raw:
+    """A device pointer as a __cuda_array_interface__ object (wrapped, not owned, by torch.as_tensor)."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class PeerMemory:
+    """Buffers every rank of `group` can read, plus a stream-ordered barrier between the ranks."""
+
+    def __init__(self, device: torch.device, group=None):
+        self.device, self.group = device, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._owned, self._opened = [], []
+        self.epoch = 0
+        self.err = torch.zeros(1, dtype=torch.int32, device=device)
+        _, self._flag_ptrs = self.shared(max(64, self.world) * 4)
+        self.flag_table = torch.tensor(self._flag_ptrs, dtype=torch.int64, device=device)
+
+    def shared(self, nbytes: int):
+        """Allocate nbytes here and map every peer's buffer of the same call -> (local ptr, [ptr of rank s])."""
+        L = capi.lib()
+        with torch.cuda.device(self.device):
+            ptr, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+            capi._check(L.hcspmm_peer_alloc(int(nbytes), ctypes.byref(ptr), handle), "hcspmm_peer_alloc")
+            self._owned.append(ptr.value)
+            ptrs = [ptr.value]
+            if self.world > 1:
+                handles = [None] * self.world
+                dist.all_gather_object(handles, handle.raw, group=self.group)
+                ptrs = []
+                for s, h in enumerate(handles):
+                    if s == self.rank:
+                        ptrs.append(ptr.value)
+                        continue
+                    p = ctypes.c_void_p()
+                    capi._check(L.hcspmm_peer_open(ctypes.create_string_buffer(h, 64), ctypes.byref(p)), "hcspmm_peer_open")
+                    self._opened.append(p.value)
+                    ptrs.append(p.value)
+        return ptr.value, ptrs
+
+    def tensor(self, ptr: int, shape, dtype=torch.float32) -> torch.Tensor:
+        typestr = {torch.float32: "<f4", torch.int32: "<i4"}[dtype]
+        return torch.as_tensor(_Raw(ptr, shape, typestr), device=self.device)
+
+    def barrier(self):
+        """Every rank's work enqueued before its barrier is visible to every rank's work after it."""
+        self.epoch += 1
+        with torch.cuda.device(self.device):
+            capi._check(capi.lib().hcspmm_peer_barrier(self.flag_table.data_ptr(), self.rank, self.world, self.epoch,
+                                                       self.err.data_ptr(),
+                                                       torch.cuda.current_stream(self.device).cuda_stream),
+                        "hcspmm_peer_barrier")
+
+    def check(self):
+        if int(self.err.item()) != 0:
+            raise capi.HcspmmError("peer barrier timed out: a rank did not reach the exchange")
+
+    def close(self):
+        L = capi.lib()
+        torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            dist.barrier(group=self.group)       # nobody still reads what is about to be freed
+        for p in self._opened:
+            L.hcspmm_peer_close(p)
+        for p in self._owned:
+            L.hcspmm_peer_free(p)
+        self._opened, self._owned = [], []
+
+
+def halo_pull(peer_table: torch.Tensor, lds: int, src_row: torch.Tensor, seg: torch.Tensor, world: int,
+              dst: torch.Tensor, col0: int = 0, width: int | None = None, row_begin: int = 0, row_end: int | None = None):
+    """hcspmm_halo_pull on the current stream: dst[i, col0:col0+width] <- owner's row src_row[i], i in [row_begin, row_end)."""
+    width = dst.shape[1] - col0 if width is None else width
+    row_end = dst.shape[0] if row_end is None else row_end
+    with torch.cuda.device(dst.device):
+        capi._check(capi.lib().hcspmm_halo_pull(peer_table.data_ptr(), lds, src_row.data_ptr(), seg.data_ptr(), world,
+                                                row_begin, row_end, col0, width, dst.data_ptr(), dst.stride(0),
+                                                torch.cuda.current_stream(dst.device).cuda_stream), "hcspmm_halo_pull")
+    return dst

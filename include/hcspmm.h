@@ -78,6 +78,12 @@ const char *hcspmm_last_error(void);
  *                are unaligned) run through zero-padded aligned copies; 0: scalar kernel
  *   "umma"       1: tcgen05 / TMEM dense super-window kernel (hcspmm_spmm_plan); 0: per-window paths
  *   "umma_gemm"  1: tcgen05 / TMEM Update GEMM; 0 (default): mma.sync GEMM
+ *   "balance"    CUDA-core windows on the merge-path balanced kernel (equal rows + stored entries per
+ *                CTA, hub rows cut into pieces that are summed in a fixed order): 1 (default) when the
+ *                mean row holds >= 8 entries, 2 always, 0 never (one CTA per "wpc" 16-row windows)
+ *   "chunk"      rows + stored entries per item of the balanced kernel (0 = about 4 MB of gathered rows)
+ *   "warp_split" items of the balanced kernel whose mean row length is >= this (default 64) give every warp
+ *                an equal run of entries; 0 = warp-per-row / CTA-per-long-row phases everywhere
  * Returns the previous value, or -1 for an unknown key.                          */
 int hcspmm_set_tuning(const char *key, int value);
 
@@ -177,6 +183,31 @@ int hcspmm_loa_reorder(const int32_t *d_rowptr, const int32_t *d_colidx, const i
                        const int32_t *d_colidx_in, int32_t n, int64_t nnz, int32_t max_degree,
                        int32_t *d_perm, int32_t *d_block_start, int32_t *d_counts, void *d_workspace,
                        size_t workspace_bytes, void *stream);
+
+/* ---- multi-GPU: the per-layer exchange of X over NVLink peer memory ------------------------------
+ * The reference is single-GPU.  Here A is partitioned by row windows, one process per GPU, and a rank
+ * needs the rows of X its shard references.  Instead of a collective every rank pulls exactly those rows
+ * out of the owners' memory with NVLink loads:
+ *   hcspmm_peer_alloc    cudaMalloc (zero-filled) + CUDA IPC handle (64 bytes) for a buffer peers will read
+ *   hcspmm_peer_open     map a peer's buffer from its handle (another process on the same node)
+ *   hcspmm_peer_close / hcspmm_peer_free
+ *   hcspmm_peer_barrier  stream-ordered barrier across the ranks: d_flag_ptrs[s] is rank s's int32[world]
+ *                        flag array (peer-mapped); epoch must increase by one per call on every rank.
+ *                        A peer that does not arrive within ~2 s sets *d_err = 1 instead of hanging.
+ *   hcspmm_halo_pull     d_dst[i, col0 .. col0+width) = d_peer_x[s][d_src_row[i], col0 .. col0+width) for the
+ *                        operand rows i in [row_begin, row_end), where s is the owner whose segment
+ *                        [d_seg[s], d_seg[s+1]) holds i (the caller skips its own segment: those rows
+ *                        are written in place).  d_dst is row 0 of the operand.  width, col0, lds, ldd
+ *                        multiples of 4 floats.                                                         */
+int hcspmm_peer_alloc(size_t bytes, void **d_ptr, void *handle64);
+int hcspmm_peer_open(const void *handle64, void **d_ptr);
+int hcspmm_peer_close(void *d_ptr);
+int hcspmm_peer_free(void *d_ptr);
+int hcspmm_peer_barrier(int32_t *const *d_flag_ptrs, int32_t rank, int32_t world, int32_t epoch, int32_t *d_err,
+                        void *stream);
+int hcspmm_halo_pull(const float *const *d_peer_x, int64_t lds, const int32_t *d_src_row, const int32_t *d_seg,
+                     int32_t world, int32_t row_begin, int32_t row_end, int32_t col0, int32_t width, float *d_dst,
+                     int64_t ldd, void *stream);
 
 /* ---- host-buffer convenience (what a non-torch caller binds) ----------------------
  * A graph handle owns device copies of the CSR and of the preprocessing products.

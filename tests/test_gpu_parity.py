@@ -137,6 +137,52 @@ def test_spmm_windows_per_cta_and_group_rows(capi, wpc, short_row):
             assert rel_fro(acc.cpu().numpy(), want + 1.0) <= 2e-5, (name, dim)
 
 
+@pytest.mark.parametrize("chunk", [64, 100, 777, 4096])
+@pytest.mark.parametrize("warp_split", [-1, 0, 1, 64])
+def test_spmm_balanced_items(capi, chunk, warp_split):
+    """Merge-path balanced CUDA-core kernel: rows cut by item boundaries (hubs), empty rows / windows,
+    mixed labels (tensor-core windows skipped there and computed by the per-window kernel), accumulate,
+    BF16-stored X.  warp_split -1 = the per-window kernel (balance off), which must agree; 0 = warp-per-row /
+    CTA-per-long-row phases inside every item; 1 / 64 = equal entry runs per warp in items of long enough rows."""
+    for name in ("rmat_hub_4096", "holes_777", "rmat_1000", "empty_48", "single_row", "rect_72x100000", "dense_2048"):
+        rp, ci = GRAPHS[name]
+        n = rp.size - 1
+        bp, etc, etr, _ = oracle.preprocess(ci, rp, 0)
+        ht = np.zeros(oracle.num_windows(n), np.int32)
+        ht[1::4] = 1
+        for dim in (32, 100, 256, 520):
+            x = xmat(x_rows_for(rp, ci), dim, seed=dim + chunk)
+            y0 = xmat(n, dim, seed=7)
+            want32 = oracle.spmm(rp, ci, x, precision=1)
+            want_h = oracle.spmm(rp, ci, x, hybrid_type=ht, precision=0 if dim % 8 == 0 else 1)
+            o1, o2 = capi.set_tuning("balance", 0 if warp_split < 0 else 2), capi.set_tuning("chunk", chunk)
+            o3 = capi.set_tuning("warp_split", max(warp_split, 0))
+            try:
+                got32 = capi.spmm(dev(x), dev(rp), dev(ci), precision="fp32").cpu().numpy()
+                got_h = capi.spmm(dev(x), dev(rp), dev(ci), dev(bp), dev(etc), dev(etr), dev(ht)).cpu().numpy()
+                acc = dev(y0)
+                capi.spmm(dev(x), dev(rp), dev(ci), precision="fp32", out=acc, accumulate=True)
+                got16 = capi.spmm(dev(x), dev(rp), dev(ci), precision="bf16").cpu().numpy()
+            finally:
+                capi.set_tuning("balance", o1), capi.set_tuning("chunk", o2), capi.set_tuning("warp_split", o3)
+            assert rel_fro(got32, want32) <= TOL_FP32, (name, dim)
+            assert rel_fro(got_h, want_h) <= 2e-5, (name, dim)
+            assert rel_fro(acc.cpu().numpy(), want32 + y0) <= 2e-5, (name, dim)
+            assert rel_fro(got16, want32) <= 1e-2, (name, dim)
+
+
+def test_spmm_balanced_is_deterministic(capi):
+    rp, ci = GRAPHS["rmat_hub_4096"]
+    x = dev(xmat(4096, 128, seed=2))
+    old, ob = capi.set_tuning("chunk", 256), capi.set_tuning("balance", 2)
+    try:
+        a = capi.spmm(x, dev(rp), dev(ci), precision="fp32")
+        for _ in range(3):
+            assert torch.equal(a, capi.spmm(x, dev(rp), dev(ci), precision="fp32"))
+    finally:
+        capi.set_tuning("chunk", old), capi.set_tuning("balance", ob)
+
+
 def test_spmm_strided_and_unaligned(capi):
     rp, ci = GRAPHS["rmat_1000"]
     big = dev(xmat(1000, 80, seed=9))

@@ -68,7 +68,7 @@ def _oracle_ops():
     return run, prep
 
 
-def _worker(rank, world, port, name, out_dir):
+def _worker(rank, world, port, name, out_dir, schedule="gather"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -76,7 +76,9 @@ def _worker(rank, world, port, name, out_dir):
         rp, ci = GRAPHS[name]
         n = rp.size - 1
         run, prep = _oracle_ops()
-        g = hd.ShardedGraph(_t(rp), _t(ci), spmm=run, preprocess=prep)
+        g = hd.ShardedGraph(_t(rp), _t(ci), spmm=run, preprocess=prep, schedule=schedule)
+        if schedule == "halo":
+            assert g.halo is not None and g.halo["rows"] <= n and sum(g.halo["recv"]) == g.halo["rows"]
         x = torch.from_numpy(np.random.default_rng(1).standard_normal((n, 12)).astype(np.float32))
         y = g.aggregate(g.shard_rows(x))
         full = oracle.spmm(rp, ci, x.numpy(), precision=1)
@@ -93,7 +95,7 @@ def _worker(rank, world, port, name, out_dir):
         at.sort_indices()
         symmetric = (at.indptr == rp).all() and (at.indices == ci).all()
         gt = None if symmetric else hd.ShardedGraph(_t(at.indptr.astype(np.int32)), _t(at.indices.astype(np.int32)),
-                                                    spmm=run, preprocess=prep, cuts=g.cuts)
+                                                    spmm=run, preprocess=prep, cuts=g.cuts, schedule=schedule)
         assert symmetric == (name != "holes_777")
         model = hd.DistGCN(g, 12, 8, 4, num_layers=2, seed=3, graph_t=gt)
         labels = torch.from_numpy(np.random.default_rng(2).integers(0, 4, n))
@@ -119,8 +121,15 @@ def _worker(rank, world, port, name, out_dir):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("schedule", ["gather", "halo", "auto"])
 @pytest.mark.parametrize("name", ["rmat_1000", "holes_777"])
-def test_sharded_aggregate_and_gcn_step_gloo_world2(tmp_path, name):
-    port = 29500 + (os.getpid() % 500) + (7 if name == "holes_777" else 0)
-    mp.spawn(_worker, args=(2, port, name, str(tmp_path)), nprocs=2, join=True)
+def test_sharded_aggregate_and_gcn_step_gloo_world2(tmp_path, name, schedule):
+    port = 29500 + (os.getpid() % 500) + (7 if name == "holes_777" else 0) + {"gather": 0, "halo": 13, "auto": 29}[schedule]
+    mp.spawn(_worker, args=(2, port, name, str(tmp_path), schedule), nprocs=2, join=True)
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+def test_halo_exchange_world3(tmp_path):
+    """Three ranks: halo rows arrive from owners on both sides of the own block."""
+    mp.spawn(_worker, args=(3, 29500 + (os.getpid() % 500) + 41, "rmat_1000", str(tmp_path), "halo"), nprocs=3, join=True)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(3))
