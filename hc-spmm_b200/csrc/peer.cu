@@ -44,36 +44,47 @@ __global__ void peer_barrier_kernel(int *const *flag_ptrs, int rank, int world, 
 
 constexpr int PULL_ROWS = 8;   // rows in flight per warp
 
-// dst[i, 0..width) = peer_x[owner(i)][src_row[i], c0 .. c0+width) for i in [row0, rows)   (width % 4 == 0)
+// dst[i, c0 .. c0+width) = peer_x[s][src_row[i], c0 .. c0+width) for the operand rows i of every owner
+// s != skip (segment [seg[s], seg[s+1])).  Batches of PULL_ROWS rows are dealt round-robin over the
+// owners, starting after `skip`: the warps of a CTA read from different peers at the same time and the
+// ranks start on different owners, so no owner's NVLink egress is the one everybody waits for.
 __global__ void __launch_bounds__(256) halo_pull_kernel(const float *const *__restrict__ peer_x, long long lds,
                                                         const int *__restrict__ src_row, const int *__restrict__ seg,
-                                                        int world, int row0, int rows, int c0, int width,
+                                                        int world, int skip, int c0, int width,
                                                         float *__restrict__ dst, long long ldd) {
   __shared__ int s_seg[65];
   __shared__ const float *s_base[64];
+  __shared__ int s_nb;
   for (int i = threadIdx.x; i <= world; i += blockDim.x) s_seg[i] = seg[i];
   for (int i = threadIdx.x; i < world; i += blockDim.x) s_base[i] = peer_x[i];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int nb = 0;
+    for (int o = 0; o < world; ++o)
+      if (o != skip) nb = max(nb, (s_seg[o + 1] - s_seg[o] + PULL_ROWS - 1) / PULL_ROWS);
+    s_nb = nb;
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int n_warps = (gridDim.x * blockDim.x) >> 5;
   const int nvec = width >> 2;
-  for (int r0 = row0 + warp * PULL_ROWS; r0 < rows; r0 += n_warps * PULL_ROWS) {
+  const long long total = (long long)s_nb * world;
+  for (long long t = warp; t < total; t += n_warps) {
+    const int o = (int)((t + skip + 1) % world);
+    const int r0 = s_seg[o] + (int)(t / world) * PULL_ROWS, r1 = s_seg[o + 1];
+    if (o == skip || r0 >= r1) continue;
+    const float *base = s_base[o] + c0;
     const float *src[PULL_ROWS];
 #pragma unroll
-    for (int j = 0; j < PULL_ROWS; ++j) {
-      const int i = min(r0 + j, rows - 1);
-      int s = 0;
-      while (s + 1 < world && i >= s_seg[s + 1]) ++s;
-      src[j] = s_base[s] + (long long)__ldg(src_row + i) * lds + c0;
-    }
+    for (int j = 0; j < PULL_ROWS; ++j) src[j] = base + (long long)__ldg(src_row + min(r0 + j, r1 - 1)) * lds;
     for (int v = lane; v < nvec; v += 32) {
-      float4 t[PULL_ROWS];
+      float4 x[PULL_ROWS];
 #pragma unroll
-      for (int j = 0; j < PULL_ROWS; ++j) t[j] = *reinterpret_cast<const float4 *>(src[j] + v * 4);
+      for (int j = 0; j < PULL_ROWS; ++j) x[j] = *reinterpret_cast<const float4 *>(src[j] + v * 4);
 #pragma unroll
       for (int j = 0; j < PULL_ROWS; ++j)
-        if (r0 + j < rows) *reinterpret_cast<float4 *>(dst + (long long)(r0 + j) * ldd + c0 + v * 4) = t[j];
+        if (r0 + j < r1) *reinterpret_cast<float4 *>(dst + (long long)(r0 + j) * ldd + c0 + v * 4) = x[j];
     }
   }
 }
@@ -137,11 +148,11 @@ int hcspmm_peer_barrier(int32_t *const *d_flag_ptrs, int32_t rank, int32_t world
 }
 
 int hcspmm_halo_pull(const float *const *d_peer_x, int64_t lds, const int32_t *d_src_row, const int32_t *d_seg,
-                     int32_t world, int32_t row_begin, int32_t row_end, int32_t col0, int32_t width, float *d_dst,
+                     int32_t world, int32_t skip_owner, int32_t rows, int32_t col0, int32_t width, float *d_dst,
                      int64_t ldd, void *stream) {
-  if (row_end <= row_begin || width == 0) return 0;
-  const int rows = row_end;
-  if (!d_peer_x || !d_src_row || !d_seg || !d_dst || world < 1 || world > 64 || row_begin < 0 || width < 0 || col0 < 0) {
+  if (rows <= 0 || width == 0) return 0;
+  if (!d_peer_x || !d_src_row || !d_seg || !d_dst || world < 1 || world > 64 || width < 0 || col0 < 0 ||
+      skip_owner >= world) {
     set_error("halo_pull: bad argument");
     return HCSPMM_E_INVALID;
   }
@@ -149,10 +160,11 @@ int hcspmm_halo_pull(const float *const *d_peer_x, int64_t lds, const int32_t *d
     set_error("halo_pull: width, col0 and leading dims must be multiples of 4 floats, dst 16-byte aligned");
     return HCSPMM_E_ALIGN;
   }
-  const long long warps = ((long long)(row_end - row_begin) + PULL_ROWS - 1) / PULL_ROWS;
+  if (skip_owner < 0) skip_owner = -1;
+  const long long warps = ((long long)rows + PULL_ROWS - 1) / PULL_ROWS + world;
   long long grid = (warps + 7) / 8;
   if (grid > 148 * 8) grid = 148 * 8;
-  halo_pull_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(d_peer_x, lds, d_src_row, d_seg, world, row_begin, rows,
+  halo_pull_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(d_peer_x, lds, d_src_row, d_seg, world, skip_owner,
                                                                      col0, width, d_dst, ldd);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("halo_pull: %s", cudaGetErrorString(e)); return (int)e; }

@@ -83,17 +83,23 @@ class ShardedGraph:
         self.nnz_local = ci_l.numel()
         self.halo = None
         self.peer = None
-        if self.world > 1 and schedule == "auto" and dev.type == "cuda" and spmm is None:
-            schedule = "peer"
+        if self.world > 1 and schedule in ("auto", "peer") and dev.type == "cuda":
+            # NVLink peer memory (CUDA IPC between the ranks' processes); "auto" falls back to the NCCL
+            # schedules, on every rank together, where the platform refuses it
+            from . import peer
+            try:
+                self.peer = peer.PeerMemory(dev, group)
+                schedule = "peer"
+            except peer.capi.HcspmmError:
+                if schedule == "peer":
+                    raise
         if self.world > 1 and schedule in ("halo", "auto", "peer"):
             self._setup_halo(ci64, bounds, dev, lists_only=schedule == "peer")
             if schedule == "auto" and self.halo["ratio"] > 0.6:
                 self.halo = None
             self.schedule = schedule if schedule == "peer" else (
                 "halo" if self.halo is not None else ("slabs" if self.n_slabs > 1 else "gather"))
-        if self.schedule == "peer":
-            from . import peer
-            self.peer = peer.PeerMemory(dev, group)
+        if self.peer is not None:
             self._pull = peer.halo_pull
             self._hi_stream = torch.cuda.Stream(device=dev, priority=-1)
         if self.halo is not None:
@@ -227,10 +233,8 @@ class ShardedGraph:
         return cat, dpad
 
     def _pull_halo(self, cat, dpad, col0=0, width=None):
-        h, own0 = self.halo, int(self._bufs[("peer", dpad)]["own0"])
-        for lo, hi in ((0, own0), (own0 + self.n_local, h["rows"])):      # around the own rows (in place)
-            if hi > lo:
-                self._pull(self._peer_tab, dpad, h["src_row"], h["seg"], self.world, cat, col0, width, lo, hi)
+        h = self.halo                                            # own rows are already in place: skip that segment
+        self._pull(self._peer_tab, dpad, h["src_row"], h["seg"], self.world, cat, col0, width, self.rank)
 
     def _aggregate_peer(self, x_local: torch.Tensor) -> torch.Tensor:
         dim, dev = x_local.shape[1], x_local.device

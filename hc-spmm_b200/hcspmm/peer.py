@@ -37,25 +37,38 @@ class PeerMemory:
         self.flag_table = torch.tensor(self._flag_ptrs, dtype=torch.int64, device=device)
 
     def shared(self, nbytes: int):
-        """Allocate nbytes here and map every peer's buffer of the same call -> (local ptr, [ptr of rank s])."""
+        """Allocate nbytes here and map every peer's buffer of the same call -> (local ptr, [ptr of rank s]).
+        Collective.  A failure on any rank (no IPC, no peer access) raises HcspmmError on EVERY rank, so the
+        caller can fall back collectively."""
         L = capi.lib()
         with torch.cuda.device(self.device):
             ptr, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
-            capi._check(L.hcspmm_peer_alloc(int(nbytes), ctypes.byref(ptr), handle), "hcspmm_peer_alloc")
-            self._owned.append(ptr.value)
+            rc = L.hcspmm_peer_alloc(int(nbytes), ctypes.byref(ptr), handle)
+            why = None if rc == 0 else f"hcspmm_peer_alloc: {L.hcspmm_last_error().decode()}"
+            if rc == 0:
+                self._owned.append(ptr.value)
             ptrs = [ptr.value]
             if self.world > 1:
                 handles = [None] * self.world
-                dist.all_gather_object(handles, handle.raw, group=self.group)
+                dist.all_gather_object(handles, None if why else handle.raw, group=self.group)
                 ptrs = []
                 for s, h in enumerate(handles):
-                    if s == self.rank:
+                    if h is None:
+                        why = why or f"rank {s} could not allocate a peer buffer"
+                    elif s == self.rank:
                         ptrs.append(ptr.value)
-                        continue
-                    p = ctypes.c_void_p()
-                    capi._check(L.hcspmm_peer_open(ctypes.create_string_buffer(h, 64), ctypes.byref(p)), "hcspmm_peer_open")
-                    self._opened.append(p.value)
-                    ptrs.append(p.value)
+                    elif why is None:
+                        p = ctypes.c_void_p()
+                        if L.hcspmm_peer_open(ctypes.create_string_buffer(h, 64), ctypes.byref(p)) != 0:
+                            why = f"hcspmm_peer_open: {L.hcspmm_last_error().decode()}"
+                        else:
+                            self._opened.append(p.value)
+                            ptrs.append(p.value)
+                oks = [None] * self.world
+                dist.all_gather_object(oks, why, group=self.group)
+                why = next((w for w in oks if w), None)
+            if why:
+                raise capi.HcspmmError(f"peer memory unavailable: {why}")
         return ptr.value, ptrs
 
     def tensor(self, ptr: int, shape, dtype=torch.float32) -> torch.Tensor:
@@ -88,12 +101,12 @@ class PeerMemory:
 
 
 def halo_pull(peer_table: torch.Tensor, lds: int, src_row: torch.Tensor, seg: torch.Tensor, world: int,
-              dst: torch.Tensor, col0: int = 0, width: int | None = None, row_begin: int = 0, row_end: int | None = None):
-    """hcspmm_halo_pull on the current stream: dst[i, col0:col0+width] <- owner's row src_row[i], i in [row_begin, row_end)."""
+              dst: torch.Tensor, col0: int = 0, width: int | None = None, skip_owner: int = -1):
+    """hcspmm_halo_pull on the current stream: dst[i, col0:col0+width] <- owner's row src_row[i] for the rows of
+    every owner but skip_owner."""
     width = dst.shape[1] - col0 if width is None else width
-    row_end = dst.shape[0] if row_end is None else row_end
     with torch.cuda.device(dst.device):
         capi._check(capi.lib().hcspmm_halo_pull(peer_table.data_ptr(), lds, src_row.data_ptr(), seg.data_ptr(), world,
-                                                row_begin, row_end, col0, width, dst.data_ptr(), dst.stride(0),
+                                                skip_owner, dst.shape[0], col0, width, dst.data_ptr(), dst.stride(0),
                                                 torch.cuda.current_stream(dst.device).cuda_stream), "hcspmm_halo_pull")
     return dst

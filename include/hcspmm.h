@@ -195,9 +195,10 @@ int hcspmm_loa_reorder(const int32_t *d_rowptr, const int32_t *d_colidx, const i
  *                        flag array (peer-mapped); epoch must increase by one per call on every rank.
  *                        A peer that does not arrive within ~2 s sets *d_err = 1 instead of hanging.
  *   hcspmm_halo_pull     d_dst[i, col0 .. col0+width) = d_peer_x[s][d_src_row[i], col0 .. col0+width) for the
- *                        operand rows i in [row_begin, row_end), where s is the owner whose segment
- *                        [d_seg[s], d_seg[s+1]) holds i (the caller skips its own segment: those rows
- *                        are written in place).  d_dst is row 0 of the operand.  width, col0, lds, ldd
+ *                        operand rows i in [d_seg[s], d_seg[s+1]) of every owner s != skip_owner (the
+ *                        caller's own rows are written in place; -1 = pull every segment).  rows =
+ *                        d_seg[world].  Row batches are dealt round-robin over the owners, starting
+ *                        after skip_owner, so all NVLink peers are read at once.  width, col0, lds, ldd
  *                        multiples of 4 floats.                                                         */
 int hcspmm_peer_alloc(size_t bytes, void **d_ptr, void *handle64);
 int hcspmm_peer_open(const void *handle64, void **d_ptr);
@@ -206,7 +207,7 @@ int hcspmm_peer_free(void *d_ptr);
 int hcspmm_peer_barrier(int32_t *const *d_flag_ptrs, int32_t rank, int32_t world, int32_t epoch, int32_t *d_err,
                         void *stream);
 int hcspmm_halo_pull(const float *const *d_peer_x, int64_t lds, const int32_t *d_src_row, const int32_t *d_seg,
-                     int32_t world, int32_t row_begin, int32_t row_end, int32_t col0, int32_t width, float *d_dst,
+                     int32_t world, int32_t skip_owner, int32_t rows, int32_t col0, int32_t width, float *d_dst,
                      int64_t ldd, void *stream);
 
 /* ---- host-buffer convenience (what a non-torch caller binds) ----------------------

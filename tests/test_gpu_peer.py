@@ -20,13 +20,15 @@ def test_halo_pull_matches_indexing(dim, col0, width):
     seg = torch.tensor([0, 123, 140, 917], dtype=torch.int32, device=dev)
     table = torch.tensor([o.data_ptr() for o in owners], dtype=torch.int64, device=dev)
     dst = torch.full((917, dim), -1.0, device=dev)
-    # the caller's own segment (here: owner 1, rows [123, 140)) is skipped: two calls around it
-    peer.halo_pull(table, dim, src_row, seg, 3, dst, col0, width, 0, 123)
-    peer.halo_pull(table, dim, src_row, seg, 3, dst, col0, width, 140, 917)
+    # the caller's own segment (here: owner 1, rows [123, 140)) is skipped
+    peer.halo_pull(table, dim, src_row, seg, 3, dst, col0, width, skip_owner=1)
     want = torch.cat([o[i.long()] for o, i in zip(owners, src)])
     assert bool((dst[123:140] == -1.0).all())
     dst[123:140, col0:col0 + width] = want[123:140, col0:col0 + width]
     assert torch.equal(dst[:, col0:col0 + width], want[:, col0:col0 + width])
+    dst2 = torch.full((917, dim), -1.0, device=dev)
+    peer.halo_pull(table, dim, src_row, seg, 3, dst2, col0, width)          # every segment
+    assert torch.equal(dst2[:, col0:col0 + width], want[:, col0:col0 + width])
     untouched = torch.ones(dim, dtype=torch.bool, device=dev)
     untouched[col0:col0 + width] = False
     assert bool((dst[:, untouched] == -1.0).all())
@@ -54,5 +56,5 @@ def test_halo_pull_rejects_misaligned():
     from hcspmm import capi
     L = capi.lib()
     d = torch.zeros(8, 6, device="cuda")
-    rc = L.hcspmm_halo_pull(d.data_ptr(), 6, d.data_ptr(), d.data_ptr(), 1, 0, 8, 0, 6, d.data_ptr(), 6, None)
+    rc = L.hcspmm_halo_pull(d.data_ptr(), 6, d.data_ptr(), d.data_ptr(), 1, -1, 8, 0, 6, d.data_ptr(), 6, None)
     assert rc == -2
