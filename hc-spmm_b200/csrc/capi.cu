@@ -168,17 +168,23 @@ int hcspmm_spmm_plan(const float *d_x, int64_t ldx, int32_t x_rows, const int32_
                      const int32_t *d_hybrid_type, int32_t n_rows, int64_t nnz, int32_t dim,
                      int precision, int accumulate, float *d_y, int64_t ldy, const int32_t *d_plan,
                      int32_t n_dense, int64_t total_cols, void *stream) {
+  // the tcgen05 kernel holds a [128 x <=256] accumulator in TMEM: wider operands go in column blocks of 256
+  const int32_t dblock = dim > 256 ? 256 : dim;
   const bool dense = d_plan && n_dense > 0 && tuning().umma && precision == HCSPMM_PRECISION_TF32 && d_x && d_y &&
-                     (ldx & 3) == 0 && dense_supported(d_x, d_y, ldy, dim);
+                     (ldx & 3) == 0 && (dim % 16) == 0 && dense_supported(d_x, d_y, ldy, dblock);
   if (!dense)
     return launch_spmm(d_x, ldx, x_rows, d_rowptr, d_colidx, d_block_partition, d_edge_to_column, d_edge_to_row,
                        d_hybrid_type, n_rows, nnz, dim, precision, accumulate, d_y, ldy, (cudaStream_t)stream);
   float *xr = nullptr;
   keep_mempool_blocks();
-  cudaError_t err = cudaMallocAsync(&xr, sizeof(float) * (size_t)x_rows * dim, (cudaStream_t)stream);
+  cudaError_t err = cudaMallocAsync(&xr, sizeof(float) * (size_t)x_rows * dblock, (cudaStream_t)stream);
   if (err != cudaSuccess) { set_error("spmm_plan: cudaMallocAsync: %s", cudaGetErrorString(err)); return (int)err; }
-  int rc = launch_spmm_dense(d_x, ldx, x_rows, n_rows, dim, d_plan, n_dense, total_cols, accumulate, d_y, ldy, xr,
-                             umma_error_flag(), (cudaStream_t)stream);
+  int rc = 0;
+  for (int32_t c0 = 0; c0 < dim && rc == 0; c0 += dblock) {
+    const int32_t w = dim - c0 < dblock ? dim - c0 : dblock;
+    rc = launch_spmm_dense(d_x + c0, ldx, x_rows, n_rows, w, d_plan, n_dense, total_cols, accumulate, d_y + c0, ldy, xr,
+                           umma_error_flag(), (cudaStream_t)stream);
+  }
   if (rc == 0)
     rc = launch_spmm(d_x, ldx, x_rows, d_rowptr, d_colidx, d_block_partition, d_edge_to_column, d_edge_to_row,
                      dense_plan_labels(d_plan, n_rows, n_dense, total_cols), n_rows, nnz, dim, precision, accumulate,

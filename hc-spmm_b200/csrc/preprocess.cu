@@ -37,7 +37,10 @@ __device__ __forceinline__ int classify(int size, unsigned n_edges, int num, int
     int upad = num * BLK_W;
     // ... and the window must fit the per-window path's residency (<= 1024 condensed columns):
     // hub windows with tens of thousands of distinct columns belong to the CUDA-core path.
-    return (n_edges >= 24u && 2u * n_edges >= 3u * (unsigned)upad && upad <= 1024) ? 1 : 0;
+    // Label 3 = "tensor-core CANDIDATE": it is computed on tcgen05 when a dense super-window plan covers it
+    // and on the CUDA cores otherwise -- the per-window mma.sync path (label 1) is never faster than the
+    // CUDA-core path on B200 (format sweep, profiles/README.md), only 128-row super-windows are.
+    return (n_edges >= 24u && 2u * n_edges >= 3u * (unsigned)upad && upad <= 1024) ? 3 : 0;
   }
   float sf = (float)size;
   float df = __fdiv_rn((float)n_edges, (float)(int)((unsigned)num << 7));

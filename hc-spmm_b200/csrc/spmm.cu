@@ -426,8 +426,10 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) spmm_hybrid_kernel(const Sp
     if (p.ht != nullptr)
       for (int i = 0; i < nwin; ++i) {
         const int l = __ldg(p.ht + w0 + i);
-        if (l == 2 || (l == 0 && p.cuda_elsewhere)) sk |= 1u << i;
-        else if (l != 0 && p.precision != HCSPMM_PRECISION_FP32 && (S & 7) == 0) m |= 1u << i;
+        // 1: tensor-core window (mma.sync path below); 2: part of a dense super-window (tcgen05 kernel);
+        // 0 / 3 (candidate left without a dense plan): CUDA cores, here or in the balanced kernel
+        if (l == 2 || ((l == 0 || l == 3) && p.cuda_elsewhere)) sk |= 1u << i;
+        else if (l == 1 && p.precision != HCSPMM_PRECISION_FP32 && (S & 7) == 0) m |= 1u << i;
       }
     s_tcmask = m;
     s_skipmask = sk;
@@ -648,8 +650,13 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) spmm_balanced_kernel(const 
   auto rp = [&](int i) -> int { return y0 + (int)rp16[i]; };
   const int L = rows_here - 1;
   const int s0 = __ldg(p.rowptr + x0), t0 = __ldg(p.rowptr + x0 + 1);
-  const bool lab0 = p.ht != nullptr && __ldg(p.ht + (x0 >> 4)) != 0;
-  const bool lab1 = p.ht != nullptr && last_in && __ldg(p.ht + (x1 >> 4)) != 0;
+  auto elsewhere = [&](int row) -> bool {   // window labels 1 (mma.sync) / 2 (tcgen05 dense): not ours
+    if (p.ht == nullptr) return false;
+    const int l = __ldg(p.ht + (row >> 4));
+    return l == 1 || l == 2;
+  };
+  const bool lab0 = elsewhere(x0);
+  const bool lab1 = last_in && elsewhere(x1);
   const bool is_tail = last_in && !lab1 && __ldg(p.rowptr + x1 + 1) > y1;     // row x1 continues in item k+1
   const bool head_skip = s0 < y0 && t0 <= y0;                                 // row x0 was finished by item k-1
   const bool is_head = s0 < y0 && t0 > y0 && !lab0 && !(is_tail && L == 0);   // row x0 began earlier, ends here
@@ -660,7 +667,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) spmm_balanced_kernel(const 
   __syncthreads();
 
   auto skip = [&](int i) -> bool {
-    return (i == 0 && head_skip) || (p.ht != nullptr && __ldg(p.ht + ((x0 + i) >> 4)) != 0);
+    return (i == 0 && head_skip) || elsewhere(x0 + i);
   };
   auto out_row = [&](int i, int &acc_flag) -> float * {
     if (i == 0 && is_head) { acc_flag = 0; return bp.partial + (size_t)(2 * k) * p.dim + feat0; }

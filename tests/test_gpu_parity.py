@@ -402,6 +402,31 @@ def test_spmm_dense_plan_mixed_labels(capi):
         capi.set_tuning("umma", old)
 
 
+def test_b200_selector_labels_candidates_and_wide_dense(capi):
+    """`b200` labels tensor-core CANDIDATES (3): without a dense plan they are exact FP32 CUDA-core windows;
+    with one, the covered super-windows are TF32 on tcgen05 -- also for dim > 256 (column blocks of 256)."""
+    rp, ci = GRAPHS["sbm_1024"]
+    d_rp, d_ci = dev(rp), dev(ci)
+    bp, etc, etr, ht = capi.preprocess(d_ci, d_rp, "b200")
+    labels = ht.cpu().numpy()
+    assert set(np.unique(labels)) <= {0, 3} and (labels == 3).any()
+    old = capi.set_tuning("umma", 1)
+    try:
+        plan = capi.DensePlan(d_rp, d_ci, etr, ht, min_reuse=2.0)
+        assert plan.n_dense > 0
+        for dim in (64, 256, 384, 512):
+            x = xmat(1024, dim, seed=dim)
+            fp32 = oracle.spmm(rp, ci, x, precision=1)
+            got = capi.spmm(dev(x), d_rp, d_ci, bp, etc, etr, ht).cpu().numpy()          # no plan: all CUDA-core
+            assert rel_fro(got, fp32) <= TOL_FP32, dim
+            got = capi.spmm_plan(dev(x), d_rp, d_ci, bp, etc, etr, ht, plan).cpu().numpy()
+            assert rel_fro(got, fp32) <= TOL_TF32, dim
+            assert rel_fro(got, fp32) > 1e-6, dim                                        # the tensor cores did run (TF32)
+            assert capi.lib().hcspmm_debug_umma_error() == 0
+    finally:
+        capi.set_tuning("umma", old)
+
+
 # ---- BF16-stored X --------------------------------------------------------------------------------
 @pytest.mark.parametrize("dim", [8, 32, 64, 128, 256, 512, 200, 100])
 @pytest.mark.parametrize("name", ["rmat_1000", "rmat_hub_4096", "ring3_256", "holes_777"])
