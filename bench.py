@@ -52,6 +52,9 @@ def parse():
     ap.add_argument("--exchange", default="auto", choices=["auto", "gather", "slabs", "halo", "peer"],
                     help="N > 1: all-gather of X, all-gather pipelined in feature slabs, halo rows only (NCCL all-to-all), "
                          "peer = halo rows pulled over NVLink peer memory by our own kernel (auto picks this)")
+    ap.add_argument("--exchange-passes", type=int, default=1, choices=[1, 2],
+                    help="peer exchange: 2 = shard cut by source into two accumulating SpMM passes, second half of the pull overlapped")
+    ap.add_argument("--overlap-ctas", type=int, default=64)
     ap.add_argument("--exchange-slabs", type=int, default=1,
                     help="N > 1: all-gather X in this many feature slabs, slab k+1 in flight while the SpMM of slab k runs "
                          "(1 = one all-gather, then one SpMM)")
@@ -269,7 +272,8 @@ def main():
 
     # row-window partition (nnz-balanced) + the exchange plan of hcspmm.dist; world == 1: the whole graph
     from hcspmm import dist as hd
-    sg = hd.ShardedGraph(rp, ci, schedule=args.exchange, n_slabs=max(1, args.exchange_slabs))
+    sg = hd.ShardedGraph(rp, ci, schedule=args.exchange, n_slabs=max(1, args.exchange_slabs), n_passes=args.exchange_passes)
+    sg.overlap_ctas = args.overlap_ctas
     cuts, r0, r1 = sg.cuts, sg.r0, sg.r1
     rp_l, ci_run, pre = sg.rowptr, sg.colidx, sg.pre
     n_l, nnz_l, x_rows_run = sg.n_local, sg.nnz_local, sg.x_rows
@@ -464,7 +468,8 @@ def main():
                                          "slabs": "NCCL all_gather_into_tensor in %d feature slabs pipelined with the SpMM" % n_slabs,
                                          "halo": "halo rows only: pack + NCCL all_to_all_single per step, %d feature slab(s)" % n_slabs,
                                          "peer": "halo rows only, pulled from the owners' memory over NVLink by hcspmm_halo_pull "
-                                                 "after hcspmm_peer_barrier, %d feature slab(s)" % n_slabs}
+                                                 "after hcspmm_peer_barrier, %d feature slab(s), %d source pass(es)"
+                                                 % (n_slabs, 2 if sg.passes is not None else 1)}
                                         [sg.schedule]) if world > 1 else "none",
                            "phases": phases,
                            "l2": "inputs larger than L2 (X %.0f MB + CSR %.0f MB vs 126 MB), no flush" %

@@ -17,7 +17,7 @@ void set_error(const char *fmt, ...) {
 }
 
 Tuning &tuning() {
-  static Tuning t = {1024, 0, 1, 1, 0, 0, 1, 0, 1, 1, 1, 0, 64};
+  static Tuning t = {1024, 0, 1, 1, 0, 0, 1, 0, 1, 1, 1, 0, 0, 64};
   return t;
 }
 
@@ -91,6 +91,7 @@ int hcspmm_set_tuning(const char *key, int value) {
   else if (key && !strcmp(key, "balance")) slot = &tuning().balance;
   else if (key && !strcmp(key, "chunk")) slot = &tuning().chunk;
   else if (key && !strcmp(key, "warp_split")) slot = &tuning().warp_split;
+  else if (key && !strcmp(key, "pull_ctas")) slot = &tuning().pull_ctas;
   if (!slot) return -1;
   int old = *slot;
   *slot = value;

@@ -28,6 +28,7 @@ struct Tuning {
   int occupancy3; // 1: low-degree graphs use the 3-CTAs-per-SM build of the hybrid kernel
   int balance;    // CUDA-core windows on the merge-path balanced kernel: 0 never, 1 when nnz >= 8 * rows, 2 always
   int chunk;      // rows + stored entries per item of the balanced kernel (0 = ~4 MB of gathered rows, 4096..8192)
+  int pull_ctas;  // grid cap of the halo-pull kernel (0 = 148 * 8)
   int warp_split; // items whose mean row length is >= this give every warp an equal run of entries (0 = never)
 };
 Tuning &tuning();

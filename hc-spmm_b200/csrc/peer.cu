@@ -44,36 +44,44 @@ __global__ void peer_barrier_kernel(int *const *flag_ptrs, int rank, int world, 
 
 constexpr int PULL_ROWS = 8;   // rows in flight per warp
 
-// dst[i, c0 .. c0+width) = peer_x[s][src_row[i], c0 .. c0+width) for the operand rows i of every owner
-// s != skip (segment [seg[s], seg[s+1])).  Batches of PULL_ROWS rows are dealt round-robin over the
-// owners, starting after `skip`: the warps of a CTA read from different peers at the same time and the
-// ranks start on different owners, so no owner's NVLink egress is the one everybody waits for.
+// dst[i, c0 .. c0+width) = peer_x[s][src_row[i], c0 .. c0+width) for the operand rows i of every owner s
+// in owner_mask (segment [seg[s], seg[s+1])).  Batches of PULL_ROWS rows are dealt round-robin over the
+// owners, starting at `first`: the warps of a CTA read from different peers at the same time and the ranks
+// start on different owners, so no owner's NVLink egress is the one everybody waits for.
 __global__ void __launch_bounds__(256) halo_pull_kernel(const float *const *__restrict__ peer_x, long long lds,
                                                         const int *__restrict__ src_row, const int *__restrict__ seg,
-                                                        int world, int skip, int c0, int width,
-                                                        float *__restrict__ dst, long long ldd) {
+                                                        int world, unsigned long long owner_mask, int first, int c0,
+                                                        int width, float *__restrict__ dst, long long ldd) {
   __shared__ int s_seg[65];
   __shared__ const float *s_base[64];
-  __shared__ int s_nb;
+  __shared__ int s_list[64];
+  __shared__ int s_nb, s_ninc;
   for (int i = threadIdx.x; i <= world; i += blockDim.x) s_seg[i] = seg[i];
   for (int i = threadIdx.x; i < world; i += blockDim.x) s_base[i] = peer_x[i];
   __syncthreads();
   if (threadIdx.x == 0) {
-    int nb = 0;
-    for (int o = 0; o < world; ++o)
-      if (o != skip) nb = max(nb, (s_seg[o + 1] - s_seg[o] + PULL_ROWS - 1) / PULL_ROWS);
+    int nb = 0, ninc = 0;
+    for (int i = 0; i < world; ++i) {
+      const int o = (first + i) % world;
+      if (!((owner_mask >> o) & 1ull)) continue;
+      s_list[ninc++] = o;
+      nb = max(nb, (s_seg[o + 1] - s_seg[o] + PULL_ROWS - 1) / PULL_ROWS);
+    }
     s_nb = nb;
+    s_ninc = ninc;
   }
   __syncthreads();
+  const int ninc = s_ninc;
+  if (ninc == 0) return;
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int n_warps = (gridDim.x * blockDim.x) >> 5;
   const int nvec = width >> 2;
-  const long long total = (long long)s_nb * world;
+  const long long total = (long long)s_nb * ninc;
   for (long long t = warp; t < total; t += n_warps) {
-    const int o = (int)((t + skip + 1) % world);
-    const int r0 = s_seg[o] + (int)(t / world) * PULL_ROWS, r1 = s_seg[o + 1];
-    if (o == skip || r0 >= r1) continue;
+    const int o = s_list[(int)(t % ninc)];
+    const int r0 = s_seg[o] + (int)(t / ninc) * PULL_ROWS, r1 = s_seg[o + 1];
+    if (r0 >= r1) continue;
     const float *base = s_base[o] + c0;
     const float *src[PULL_ROWS];
 #pragma unroll
@@ -148,11 +156,11 @@ int hcspmm_peer_barrier(int32_t *const *d_flag_ptrs, int32_t rank, int32_t world
 }
 
 int hcspmm_halo_pull(const float *const *d_peer_x, int64_t lds, const int32_t *d_src_row, const int32_t *d_seg,
-                     int32_t world, int32_t skip_owner, int32_t rows, int32_t col0, int32_t width, float *d_dst,
-                     int64_t ldd, void *stream) {
-  if (rows <= 0 || width == 0) return 0;
+                     int32_t world, uint64_t owner_mask, int32_t first_owner, int32_t rows, int32_t col0, int32_t width,
+                     float *d_dst, int64_t ldd, void *stream) {
+  if (rows <= 0 || width == 0 || owner_mask == 0) return 0;
   if (!d_peer_x || !d_src_row || !d_seg || !d_dst || world < 1 || world > 64 || width < 0 || col0 < 0 ||
-      skip_owner >= world) {
+      first_owner < 0) {
     set_error("halo_pull: bad argument");
     return HCSPMM_E_INVALID;
   }
@@ -160,12 +168,12 @@ int hcspmm_halo_pull(const float *const *d_peer_x, int64_t lds, const int32_t *d
     set_error("halo_pull: width, col0 and leading dims must be multiples of 4 floats, dst 16-byte aligned");
     return HCSPMM_E_ALIGN;
   }
-  if (skip_owner < 0) skip_owner = -1;
   const long long warps = ((long long)rows + PULL_ROWS - 1) / PULL_ROWS + world;
   long long grid = (warps + 7) / 8;
-  if (grid > 148 * 8) grid = 148 * 8;
-  halo_pull_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(d_peer_x, lds, d_src_row, d_seg, world, skip_owner,
-                                                                     col0, width, d_dst, ldd);
+  const long long cap = tuning().pull_ctas > 0 ? tuning().pull_ctas : 148 * 8;
+  if (grid > cap) grid = cap;
+  halo_pull_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(d_peer_x, lds, d_src_row, d_seg, world, owner_mask,
+                                                                     first_owner % world, col0, width, d_dst, ldd);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("halo_pull: %s", cudaGetErrorString(e)); return (int)e; }
   return 0;

@@ -65,6 +65,7 @@ struct BalParams {
   int *split_row;    // [n_items][2]: row whose sum ENDS in this item but began earlier (slot 0) /
                      //               row whose sum continues in the next item (slot 1); -1 = none
   const int *splits; // [n_items + 1]: rows consumed before diagonal k * chunk (merge_path_splits_kernel)
+  int low_degree;    // mean row length < 64: launch the three-CTAs-per-SM build
   int warp_split;    // > 0: items with a mean row length >= warp_split give every warp an equal run of entries;
                      // other items (and 0) use the warp-per-row / CTA-per-long-row phases
 };
@@ -1015,15 +1016,25 @@ static cudaError_t launch_hybrid(const SpmmParams &p, dim3 grid, size_t smem, cu
   return launch_hybrid_b<LPE, NV, VW, HCSPMM_MIN_CTAS>(p, grid, smem, stream);
 }
 
-template <int LPE, int NV, int VW, bool B16>
-static cudaError_t launch_balanced_t(const BalParams &bp, dim3 grid, size_t smem, cudaStream_t stream) {
-  auto kern = spmm_balanced_kernel<LPE, NV, VW, HCSPMM_MIN_CTAS, B16>;
+template <int LPE, int NV, int VW, bool B16, int MINB>
+static cudaError_t launch_balanced_b(const BalParams &bp, dim3 grid, size_t smem, cudaStream_t stream) {
+  auto kern = spmm_balanced_kernel<LPE, NV, VW, MINB, B16>;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
   BalParams q = bp;
   q.s.short_row = bp.s.short_row * (32 / LPE);
   kern<<<grid, CTA_THREADS, smem, stream>>>(q);
   return cudaGetLastError();
+}
+template <int LPE, int NV, int VW, bool B16>
+static cudaError_t launch_balanced_t(const BalParams &bp, dim3 grid, size_t smem, cudaStream_t stream) {
+  // low-degree graphs (rows of a few dozen entries) are latency-bound: three CTAs per SM hide more of it than
+  // the deeper gather ring of the two-CTA build does (FP32 256-bit variants only, to bound compile time)
+  if constexpr (!B16 && VW == 8 && NV == 1) {
+    if (bp.low_degree && tuning().occupancy3 >= 2) return launch_balanced_b<LPE, NV, VW, B16, 4>(bp, grid, smem, stream);
+    if (bp.low_degree && tuning().occupancy3) return launch_balanced_b<LPE, NV, VW, B16, 3>(bp, grid, smem, stream);
+  }
+  return launch_balanced_b<LPE, NV, VW, B16, HCSPMM_MIN_CTAS>(bp, grid, smem, stream);
 }
 
 // "balance" knob: 0 off, 2 always, 1 (default) when the mean row holds >= 8 entries -- below that the
@@ -1060,6 +1071,7 @@ static cudaError_t run_balanced(const SpmmParams &p, long long nnz, bool v8, boo
   int *splits = bp.split_row + 2 * (size_t)n_items;
   bp.splits = splits;
   bp.warp_split = tuning().warp_split;   // mean row length from which an item is cut by warp runs
+  bp.low_degree = nnz < 64LL * p.n_rows;
   merge_path_splits_kernel<<<(unsigned)((n_items + 1 + 127) / 128), 128, 0, stream>>>(p.rowptr, p.n_rows, nnz, chunk,
                                                                                     (int)n_items, splits);
   const int slab = p.slab;

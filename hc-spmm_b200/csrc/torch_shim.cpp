@@ -293,7 +293,7 @@ bool set_bug_compat(bool on) {
 
 int64_t set_tuning(const std::string &key, int64_t value) {
   int old = hcspmm_set_tuning(key.c_str(), (int)value);
-  TORCH_CHECK(old != -1 || key == "slab" || key == "long_row" || key == "vec8" || key == "short_row" || key == "wpc" || key == "umma" || key == "pad_odd" || key == "umma_gemm" || key == "dense_ws" || key == "occupancy3" || key == "balance" || key == "chunk" || key == "warp_split",
+  TORCH_CHECK(old != -1 || key == "slab" || key == "long_row" || key == "vec8" || key == "short_row" || key == "wpc" || key == "umma" || key == "pad_odd" || key == "umma_gemm" || key == "dense_ws" || key == "occupancy3" || key == "balance" || key == "chunk" || key == "warp_split" || key == "pull_ctas",
               "unknown tuning key '", key, "'");
   return old;
 }

@@ -75,7 +75,7 @@ def lib() -> ctypes.CDLL:
         L.hcspmm_peer_close.argtypes = [_vp]
         L.hcspmm_peer_free.argtypes = [_vp]
         L.hcspmm_peer_barrier.argtypes = [_vp, _i32, _i32, _i32, _vp, _vp]
-        L.hcspmm_halo_pull.argtypes = [_vp, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp]
+        L.hcspmm_halo_pull.argtypes = [_vp, _i64, _vp, _vp, _i32, ctypes.c_uint64, _i32, _i32, _i32, _i32, _vp, _i64, _vp]
         _lib = L
     return _lib
 

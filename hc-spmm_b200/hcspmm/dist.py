@@ -45,13 +45,18 @@ import torch.distributed as dist
 from . import partition
 
 
+def capi_set_tuning(key, value):
+    from . import capi
+    return capi.set_tuning(key, value)
+
+
 def _default_spmm():
     import HCSPMM
 
-    def run(x, rowptr, colidx, pre, out=None):
+    def run(x, rowptr, colidx, pre, out=None, accumulate=False):
         if out is None:
             return HCSPMM.forward(x, rowptr, colidx, *pre)[0]
-        return HCSPMM.spmm_strided(x, rowptr, colidx, *pre[:4], out, False)
+        return HCSPMM.spmm_strided(x, rowptr, colidx, *pre[:4], out, accumulate)
 
     def prep(colidx, rowptr):
         n = rowptr.numel() - 1
@@ -62,10 +67,13 @@ def _default_spmm():
 
 class ShardedGraph:
     def __init__(self, rowptr: torch.Tensor, colidx: torch.Tensor, group=None, schedule: str = "gather",
-                 n_slabs: int = 2, spmm=None, preprocess=None, cuts=None):
+                 n_slabs: int = 2, spmm=None, preprocess=None, cuts=None, n_passes: int = 1):
         """rowptr / colidx: the FULL graph's CSR on this rank's device (identical on every rank).
         cuts: reuse another ShardedGraph's row cuts (the transposed graph for backward must be
-        partitioned like the forward one)."""
+        partitioned like the forward one).
+        n_passes = 2 ("peer" schedule only): the shard is cut by SOURCE into two CSRs -- own rows + the nearer half
+        of the owners, and the farther half -- and aggregated in two accumulating SpMM passes, the second
+        half of the pull travelling (few CTAs, high-priority stream) while the first pass computes."""
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -112,6 +120,10 @@ class ShardedGraph:
             spmm, preprocess = _default_spmm()
         self._spmm = spmm
         self.pre = preprocess(self.colidx, self.rowptr) if preprocess is not None else ()
+        self.passes = None
+        self.overlap_ctas = 64
+        if self.peer is not None and n_passes == 2 and self.world > 2:
+            self._setup_passes(preprocess)
         self._bufs = {}
         self._comm_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
 
@@ -208,6 +220,25 @@ class ShardedGraph:
             self.peer.close()
             self.peer = None
 
+    def _setup_passes(self, preprocess):
+        """Cut the shard by source: pass 0 = own rows + the owners rank+1 .. rank+h (mod P), pass 1 = the rest."""
+        P, r, seg = self.world, self.rank, self.halo["seg"].to(torch.int64)
+        h = (P - 1 + 1) // 2
+        near = [(r + i) % P for i in range(1, h + 1)]
+        far = [o for o in range(P) if o != r and o not in near]
+        owner = torch.bucketize(self.colidx.to(torch.int64), seg[1:-1], right=True)
+        in0 = torch.zeros(P, dtype=torch.bool, device=owner.device)
+        in0[[r] + near] = True
+        m0 = in0[owner]
+        rows = torch.repeat_interleave(torch.arange(self.n_local, device=owner.device),
+                                       (self.rowptr[1:] - self.rowptr[:-1]).to(torch.int64))
+        self.passes = []
+        for m, owners in ((m0, near), (~m0, far)):
+            rp = torch.zeros(self.n_local + 1, dtype=torch.int64, device=owner.device)
+            rp[1:] = torch.cumsum(torch.bincount(rows[m], minlength=self.n_local), 0)
+            rp, ci = rp.to(torch.int32), self.colidx[m].contiguous()
+            self.passes.append(dict(rowptr=rp, colidx=ci, pre=preprocess(ci, rp), mask=sum(1 << o for o in owners)))
+
     def _peer_stage(self, x_local: torch.Tensor):
         """Write the shard into the own-rows segment of this width's next operand buffer (peer-visible) and pass
         the barrier: afterwards every rank's shard of this aggregation can be pulled.  -> (operand, padded width)."""
@@ -232,14 +263,33 @@ class ShardedGraph:
         self.peer.barrier()
         return cat, dpad
 
-    def _pull_halo(self, cat, dpad, col0=0, width=None):
-        h = self.halo                                            # own rows are already in place: skip that segment
-        self._pull(self._peer_tab, dpad, h["src_row"], h["seg"], self.world, cat, col0, width, self.rank)
+    def _pull_halo(self, cat, dpad, col0=0, width=None, mask=None):
+        h = self.halo                                            # own rows are already in place: own bit clear
+        mask = (((1 << self.world) - 1) & ~(1 << self.rank)) if mask is None else mask
+        self._pull(self._peer_tab, dpad, h["src_row"], h["seg"], self.world, cat, col0, width, mask, self.rank + 1)
 
     def _aggregate_peer(self, x_local: torch.Tensor) -> torch.Tensor:
         dim, dev = x_local.shape[1], x_local.device
         cat, dpad = self._peer_stage(x_local.float())
         n_slabs = self.n_slabs if dpad >= 32 * self.n_slabs else 1
+        if self.passes is not None:
+            p0, p1 = self.passes
+            y = torch.empty(self.n_local, dpad, device=dev)
+            cur, comm = torch.cuda.current_stream(dev), self._hi_stream
+            self._pull_halo(cat, dpad, mask=p0["mask"])
+            ev0 = torch.cuda.Event()
+            ev0.record(cur)
+            with torch.cuda.stream(comm):
+                comm.wait_event(ev0)                              # first half has landed
+                old = capi_set_tuning("pull_ctas", self.overlap_ctas)   # NVLink-bound: leave the SMs to pass 0
+                self._pull_halo(cat, dpad, mask=p1["mask"])
+                capi_set_tuning("pull_ctas", old)
+                ev1 = torch.cuda.Event()
+                ev1.record(comm)
+            self._spmm(cat, p0["rowptr"], p0["colidx"], p0["pre"], out=y)
+            cur.wait_event(ev1)
+            self._spmm(cat, p1["rowptr"], p1["colidx"], p1["pre"], out=y, accumulate=True)
+            return y if dpad == dim else y[:, :dim]
         if n_slabs == 1:
             self._pull_halo(cat, dpad)
             y = self._spmm(cat, self.rowptr, self.colidx, self.pre)

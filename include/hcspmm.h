@@ -82,6 +82,7 @@ const char *hcspmm_last_error(void);
  *                CTA, hub rows cut into pieces that are summed in a fixed order): 1 (default) when the
  *                mean row holds >= 8 entries, 2 always, 0 never (one CTA per "wpc" 16-row windows)
  *   "chunk"      rows + stored entries per item of the balanced kernel (0 = about 4 MB of gathered rows)
+ *   "pull_ctas"  grid cap of hcspmm_halo_pull (0 = 1184)
  *   "warp_split" items of the balanced kernel whose mean row length is >= this (default 64) give every warp
  *                an equal run of entries; 0 = warp-per-row / CTA-per-long-row phases everywhere
  * Returns the previous value, or -1 for an unknown key.                          */
@@ -195,11 +196,13 @@ int hcspmm_loa_reorder(const int32_t *d_rowptr, const int32_t *d_colidx, const i
  *                        flag array (peer-mapped); epoch must increase by one per call on every rank.
  *                        A peer that does not arrive within ~2 s sets *d_err = 1 instead of hanging.
  *   hcspmm_halo_pull     d_dst[i, col0 .. col0+width) = d_peer_x[s][d_src_row[i], col0 .. col0+width) for the
- *                        operand rows i in [d_seg[s], d_seg[s+1]) of every owner s != skip_owner (the
- *                        caller's own rows are written in place; -1 = pull every segment).  rows =
- *                        d_seg[world].  Row batches are dealt round-robin over the owners, starting
- *                        after skip_owner, so all NVLink peers are read at once.  width, col0, lds, ldd
- *                        multiples of 4 floats.                                                         */
+ *                        operand rows i in [d_seg[s], d_seg[s+1]) of every owner s whose bit is set in
+ *                        owner_mask (the caller leaves its own bit clear: its rows are written in place).
+ *                        rows = d_seg[world].  Row batches are dealt round-robin over those owners,
+ *                        starting at first_owner (use own rank + 1), so all NVLink peers are read at once
+ *                        and the ranks do not gang up on one owner.  width, col0, lds, ldd multiples of 4
+ *                        floats.  Knob "pull_ctas" caps the grid (a pull that overlaps an SpMM should
+ *                        leave it the SMs: the copy is NVLink-bound).                                    */
 int hcspmm_peer_alloc(size_t bytes, void **d_ptr, void *handle64);
 int hcspmm_peer_open(const void *handle64, void **d_ptr);
 int hcspmm_peer_close(void *d_ptr);
@@ -207,8 +210,8 @@ int hcspmm_peer_free(void *d_ptr);
 int hcspmm_peer_barrier(int32_t *const *d_flag_ptrs, int32_t rank, int32_t world, int32_t epoch, int32_t *d_err,
                         void *stream);
 int hcspmm_halo_pull(const float *const *d_peer_x, int64_t lds, const int32_t *d_src_row, const int32_t *d_seg,
-                     int32_t world, int32_t skip_owner, int32_t rows, int32_t col0, int32_t width, float *d_dst,
-                     int64_t ldd, void *stream);
+                     int32_t world, uint64_t owner_mask, int32_t first_owner, int32_t rows, int32_t col0, int32_t width,
+                     float *d_dst, int64_t ldd, void *stream);
 
 /* ---- host-buffer convenience (what a non-torch caller binds) ----------------------
  * A graph handle owns device copies of the CSR and of the preprocessing products.

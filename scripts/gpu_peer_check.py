@@ -23,8 +23,9 @@ def main():
     n = rp.numel() - 1
     ref = hd.ShardedGraph(rp, ci, schedule="gather")
     ok = True
-    for slabs in (1, 2):
-        g = hd.ShardedGraph(rp, ci, schedule="peer", n_slabs=slabs)
+    for slabs, passes in ((1, 1), (2, 1), (1, 2)):
+        g = hd.ShardedGraph(rp, ci, schedule="peer", n_slabs=slabs, n_passes=passes)
+        assert passes == 1 or dist.get_world_size() <= 2 or g.passes is not None
         assert g.schedule == "peer" and g.halo["rows"] <= n
         for dim in (128, 47, 256, 64):
             x = torch.randn(n, dim, device=dev, generator=torch.Generator(device=dev).manual_seed(dim))[g.r0:g.r1].contiguous()
@@ -33,9 +34,9 @@ def main():
                 got = g.aggregate(x + rep)
                 err = float((got - want).abs().max() / want.abs().max())
                 # (a width that is not a multiple of 4 takes the scalar CSR-order kernel on small gather shards)
-                if err > (1e-6 if dim % 4 == 0 else 2e-5):
+                if err > (1e-6 if dim % 4 == 0 and passes == 1 else 2e-5):
                     ok = False
-                    print(f"rank {g.rank} slabs {slabs} dim {dim} rep {rep}: rel err {err}", flush=True)
+                    print(f"rank {g.rank} slabs {slabs} passes {passes} dim {dim} rep {rep}: rel err {err}", flush=True)
         torch.manual_seed(0)
         m_ref = hd.DistGCN(ref, 100, 128, 47, seed=1).to(dev)
         m = hd.DistGCN(g, 100, 128, 47, seed=1).to(dev)

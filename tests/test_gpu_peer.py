@@ -21,7 +21,7 @@ def test_halo_pull_matches_indexing(dim, col0, width):
     table = torch.tensor([o.data_ptr() for o in owners], dtype=torch.int64, device=dev)
     dst = torch.full((917, dim), -1.0, device=dev)
     # the caller's own segment (here: owner 1, rows [123, 140)) is skipped
-    peer.halo_pull(table, dim, src_row, seg, 3, dst, col0, width, skip_owner=1)
+    peer.halo_pull(table, dim, src_row, seg, 3, dst, col0, width, owner_mask=0b101, first_owner=2)
     want = torch.cat([o[i.long()] for o, i in zip(owners, src)])
     assert bool((dst[123:140] == -1.0).all())
     dst[123:140, col0:col0 + width] = want[123:140, col0:col0 + width]
@@ -56,5 +56,5 @@ def test_halo_pull_rejects_misaligned():
     from hcspmm import capi
     L = capi.lib()
     d = torch.zeros(8, 6, device="cuda")
-    rc = L.hcspmm_halo_pull(d.data_ptr(), 6, d.data_ptr(), d.data_ptr(), 1, -1, 8, 0, 6, d.data_ptr(), 6, None)
+    rc = L.hcspmm_halo_pull(d.data_ptr(), 6, d.data_ptr(), d.data_ptr(), 1, 1, 0, 8, 0, 6, d.data_ptr(), 6, None)
     assert rc == -2
