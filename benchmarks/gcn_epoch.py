@@ -35,6 +35,9 @@ def main():
     ap.add_argument("--model", default="gcn", choices=["gcn", "gin"],
                     help="gcn: X' = A (X W) (GNN_model.py:61-162); gin: X' = (A X) W (GNN_model.py:166-232)")
     ap.add_argument("--dense", action="store_true", help="tcgen05 dense super-window plans (single GPU)")
+    ap.add_argument("--fp32-matmul", action="store_true",
+                    help="Update GEMMs (torch.mm) in full FP32; default TF32 like the reference's stack "
+                         "(PyTorch 1.8: allow_tf32 on by default; its fused kernels use wmma TF32, :1809-1837)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -45,6 +48,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     import HCSPMM
     from hcspmm import dist as hd, graphs
+    torch.backends.cuda.matmul.allow_tf32 = not args.fp32_matmul
     HCSPMM.set_dense(bool(args.dense))
     HCSPMM.set_classifier(args.classifier)
     rp, ci, info = graphs.named(args.shape, device=dev, scale=args.scale)
@@ -114,7 +118,7 @@ def main():
                                      "stored_entries": info["nnz"], "feat": args.feat, "hidden": args.hidden,
                                      "classes": args.classes, "schedule": g.schedule, "slabs": g.n_slabs,
                                      "exchange_rows_vs_allgather": (g.exchange_rows() / max(1, (world - 1) * g.max_rows)) if world > 1 else None,
-                                     "classifier": args.classifier},
+                                     "classifier": args.classifier, "update_gemm": "fp32" if args.fp32_matmul else "tf32 (torch.mm, allow_tf32)"},
                           "phases": phases, "loss_first": losses[0], "loss_last": losses[-1]}))
     if world > 1:
         g.close()
