@@ -375,11 +375,12 @@ def main():
     peak, peak_src = measured_peak_gbs()
     bytes_alg = nnz_l * (4 + 4 * dim) + n_l * (4 * dim + 4)
     bytes_min = 4 * nnz_l + 4 * (n_l + 1) + 4 * (n + n_l) * dim
-    kern_ms = statistics.mean(step_ms) if world == 1 else None
+    # N = 1: the step IS the SpMM; N > 1: this rank's local SpMM timed on its own (phases, max over ranks)
+    kern_ms = statistics.mean(step_ms) if world == 1 else (phases or {}).get("kernel_only_ms")
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = tj.get(f"{args.shape}_dim{dim}_{args.classifier}")
+        traffic = tj.get(f"{args.shape}_dim{dim}_{args.classifier}") if world == 1 else None
     except Exception:
         pass
     roofline = None
@@ -391,7 +392,9 @@ def main():
                               if balanced else "spmm_hybrid_kernel",
                     "kernel_ms": kern_ms, "algorithmic_bytes": bytes_alg,
                     "compulsory_bytes": bytes_min, "compulsory_frac": bytes_min / (kern_ms * 1e-3) / 1e9 / peak,
-                    "frac_of_nominal_8TBs": ach / 8000.0}
+                    "frac_of_nominal_8TBs": ach / 8000.0,
+                    "scope": "whole graph, one GPU" if world == 1 else
+                             "rank 0's row shard on one GPU (local SpMM timed alone, max over ranks)"}
 
     # e2e: the reference-facing module with HOST buffers, H2D of X and D2H of Y inside the timed region
     e2e = None

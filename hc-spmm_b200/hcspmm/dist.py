@@ -5,8 +5,9 @@ multi-GPU code at all; this layer sits above the HCSPMM entry points and changes
 
 Rank r owns the 16-row windows [cuts[r], cuts[r+1]) of A (nnz-balanced, hcspmm.partition), the
 matching rows of X / Y, and the preprocessing of its shard.  One aggregation Y_r = A_r * X is
-    exchange:  all-gather of the row shards of X   (NCCL over NVLink / NVSwitch)
-    compute:   local hybrid SpMM on the gathered X (rectangular: n_r x N)
+    exchange:  the rows of X the shard references reach the rank (default: pulled over NVLink peer
+               memory by our own kernels; NCCL collectives as alternatives / fallback)
+    compute:   local hybrid SpMM on the exchanged operand (rectangular: n_r x operand rows)
 Schedules:
   * "gather":   one all_gather_into_tensor, then one SpMM launch;
   * "slabs":    X is exchanged in feature slabs; the SpMM of slab k (a strided view of the gathered
@@ -45,11 +46,6 @@ import torch.distributed as dist
 from . import partition
 
 
-def capi_set_tuning(key, value):
-    from . import capi
-    return capi.set_tuning(key, value)
-
-
 def _default_spmm():
     import HCSPMM
 
@@ -67,7 +63,7 @@ def _default_spmm():
 
 class ShardedGraph:
     def __init__(self, rowptr: torch.Tensor, colidx: torch.Tensor, group=None, schedule: str = "gather",
-                 n_slabs: int = 2, spmm=None, preprocess=None, cuts=None, n_passes: int = 1):
+                 n_slabs: int = 1, spmm=None, preprocess=None, cuts=None, n_passes: int = 1):
         """rowptr / colidx: the FULL graph's CSR on this rank's device (identical on every rank).
         cuts: reuse another ShardedGraph's row cuts (the transposed graph for backward must be
         partitioned like the forward one).
@@ -185,7 +181,8 @@ class ShardedGraph:
         return self.halo["rows"] if self.halo is not None else self.world * self.max_rows
 
     def exchange(self, x_local: torch.Tensor) -> torch.Tensor:
-        """The exchange step on its own (one piece, not pipelined): the operand of the local SpMM."""
+        """The exchange step on its own (one piece, not pipelined): the operand of the local SpMM.  The result is
+        one of the graph's reusable exchange buffers: consume it before the next exchange of the same width."""
         dim, dev, dt = x_local.shape[1], x_local.device, x_local.dtype
         if self.world == 1:
             return x_local
@@ -281,9 +278,10 @@ class ShardedGraph:
             ev0.record(cur)
             with torch.cuda.stream(comm):
                 comm.wait_event(ev0)                              # first half has landed
-                old = capi_set_tuning("pull_ctas", self.overlap_ctas)   # NVLink-bound: leave the SMs to pass 0
+                from . import capi
+                old = capi.set_tuning("pull_ctas", self.overlap_ctas)   # NVLink-bound: leave the SMs to pass 0
                 self._pull_halo(cat, dpad, mask=p1["mask"])
-                capi_set_tuning("pull_ctas", old)
+                capi.set_tuning("pull_ctas", old)
                 ev1 = torch.cuda.Event()
                 ev1.record(comm)
             self._spmm(cat, p0["rowptr"], p0["colidx"], p0["pre"], out=y)
