@@ -1029,8 +1029,8 @@ static cudaError_t launch_balanced_b(const BalParams &bp, dim3 grid, size_t smem
 template <int LPE, int NV, int VW, bool B16>
 static cudaError_t launch_balanced_t(const BalParams &bp, dim3 grid, size_t smem, cudaStream_t stream) {
   // low-degree graphs (rows of a few dozen entries) are latency-bound: three CTAs per SM hide more of it than
-  // the deeper gather ring of the two-CTA build does (FP32 256-bit variants only, to bound compile time)
-  if constexpr (!B16 && VW == 8 && NV == 1) {
+  // the deeper gather ring of the two-CTA build does (FP32, one vector per lane: dim <= 256 / 128)
+  if constexpr (!B16 && NV == 1) {
     if (bp.low_degree && tuning().occupancy3 >= 2) return launch_balanced_b<LPE, NV, VW, B16, 4>(bp, grid, smem, stream);
     if (bp.low_degree && tuning().occupancy3) return launch_balanced_b<LPE, NV, VW, B16, 3>(bp, grid, smem, stream);
   }

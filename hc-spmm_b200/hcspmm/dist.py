@@ -240,7 +240,7 @@ class ShardedGraph:
         """Write the shard into the own-rows segment of this width's next operand buffer (peer-visible) and pass
         the barrier: afterwards every rank's shard of this aggregation can be pulled.  -> (operand, padded width)."""
         dim, dev = x_local.shape[1], x_local.device
-        dpad = (dim + 3) // 4 * 4
+        dpad = (dim + 7) // 8 * 8                                 # 32-byte rows: the 256-bit gather path
         key = ("peer", dpad)
         h = self.halo
         if key not in self._bufs:

@@ -27,14 +27,14 @@ def main():
         g = hd.ShardedGraph(rp, ci, schedule="peer", n_slabs=slabs, n_passes=passes)
         assert passes == 1 or dist.get_world_size() <= 2 or g.passes is not None
         assert g.schedule == "peer" and g.halo["rows"] <= n
-        for dim in (128, 47, 256, 64):
+        for dim in (128, 47, 100, 256, 64):
             x = torch.randn(n, dim, device=dev, generator=torch.Generator(device=dev).manual_seed(dim))[g.r0:g.r1].contiguous()
             for rep in range(3):                      # both buffer slots, repeatedly
                 want = ref.aggregate(x + rep)
                 got = g.aggregate(x + rep)
                 err = float((got - want).abs().max() / want.abs().max())
                 # (a width that is not a multiple of 4 takes the scalar CSR-order kernel on small gather shards)
-                if err > (1e-6 if dim % 4 == 0 and passes == 1 else 2e-5):
+                if err > (1e-6 if dim % 8 == 0 and passes == 1 else 2e-5):
                     ok = False
                     print(f"rank {g.rank} slabs {slabs} passes {passes} dim {dim} rep {rep}: rel err {err}", flush=True)
         torch.manual_seed(0)
