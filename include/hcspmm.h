@@ -43,7 +43,8 @@ extern "C" {
 
 /* Core selector (hybrid_type) variants.  0/1 are bit-exact restatements of the
  * reference, hybrid_all_kernel.cu:262 (shipped) and :261 (intended, commented
- * out in the reference).  2 is the B200 re-fit.                    */
+ * out in the reference).  2 is the B200 re-fit: it labels tensor-core
+ * CANDIDATES (value 3 in hybrid_type), never 1.                                */
 #define HCSPMM_CLASSIFIER_SHIPPED   0
 #define HCSPMM_CLASSIFIER_INTENDED  1
 #define HCSPMM_CLASSIFIER_B200      2
@@ -83,6 +84,9 @@ const char *hcspmm_last_error(void);
  *                mean row holds >= 8 entries, 2 always, 0 never (one CTA per "wpc" 16-row windows)
  *   "chunk"      rows + stored entries per item of the balanced kernel (0 = about 4 MB of gathered rows)
  *   "pull_ctas"  grid cap of hcspmm_halo_pull (0 = 1184)
+ *   "occupancy3" low-degree graphs (mean row < 64 entries) use a build of the SpMM kernels that fits 3 (value 1,
+ *                default) or 4 (value 2) CTAs per SM instead of 2; 0 = always the 2-CTA build
+ *   "dense_ws"   1 (default): warp-specialised tcgen05 dense kernel; 0: the single-role variant
  *   "warp_split" items of the balanced kernel whose mean row length is >= this (default 64) give every warp
  *                an equal run of entries; 0 = warp-per-row / CTA-per-long-row phases everywhere
  * Returns the previous value, or -1 for an unknown key.                          */
@@ -106,9 +110,12 @@ int hcspmm_preprocess(const int32_t *d_colidx, const int32_t *d_rowptr, int32_t 
  * Replaces spmm_forward_plus / _more / _fixed32 / _fixed64 and their kernels
  * (hybrid_all_kernel.cu:410-595, 919-1637; pybind hybrid_all.cpp:194-308) for ANY
  * dim (the reference needs dim == 32 / 64 / <= 48 depending on the entry point).
- * One launch; each 16-row window takes the CUDA-core or the tensor-core path by
- * d_hybrid_type[w].  d_hybrid_type may be NULL (all CUDA-core).  accumulate != 0
- * computes Y += A*X (used by the shard-pipelined multi-GPU path).
+ * Each 16-row window takes the CUDA-core or the tensor-core path by d_hybrid_type[w]
+ * (0 = CUDA cores, 1 = tensor cores as in the reference; 3 = tensor-core candidate of the
+ * B200 selector: CUDA cores here, tcgen05 under hcspmm_spmm_plan).  CUDA-core windows run
+ * on the work-balanced kernel (merge_path_splits + spmm_balanced + fixup launches), windows
+ * labelled 1 on the per-window mma.sync kernel; results do not depend on scheduling.
+ * d_hybrid_type may be NULL (all CUDA-core).  accumulate != 0 computes Y += A*X.
  * Fast paths need d_x/d_y 16-byte aligned and ldx/ldy/dim multiples of 4; anything
  * else takes a scalar kernel.                                                       */
 int hcspmm_spmm(const float *d_x, int64_t ldx, int32_t x_rows, const int32_t *d_rowptr,
