@@ -356,6 +356,7 @@ def main():
                   "exchange_bytes_per_rank": int(sg.exchange_rows() * dim * 4),
                   "exchange_rows_vs_allgather": sg.exchange_rows() / max(1, (world - 1) * sg.max_rows)}
 
+    sg.check()          # a peer barrier that timed out would have left stale rows in the operand
     # quick full-size sanity inside the bench (not timed): X = 1 gives the row degrees exactly
     ones = torch.ones(x_rows_run, 8, device=dev)
     deg = HCSPMM.forward(ones, rp_l, ci_run, *pre)[0][:, 0]

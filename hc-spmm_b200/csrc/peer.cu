@@ -9,7 +9,7 @@
 //     process per GPU, any launcher; the own rows are written in place and are what the peers read;
 //   * hcspmm_peer_barrier: one tiny kernel; thread s stores this rank's epoch into peer s's flag
 //     array (system-scope release) and spins on the local flag of peer s (acquire), so after it every
-//     peer's shard written before ITS barrier is visible.  Spins are bounded (~2 s) and report through
+//     peer's shard written before ITS barrier is visible.  Spins are bounded (~10 s) and report through
 //     *d_err instead of hanging the device;
 //   * hcspmm_halo_pull: operand row i (owner s = segment of i, row src_row[i] there) is copied with
 //     128-bit loads from peer_x[s]; eight rows in flight per warp cover the NVLink latency.
@@ -33,7 +33,7 @@ __global__ void peer_barrier_kernel(int *const *flag_ptrs, int rank, int world, 
   do {
     asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(local) : "memory");
     if (v - epoch >= 0) break;
-    if (clock64() - t0 > 4000000000LL) {   // ~2 s at 2 GHz: a peer never arrived
+    if (clock64() - t0 > 20000000000LL) {   // ~10 s at 2 GHz: a peer never arrived
       if (err) atomicExch(err, 1);
       break;
     }

@@ -211,6 +211,14 @@ class ShardedGraph:
             return 0
         return self.halo["rows"] - self.n_local if self.halo is not None else (self.world - 1) * self.max_rows
 
+    def check(self):
+        """Raise if a peer barrier ever timed out (a rank did not reach an exchange): results would be stale."""
+        if self.peer is not None:                                # collective: every rank raises, or none does
+            flag = self.peer.err.clone()
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
+            if int(flag.item()) != 0:
+                raise RuntimeError("peer barrier timed out on some rank: a rank did not reach an exchange")
+
     def close(self):
         if self.peer is not None:
             self._bufs.clear()

@@ -201,7 +201,7 @@ int hcspmm_loa_reorder(const int32_t *d_rowptr, const int32_t *d_colidx, const i
  *   hcspmm_peer_close / hcspmm_peer_free
  *   hcspmm_peer_barrier  stream-ordered barrier across the ranks: d_flag_ptrs[s] is rank s's int32[world]
  *                        flag array (peer-mapped); epoch must increase by one per call on every rank.
- *                        A peer that does not arrive within ~2 s sets *d_err = 1 instead of hanging.
+ *                        A peer that does not arrive within ~10 s sets *d_err = 1 instead of hanging.
  *   hcspmm_halo_pull     d_dst[i, col0 .. col0+width) = d_peer_x[s][d_src_row[i], col0 .. col0+width) for the
  *                        operand rows i in [d_seg[s], d_seg[s+1]) of every owner s whose bit is set in
  *                        owner_mask (the caller leaves its own bit clear: its rows are written in place).
