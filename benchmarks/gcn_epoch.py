@@ -86,6 +86,7 @@ def main():
             times.append(float(t))
             losses.append(float(l))
     times.sort()
+    g.check()
 
     # where an epoch goes: exchange and local SpMM of every aggregation width, timed on their own (max over ranks)
     def tm(fn, k=5):
