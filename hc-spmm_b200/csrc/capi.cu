@@ -17,8 +17,37 @@ void set_error(const char *fmt, ...) {
 }
 
 Tuning &tuning() {
-  static Tuning t = {1024, 0, 1, 1, 0, 0, 1, 0, 1, 1, 1, 0, 0, 64};
+  static Tuning t = {1024, 0, 1, 1, 0, 0, 1, 2, 1, 1, 1, 0, 0, 64, 1, 0, 2048};
   return t;
+}
+
+cudaError_t scratch_alloc(void **ptr, size_t bytes, cudaStream_t stream) {
+  static cudaMemPool_t pools[64] = {nullptr};
+  static int keep_mb[64] = {0};
+  int dev = 0;
+  cudaError_t err = cudaGetDevice(&dev);
+  if (err != cudaSuccess) return err;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (!pools[dev]) {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    err = cudaMemPoolCreate(&pools[dev], &props);
+    if (err != cudaSuccess) { pools[dev] = nullptr; return err; }
+    keep_mb[dev] = -1;
+  }
+  if (keep_mb[dev] != tuning().pool_keep_mb) {
+    keep_mb[dev] = tuning().pool_keep_mb;
+    unsigned long long keep = (unsigned long long)(keep_mb[dev] > 0 ? keep_mb[dev] : 0) << 20;
+    cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  return cudaMallocFromPoolAsync(ptr, bytes ? bytes : 1, pools[dev], stream);
+}
+
+void scratch_free(void *ptr, cudaStream_t stream) {
+  if (ptr) cudaFreeAsync(ptr, stream);
 }
 
 size_t preprocess_workspace_bytes(int32_t n_rows, int64_t nnz);
@@ -26,14 +55,20 @@ int launch_preprocess(const int32_t *, const int32_t *, int32_t, int64_t, int32_
                       int32_t *, int32_t *, int32_t *, void *, size_t, cudaStream_t);
 int launch_spmm(const float *, int64_t, int32_t, const int32_t *, const int32_t *, const int32_t *,
                 const int32_t *, const int32_t *, const int32_t *, int32_t, int64_t, int32_t, int,
-                int, float *, int64_t, cudaStream_t);
+                int, float *, int64_t, const hcspmm_aux_t *, cudaStream_t);
+int launch_merge_path_splits(const int32_t *, int32_t, int64_t, int32_t, int32_t *, cudaStream_t);
+size_t balanced_workspace_bytes(int32_t, int64_t, int32_t);
 int launch_gemm_tf32(const float *, int64_t, const float *, int64_t, int32_t, int32_t, int32_t,
                      float *, int64_t, cudaStream_t);
 
 bool umma_gemm_supported(const float *, int64_t, const float *, int64_t, int32_t, int32_t);
+bool update_gemm_tma_supported(const float *, int64_t, const float *, int64_t, const float *, int64_t, int32_t, int32_t,
+                               int32_t);
+size_t update_gemm_scratch_floats(int32_t k, int32_t n);
+int launch_update_gemm_tma(const float *, int64_t, const float *, int64_t, int32_t, int32_t, int32_t, float *, int64_t,
+                           float *, int *, cudaStream_t);
 int launch_umma_gemm(const float *, int64_t, const float *, int64_t, int32_t, int32_t, int32_t, float *, int64_t,
                      int *, cudaStream_t);
-void keep_mempool_blocks();
 size_t dense_plan_workspace_bytes(int32_t n_rows, int64_t nnz);
 int dense_plan_count(const int32_t *, const int32_t *, const int32_t *, int32_t, int64_t, int, void *, size_t, int32_t *,
                      cudaStream_t);
@@ -92,6 +127,9 @@ int hcspmm_set_tuning(const char *key, int value) {
   else if (key && !strcmp(key, "chunk")) slot = &tuning().chunk;
   else if (key && !strcmp(key, "warp_split")) slot = &tuning().warp_split;
   else if (key && !strcmp(key, "pull_ctas")) slot = &tuning().pull_ctas;
+  else if (key && !strcmp(key, "gemm_round")) slot = &tuning().gemm_round;
+  else if (key && !strcmp(key, "gemm_stages")) slot = &tuning().gemm_stages;
+  else if (key && !strcmp(key, "pool_keep_mb")) slot = &tuning().pool_keep_mb;
   if (!slot) return -1;
   int old = *slot;
   *slot = value;
@@ -118,11 +156,25 @@ int hcspmm_spmm(const float *d_x, int64_t ldx, int32_t x_rows, const int32_t *d_
                 int precision, int accumulate, float *d_y, int64_t ldy, void *stream) {
   return launch_spmm(d_x, ldx, x_rows, d_rowptr, d_colidx, d_block_partition, d_edge_to_column,
                      d_edge_to_row, d_hybrid_type, n_rows, nnz, dim, precision, accumulate, d_y,
-                     ldy, (cudaStream_t)stream);
+                     ldy, nullptr, (cudaStream_t)stream);
+}
+
+size_t hcspmm_merge_path_count(int32_t n_rows, int64_t nnz, int32_t chunk) {
+  if (chunk <= 0 || n_rows < 0 || nnz < 0) return 0;
+  return (size_t)(((long long)n_rows + nnz + chunk - 1) / chunk) + 1;
+}
+
+int hcspmm_merge_path_splits(const int32_t *d_rowptr, int32_t n_rows, int64_t nnz, int32_t chunk, int32_t *d_splits,
+                             void *stream) {
+  return launch_merge_path_splits(d_rowptr, n_rows, nnz, chunk, d_splits, (cudaStream_t)stream);
+}
+
+size_t hcspmm_spmm_workspace_bytes(int32_t n_rows, int64_t nnz, int32_t dim) {
+  return balanced_workspace_bytes(n_rows, nnz, dim);
 }
 
 static int *umma_error_flag() {
-  static thread_local int *flag[16] = {nullptr};
+  static int *flag[16] = {nullptr};   // per device, shared by all host threads (autograd worker included)
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 16) return nullptr;
@@ -135,8 +187,19 @@ static int *umma_error_flag() {
 
 int hcspmm_gemm_tf32(const float *d_a, int64_t lda, const float *d_b, int64_t ldb, int32_t m,
                      int32_t k, int32_t n, float *d_out, int64_t ldo, void *stream) {
-  if (tuning().umma_gemm && d_a && d_b && d_out && m > 0 && n > 0 && lda >= k && ldb >= n && ldo >= n &&
-      umma_gemm_supported(d_a, lda, d_b, ldb, k, n))
+  if (!d_a || !d_b || !d_out) { set_error("gemm_tf32: null pointer argument"); return HCSPMM_E_INVALID; }
+  if (m <= 0 || n <= 0) return 0;
+  // 2 (default): TMA + tcgen05 persistent kernel; 1: register-staged tcgen05 kernel; 0: mma.sync kernel
+  if (tuning().umma_gemm >= 2 && lda >= k && ldb >= n && ldo >= n &&
+      update_gemm_tma_supported(d_a, lda, d_b, ldb, d_out, ldo, m, k, n)) {
+    float *wt = nullptr;
+    cudaError_t e = scratch_alloc((void **)&wt, sizeof(float) * update_gemm_scratch_floats(k, n), (cudaStream_t)stream);
+    if (e != cudaSuccess) { set_error("gemm_tf32: scratch: %s", cudaGetErrorString(e)); return (int)e; }
+    const int rc = launch_update_gemm_tma(d_a, lda, d_b, ldb, m, k, n, d_out, ldo, wt, umma_error_flag(), (cudaStream_t)stream);
+    scratch_free(wt, (cudaStream_t)stream);
+    return rc;
+  }
+  if (tuning().umma_gemm == 1 && lda >= k && ldb >= n && ldo >= n && umma_gemm_supported(d_a, lda, d_b, ldb, k, n))
     return launch_umma_gemm(d_a, lda, d_b, ldb, m, k, n, d_out, ldo, umma_error_flag(), (cudaStream_t)stream);
   return launch_gemm_tf32(d_a, lda, d_b, ldb, m, k, n, d_out, ldo, (cudaStream_t)stream);
 }
@@ -163,35 +226,53 @@ int hcspmm_dense_plan_fill(const int32_t *d_colidx, const int32_t *d_edge_to_row
                          (cudaStream_t)stream);
 }
 
-int hcspmm_spmm_plan(const float *d_x, int64_t ldx, int32_t x_rows, const int32_t *d_rowptr,
-                     const int32_t *d_colidx, const int32_t *d_block_partition,
-                     const int32_t *d_edge_to_column, const int32_t *d_edge_to_row,
-                     const int32_t *d_hybrid_type, int32_t n_rows, int64_t nnz, int32_t dim,
-                     int precision, int accumulate, float *d_y, int64_t ldy, const int32_t *d_plan,
-                     int32_t n_dense, int64_t total_cols, void *stream) {
+int hcspmm_spmm_aux(const float *d_x, int64_t ldx, int32_t x_rows, const int32_t *d_rowptr,
+                    const int32_t *d_colidx, const int32_t *d_block_partition,
+                    const int32_t *d_edge_to_column, const int32_t *d_edge_to_row,
+                    const int32_t *d_hybrid_type, int32_t n_rows, int64_t nnz, int32_t dim,
+                    int precision, int accumulate, float *d_y, int64_t ldy, const hcspmm_aux_t *aux, void *stream) {
+  const int32_t *d_plan = aux ? aux->d_plan : nullptr;
+  const int32_t n_dense = aux ? aux->n_dense : 0;
+  const int64_t total_cols = aux ? aux->total_cols : 0;
   // the tcgen05 kernel holds a [128 x <=256] accumulator in TMEM: wider operands go in column blocks of 256
   const int32_t dblock = dim > 256 ? 256 : dim;
   const bool dense = d_plan && n_dense > 0 && tuning().umma && precision == HCSPMM_PRECISION_TF32 && d_x && d_y &&
                      (ldx & 3) == 0 && (dim % 16) == 0 && dense_supported(d_x, d_y, ldy, dblock);
   if (!dense)
     return launch_spmm(d_x, ldx, x_rows, d_rowptr, d_colidx, d_block_partition, d_edge_to_column, d_edge_to_row,
-                       d_hybrid_type, n_rows, nnz, dim, precision, accumulate, d_y, ldy, (cudaStream_t)stream);
+                       d_hybrid_type, n_rows, nnz, dim, precision, accumulate, d_y, ldy, aux, (cudaStream_t)stream);
   float *xr = nullptr;
-  keep_mempool_blocks();
-  cudaError_t err = cudaMallocAsync(&xr, sizeof(float) * (size_t)x_rows * dblock, (cudaStream_t)stream);
-  if (err != cudaSuccess) { set_error("spmm_plan: cudaMallocAsync: %s", cudaGetErrorString(err)); return (int)err; }
+  cudaError_t err = scratch_alloc((void **)&xr, sizeof(float) * (size_t)x_rows * dblock, (cudaStream_t)stream);
+  if (err != cudaSuccess) { set_error("spmm_plan: scratch: %s", cudaGetErrorString(err)); return (int)err; }
   int rc = 0;
   for (int32_t c0 = 0; c0 < dim && rc == 0; c0 += dblock) {
     const int32_t w = dim - c0 < dblock ? dim - c0 : dblock;
     rc = launch_spmm_dense(d_x + c0, ldx, x_rows, n_rows, w, d_plan, n_dense, total_cols, accumulate, d_y + c0, ldy, xr,
                            umma_error_flag(), (cudaStream_t)stream);
   }
-  if (rc == 0)
+  scratch_free(xr, (cudaStream_t)stream);
+  if (rc == 0) {
+    hcspmm_aux_t rest = *aux;
+    rest.n_tc_windows = -1;   // the plan's labels differ from the caller's count
     rc = launch_spmm(d_x, ldx, x_rows, d_rowptr, d_colidx, d_block_partition, d_edge_to_column, d_edge_to_row,
                      dense_plan_labels(d_plan, n_rows, n_dense, total_cols), n_rows, nnz, dim, precision, accumulate,
-                     d_y, ldy, (cudaStream_t)stream);
-  cudaFreeAsync(xr, (cudaStream_t)stream);
+                     d_y, ldy, &rest, (cudaStream_t)stream);
+  }
   return rc;
+}
+
+int hcspmm_spmm_plan(const float *d_x, int64_t ldx, int32_t x_rows, const int32_t *d_rowptr,
+                     const int32_t *d_colidx, const int32_t *d_block_partition,
+                     const int32_t *d_edge_to_column, const int32_t *d_edge_to_row,
+                     const int32_t *d_hybrid_type, int32_t n_rows, int64_t nnz, int32_t dim,
+                     int precision, int accumulate, float *d_y, int64_t ldy, const int32_t *d_plan,
+                     int32_t n_dense, int64_t total_cols, void *stream) {
+  hcspmm_aux_t aux;
+  memset(&aux, 0, sizeof(aux));
+  aux.n_tc_windows = -1;
+  aux.d_plan = d_plan; aux.n_dense = n_dense; aux.total_cols = total_cols;
+  return hcspmm_spmm_aux(d_x, ldx, x_rows, d_rowptr, d_colidx, d_block_partition, d_edge_to_column, d_edge_to_row,
+                         d_hybrid_type, n_rows, nnz, dim, precision, accumulate, d_y, ldy, &aux, stream);
 }
 
 int hcspmm_debug_umma_error(void) {
@@ -215,7 +296,7 @@ int hcspmm_spmm_gemm(const float *d_x, int64_t ldx, int32_t x_rows, const int32_
   }
   int rc = launch_spmm(d_x, ldx, x_rows, d_rowptr, d_colidx, d_block_partition, d_edge_to_column,
                        d_edge_to_row, d_hybrid_type, n_rows, nnz, dim, precision, 0, d_z, ldz,
-                       (cudaStream_t)stream);
+                       nullptr, (cudaStream_t)stream);
   if (rc) return rc;
   return hcspmm_gemm_tf32(d_z, ldz, d_w, ldw, n_rows, dim, hidden, d_out, ldo, stream);
 }
@@ -306,7 +387,7 @@ int hcspmm_graph_spmm_host(hcspmm_graph_t *g, const float *h_x, int32_t dim, int
   CUDA_TRY(cudaMemcpyAsync(g->x, h_x, sizeof(float) * (size_t)g->x_rows * dim,
                            cudaMemcpyHostToDevice, g->stream));
   int rc = launch_spmm(g->x, dim, g->x_rows, g->rowptr, g->colidx, g->bp, g->etc, g->etr, g->ht,
-                       g->n_rows, g->nnz, dim, precision, 0, g->y, dim, g->stream);
+                       g->n_rows, g->nnz, dim, precision, 0, g->y, dim, nullptr, g->stream);
   if (rc) return rc;
   CUDA_TRY(cudaMemcpyAsync(h_y, g->y, sizeof(float) * (size_t)g->n_rows * dim,
                            cudaMemcpyDeviceToHost, g->stream));

@@ -30,8 +30,17 @@ struct Tuning {
   int chunk;      // rows + stored entries per item of the balanced kernel (0 = ~4 MB of gathered rows, 4096..8192)
   int pull_ctas;  // grid cap of the halo-pull kernel (0 = 148 * 8)
   int warp_split; // items whose mean row length is >= this give every warp an equal run of entries (0 = never)
+  int gemm_round;  // TMA Update GEMM: 1 = rounder warps cvt.rna the Z boxes in shared memory, 0 = TF32-typed tensor map
+  int gemm_stages; // TMA Update GEMM: cap on the shared-memory ring depth (0 = as many as fit)
+  int pool_keep_mb; // scratch pool: megabytes of freed blocks kept across synchronisations
 };
 Tuning &tuning();
+
+// Stream-ordered scratch from the library's PRIVATE memory pool (one per device): freed blocks up to
+// "pool_keep_mb" stay cached across synchronisations (a fresh mapping per call costs more than the
+// kernels it serves); the device's default pool and PyTorch's caching allocator are left alone.
+cudaError_t scratch_alloc(void **ptr, size_t bytes, cudaStream_t stream);
+void scratch_free(void *ptr, cudaStream_t stream);
 
 // ---- small PTX wrappers -------------------------------------------------------------
 __device__ __forceinline__ float4 ldg_f4(const float *p) {

@@ -64,7 +64,10 @@ struct BalParams {
   float *partial;    // [n_items][2][dim] FP32 partial sums of rows that straddle item boundaries
   int *split_row;    // [n_items][2]: row whose sum ENDS in this item but began earlier (slot 0) /
                      //               row whose sum continues in the next item (slot 1); -1 = none
-  const int *splits; // [n_items + 1]: rows consumed before diagonal k * chunk (merge_path_splits_kernel)
+  const int *splits; // rows consumed before diagonal i * (chunk / split_stride), i = 0 .. split_max
+                     // (merge_path_splits_kernel; precomputed once per graph at a base chunk when the caller
+                     // passes hcspmm_aux_t.d_splits -- item k then reads entries k * split_stride, clamped)
+  int split_stride, split_max;
   int low_degree;    // mean row length < 64: launch the three-CTAs-per-SM build
   int warp_split;    // > 0: items with a mean row length >= warp_split give every warp an equal run of entries;
                      // other items (and 0) use the warp-per-row / CTA-per-long-row phases
@@ -631,7 +634,8 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) spmm_balanced_kernel(const 
   // the item's two diagonals: rows consumed (precomputed) and entries consumed
   const long long total = (long long)p.n_rows + bp.nnz;
   const long long d0 = min(total, (long long)k * bp.chunk), d1 = min(total, (long long)(k + 1) * bp.chunk);
-  const int x0 = __ldg(bp.splits + k), x1 = __ldg(bp.splits + k + 1);
+  const int x0 = __ldg(bp.splits + min(k * bp.split_stride, bp.split_max));
+  const int x1 = __ldg(bp.splits + min((k + 1) * bp.split_stride, bp.split_max));
   const int y0 = (int)(d0 - x0), y1 = (int)(d1 - x1);
   if (tid == 0) s_next = 0;
   // entries [y0, y1); rows x0 .. x1-1 end here, row x1 takes part through its entries below y1
@@ -952,21 +956,6 @@ __global__ void unpad_rows_kernel(const float *__restrict__ src, int dpad, int d
   dst[r * ldd + c] = src[r * dpad + c];
 }
 
-// Keep freed blocks in the stream-ordered pool: the default release threshold (0) hands them back to
-// the driver at every synchronisation, which makes the next cudaMallocAsync pay for a fresh mapping.
-void keep_mempool_blocks() {
-  static bool tuned[64] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || tuned[dev]) return;
-  cudaMemPool_t pool;
-  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-    unsigned long long keep = ~0ull;
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-  }
-  tuned[dev] = true;
-}
-
 // X (FP32, leading dim ldx) -> dense BF16 copy [rows, dim], round to nearest even
 __global__ void f32_to_bf16_rows_kernel(const float *__restrict__ x, long long ldx, int dim2, uint32_t *__restrict__ xb,
                                         long long total2) {
@@ -1044,16 +1033,34 @@ static bool use_balanced(int n_rows, long long nnz) {
   return b >= 2 || (b == 1 && nnz >= 8LL * n_rows);
 }
 
+// Caller-provided per-graph products (hcspmm_aux_t): precomputed merge-path split points and a workspace for the
+// partial sums, so that a step of a static graph neither recomputes the splits nor allocates.
+struct BalAux {
+  const int *splits = nullptr;   // split points at diagonals i * splits_chunk
+  int splits_chunk = 0, n_splits = 0;
+  void *ws = nullptr;
+  size_t ws_bytes = 0;
+};
+
+static int default_chunk(int slab, bool b16) {
+  // item size: about 4 MB of gathered rows -- 4096 steps for rows of >= 1 KB, 8192 below (measured: Reddit
+  // shape dim 256 FP32 best at 4096, dim 64 / BF16 / products dim 128 at 8192)
+  const long long row_bytes = (long long)slab * (b16 ? 2 : 4);
+  return row_bytes >= 1024 ? 4096 : 8192;
+}
+
+size_t balanced_workspace_bytes(int32_t n_rows, int64_t nnz, int32_t dim) {
+  const long long n_items = ((long long)n_rows + nnz + 4095) / 4096 + 1;   // the smallest default item size
+  return sizeof(float) * 2 * (size_t)n_items * (size_t)dim + sizeof(int) * (3 * (size_t)n_items + 2) + 256;
+}
+
 // CUDA-core windows of p (all of them when p.ht == nullptr) on the work-balanced kernel.
-static cudaError_t run_balanced(const SpmmParams &p, long long nnz, bool v8, bool b16, cudaStream_t stream) {
+static cudaError_t run_balanced(const SpmmParams &p, long long nnz, bool v8, bool b16, const BalAux &aux,
+                                cudaStream_t stream) {
   BalParams bp;
   bp.s = p;
   bp.nnz = nnz;
-  // item size: about 4 MB of gathered rows, between 4096 and 8192 steps (measured: Reddit shape dim 256
-  // FP32 best at 4096, dim 64 / BF16 / products dim 128 at 8192)
-  const long long row_bytes = (long long)p.slab * (b16 ? 2 : 4);
-  int chunk = tuning().chunk > 0 ? tuning().chunk : (int)((4 << 20) / (row_bytes > 0 ? row_bytes : 4));
-  if (tuning().chunk <= 0) chunk = chunk < 4096 ? 4096 : (chunk > 8192 ? 8192 : chunk / 1024 * 1024);
+  int chunk = tuning().chunk > 0 ? tuning().chunk : default_chunk(p.slab, b16);
   if (chunk < 64) chunk = 64;
   if (chunk > 16384) chunk = 16384;
   const long long total = (long long)p.n_rows + nnz;
@@ -1061,19 +1068,32 @@ static cudaError_t run_balanced(const SpmmParams &p, long long nnz, bool v8, boo
   if (n_items > 0x7fffffffLL / 2) return cudaErrorInvalidValue;
   bp.chunk = chunk;
   bp.n_items = (int)n_items;
-  keep_mempool_blocks();
+  const bool have_splits = aux.splits != nullptr && aux.splits_chunk > 0 && chunk % aux.splits_chunk == 0 &&
+                           (long long)aux.n_splits == (total + aux.splits_chunk - 1) / aux.splits_chunk;
   void *ws = nullptr;
   const size_t part_bytes = sizeof(float) * 2 * (size_t)n_items * p.dim;
-  cudaError_t err = cudaMallocAsync(&ws, part_bytes + sizeof(int) * (3 * (size_t)n_items + 1), stream);
+  const size_t need = part_bytes + sizeof(int) * (2 * (size_t)n_items + (have_splits ? 0 : (size_t)n_items + 1));
+  const bool own_ws = !(aux.ws != nullptr && aux.ws_bytes >= need && (reinterpret_cast<uintptr_t>(aux.ws) & 15) == 0);
+  cudaError_t err = cudaSuccess;
+  if (own_ws) err = scratch_alloc(&ws, need, stream);
+  else ws = aux.ws;
   if (err != cudaSuccess) return err;
   bp.partial = reinterpret_cast<float *>(ws);
   bp.split_row = reinterpret_cast<int *>(reinterpret_cast<char *>(ws) + part_bytes);
-  int *splits = bp.split_row + 2 * (size_t)n_items;
-  bp.splits = splits;
+  if (have_splits) {
+    bp.splits = aux.splits;
+    bp.split_stride = chunk / aux.splits_chunk;
+    bp.split_max = aux.n_splits;
+  } else {
+    int *splits = bp.split_row + 2 * (size_t)n_items;
+    bp.splits = splits;
+    bp.split_stride = 1;
+    bp.split_max = (int)n_items;
+    merge_path_splits_kernel<<<(unsigned)((n_items + 1 + 127) / 128), 128, 0, stream>>>(p.rowptr, p.n_rows, nnz, chunk,
+                                                                                      (int)n_items, splits);
+  }
   bp.warp_split = tuning().warp_split;   // mean row length from which an item is cut by warp runs
   bp.low_degree = nnz < 64LL * p.n_rows;
-  merge_path_splits_kernel<<<(unsigned)((n_items + 1 + 127) / 128), 128, 0, stream>>>(p.rowptr, p.n_rows, nnz, chunk,
-                                                                                    (int)n_items, splits);
   const int slab = p.slab;
   dim3 grid((unsigned)n_items, (p.dim + slab - 1) / slab, 1);
   const size_t smem = (size_t)2 * CTA_WARPS * slab * sizeof(float) + (size_t)(chunk + 4) / 2 * sizeof(int);
@@ -1101,14 +1121,33 @@ static cudaError_t run_balanced(const SpmmParams &p, long long nnz, bool v8, boo
     spmm_balanced_fixup_kernel<<<fgrid, 64, 0, stream>>>(bp);
     err = cudaGetLastError();
   }
-  cudaFreeAsync(ws, stream);
+  if (own_ws) scratch_free(ws, stream);
   return err;
+}
+
+int launch_merge_path_splits(const int32_t *rowptr, int32_t n_rows, int64_t nnz, int32_t chunk, int32_t *splits,
+                             cudaStream_t stream) {
+  if (!rowptr || !splits || n_rows < 0 || nnz < 0 || chunk < 64) { set_error("merge_path_splits: bad argument"); return HCSPMM_E_INVALID; }
+  const long long total = (long long)n_rows + nnz;
+  const long long n_items = (total + chunk - 1) / chunk;
+  merge_path_splits_kernel<<<(unsigned)((n_items + 1 + 127) / 128), 128, 0, stream>>>(rowptr, n_rows, nnz, chunk, (int)n_items,
+                                                                                    splits);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) { set_error("merge_path_splits: %s", cudaGetErrorString(err)); return (int)err; }
+  return 0;
 }
 
 int launch_spmm(const float *x, int64_t ldx, int32_t x_rows, const int32_t *rowptr,
                 const int32_t *colidx, const int32_t *bp, const int32_t *etc, const int32_t *etr,
                 const int32_t *ht, int32_t n_rows, int64_t nnz, int32_t dim, int precision,
-                int accumulate, float *y, int64_t ldy, cudaStream_t stream) {
+                int accumulate, float *y, int64_t ldy, const hcspmm_aux_t *aux_in, cudaStream_t stream) {
+  BalAux aux;
+  int n_tc_windows = -1;   // windows labelled 1 (mma.sync path); -1 = unknown
+  if (aux_in) {
+    aux.splits = aux_in->d_splits; aux.splits_chunk = aux_in->splits_chunk; aux.n_splits = aux_in->n_splits;
+    aux.ws = aux_in->d_workspace; aux.ws_bytes = aux_in->workspace_bytes;
+    n_tc_windows = aux_in->n_tc_windows;
+  }
   if (n_rows < 0 || dim < 0 || nnz < 0 || x_rows < 0) {
     set_error("spmm: negative size");
     return HCSPMM_E_INVALID;
@@ -1155,8 +1194,7 @@ int launch_spmm(const float *x, int64_t ldx, int32_t x_rows, const int32_t *rowp
   cudaError_t err;
   if (precision == HCSPMM_PRECISION_BF16) {
     uint32_t *xb = nullptr;
-    keep_mempool_blocks();
-    err = cudaMallocAsync(&xb, sizeof(uint16_t) * (size_t)x_rows * dim, stream);
+    err = scratch_alloc((void **)&xb, sizeof(uint16_t) * (size_t)x_rows * dim, stream);
     if (err != cudaSuccess) { set_error("spmm bf16: cudaMallocAsync: %s", cudaGetErrorString(err)); return (int)err; }
     const long long total2 = (long long)x_rows * (dim / 2);
     f32_to_bf16_rows_kernel<<<1184, 256, 0, stream>>>(x, ldx, dim / 2, xb, total2);
@@ -1174,13 +1212,13 @@ int launch_spmm(const float *x, int64_t ldx, int32_t x_rows, const int32_t *rowp
     p.n_windows = n_windows;
     dim3 grid((n_windows + wpc - 1) / wpc, (dim + slab - 1) / slab, 1);
     const size_t smem = hybrid_smem_bytes(slab, false);
-    if (use_balanced(n_rows, nnz)) err = run_balanced(p, nnz, true, true, stream);
+    if (use_balanced(n_rows, nnz)) err = run_balanced(p, nnz, true, true, aux, stream);
     else if (slab <= 32) err = launch_hybrid_bf16<4, 1>(p, grid, smem, stream);
     else if (slab <= 64) err = launch_hybrid_bf16<8, 1>(p, grid, smem, stream);
     else if (slab <= 128) err = launch_hybrid_bf16<16, 1>(p, grid, smem, stream);
     else if (slab <= 256) err = launch_hybrid_bf16<32, 1>(p, grid, smem, stream);
     else err = launch_hybrid_bf16<32, 2>(p, grid, smem, stream);
-    cudaFreeAsync(xb, stream);
+    scratch_free(xb, stream);
     if (err != cudaSuccess) { set_error("spmm bf16 launch: %s", cudaGetErrorString(err)); return (int)err; }
     return 0;
   }
@@ -1190,11 +1228,10 @@ int launch_spmm(const float *x, int64_t ldx, int32_t x_rows, const int32_t *rowp
     // Two streaming copies cost 2 * (x_rows + n_rows) * dim * 4 bytes -- small next to the gather.
     const int dpad = (dim + 7) / 8 * 8;
     float *xp = nullptr, *yp = nullptr;
-    keep_mempool_blocks();
-    err = cudaMallocAsync(&xp, sizeof(float) * (size_t)x_rows * dpad, stream);
-    if (err == cudaSuccess) err = cudaMallocAsync(&yp, sizeof(float) * (size_t)n_rows * dpad, stream);
+      err = scratch_alloc((void **)&xp, sizeof(float) * (size_t)x_rows * dpad, stream);
+    if (err == cudaSuccess) err = scratch_alloc((void **)&yp, sizeof(float) * (size_t)n_rows * dpad, stream);
     if (err != cudaSuccess) {
-      if (xp) cudaFreeAsync(xp, stream);
+      if (xp) scratch_free(xp, stream);
       set_error("spmm: cudaMallocAsync: %s", cudaGetErrorString(err));
       return (int)err;
     }
@@ -1202,15 +1239,15 @@ int launch_spmm(const float *x, int64_t ldx, int32_t x_rows, const int32_t *rowp
     pad_rows_kernel<<<(unsigned)((nx + 255) / 256), 256, 0, stream>>>(x, ldx, dim, xp, dpad, nx);
     if (accumulate) pad_rows_kernel<<<(unsigned)((ny + 255) / 256), 256, 0, stream>>>(y, ldy, dim, yp, dpad, ny);
     int rc = launch_spmm(xp, dpad, x_rows, rowptr, colidx, bp, etc, etr, ht, n_rows, nnz, dpad, precision,
-                         accumulate, yp, dpad, stream);
+                         accumulate, yp, dpad, aux_in, stream);
     if (rc == 0) {
       unpad_rows_kernel<<<(unsigned)(((long long)n_rows * dim + 255) / 256), 256, 0, stream>>>(
           yp, dpad, dim, y, ldy, (long long)n_rows * dim);
       err = cudaGetLastError();
       if (err != cudaSuccess) { set_error("spmm pad path: %s", cudaGetErrorString(err)); rc = (int)err; }
     }
-    cudaFreeAsync(xp, stream);
-    cudaFreeAsync(yp, stream);
+    scratch_free(xp, stream);
+    scratch_free(yp, stream);
     return rc;
   }
   if (!vec) {
@@ -1243,7 +1280,7 @@ int launch_spmm(const float *x, int64_t ldx, int32_t x_rows, const int32_t *rowp
     if (use_balanced(n_rows, nnz)) {
       // tensor-core windows (if any are labelled) on the per-window kernel, everything else balanced
       err = cudaSuccess;
-      if (labels) {
+      if (labels && n_tc_windows != 0) {   // no window labelled 1 (e.g. the shipped selector): nothing to launch
         SpmmParams pt = p;
         pt.cuda_elsewhere = 1;
         if (v8) {
@@ -1260,7 +1297,7 @@ int launch_spmm(const float *x, int64_t ldx, int32_t x_rows, const int32_t *rowp
           else err = launch_hybrid<32, 4, 4>(pt, grid, smem, stream);
         }
       }
-      if (err == cudaSuccess) err = run_balanced(p, nnz, v8, false, stream);
+      if (err == cudaSuccess) err = run_balanced(p, nnz, v8, false, aux, stream);
     } else if (v8) {
       if (slab <= 32) err = launch_hybrid<4, 1, 8>(p, grid, smem, stream);
       else if (slab <= 64) err = launch_hybrid<8, 1, 8>(p, grid, smem, stream);

@@ -21,7 +21,7 @@ LIB_DIR = os.path.join(PKG_ROOT, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libhcspmm.so")
 EXT_PATH = os.path.join(PKG_ROOT, "HCSPMM.so")
 
-CU_SOURCES = ["capi.cu", "preprocess.cu", "spmm.cu", "gemm.cu", "loa.cu", "umma_gemm.cu", "dense.cu", "peer.cu"]
+CU_SOURCES = ["capi.cu", "preprocess.cu", "spmm.cu", "gemm.cu", "loa.cu", "umma_gemm.cu", "update_gemm.cu", "dense.cu", "peer.cu", "microbench.cu"]
 HEADERS = ["common.cuh", "umma.cuh", os.path.join(REPO_ROOT, "include", "hcspmm.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -42,16 +42,33 @@ def _nvcc() -> str:
 
 
 def build_lib(force: bool = False, verbose: bool = False) -> str:
+    """One nvcc process per translation unit (objects under lib/obj/, rebuilt only when the source or a
+    header is newer), run in parallel, then one link."""
+    from concurrent.futures import ThreadPoolExecutor
     srcs = [os.path.join(CSRC, s) for s in CU_SOURCES]
-    deps = srcs + [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HEADERS]
-    if not force and _newer(LIB_PATH, deps):
+    hdrs = [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HEADERS]
+    if not force and _newer(LIB_PATH, srcs + hdrs):
         return LIB_PATH
-    os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc(), *NVCC_FLAGS, "-ccbin", "g++", "-o", LIB_PATH, *srcs]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd))
-    subprocess.check_call(cmd)
+    obj_dir = os.path.join(LIB_DIR, "obj")
+    os.makedirs(obj_dir, exist_ok=True)
+    nvcc = _nvcc()
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(src):
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
+        if not force and _newer(obj, [src] + hdrs):
+            return obj
+        cmd = [nvcc, *flags, "-ccbin", "g++", "-c", "-o", obj, src]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+            print(" ".join(cmd))
+        subprocess.check_call(cmd)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 4)) as ex:
+        objs = list(ex.map(compile_one, srcs))
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "g++",
+                           "-o", LIB_PATH, *objs])
     return LIB_PATH
 
 

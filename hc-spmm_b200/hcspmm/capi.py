@@ -24,7 +24,7 @@ EXPORTS = [
     "hcspmm_dense_plan_fill", "hcspmm_spmm_plan", "hcspmm_debug_umma_error", "hcspmm_loa_workspace_bytes", "hcspmm_loa_reorder", "hcspmm_graph_create", "hcspmm_graph_spmm_host",
     "hcspmm_graph_get_preprocess", "hcspmm_graph_destroy",
     "hcspmm_peer_alloc", "hcspmm_peer_open", "hcspmm_peer_close", "hcspmm_peer_free", "hcspmm_peer_barrier",
-    "hcspmm_halo_pull",
+    "hcspmm_halo_pull", "hcspmm_debug_l2_gather",
 ]
 
 _lib = None
@@ -76,6 +76,7 @@ def lib() -> ctypes.CDLL:
         L.hcspmm_peer_free.argtypes = [_vp]
         L.hcspmm_peer_barrier.argtypes = [_vp, _i32, _i32, _i32, _vp, _vp]
         L.hcspmm_halo_pull.argtypes = [_vp, _i64, _vp, _vp, _i32, ctypes.c_uint64, _i32, _i32, _i32, _i32, _vp, _i64, _vp]
+        L.hcspmm_debug_l2_gather.argtypes = [_vp, _i32, _i32, _i32, _i32, _vp, _vp]
         _lib = L
     return _lib
 
@@ -196,6 +197,31 @@ def gemm_tf32(a: torch.Tensor, b: torch.Tensor):
                                       b.shape[1], _ptr(out), out.stride(0), _stream(a)),
                "hcspmm_gemm_tf32")
     return out
+
+
+def l2_gather_bandwidth(device, row_floats: int = 256, megabytes: int = 32, iters: int = 512, reps: int = 5) -> float:
+    """Measured L2 -> SM gather bandwidth in GB/s (hcspmm_debug_l2_gather): random rows of an L2-resident
+    [rows, row_floats] buffer, the SpMM's 256-bit evict_last loads, best of `reps` timed launches."""
+    rows = megabytes * (1 << 20) // (row_floats * 4)
+    with torch.cuda.device(device):
+        buf = torch.zeros(rows, row_floats, device=device)
+        sink = torch.zeros(1, device=device)
+        sms = torch.cuda.get_device_properties(device).multi_processor_count
+        ctas = sms * 2 * 4
+        iters = (iters + 7) // 8 * 8
+        st = torch.cuda.current_stream(device).cuda_stream
+
+        def go():
+            _check(lib().hcspmm_debug_l2_gather(buf.data_ptr(), rows, row_floats, iters, ctas, sink.data_ptr(), st),
+                   "hcspmm_debug_l2_gather")
+        go(); go()
+        best = float("inf")
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); go(); b.record()
+            torch.cuda.synchronize(device)
+            best = min(best, a.elapsed_time(b))
+    return ctas * 8 * iters * row_floats * 4 / (best * 1e-3) / 1e9
 
 
 def csc_of(rowptr: torch.Tensor, colidx: torch.Tensor):

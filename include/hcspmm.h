@@ -78,7 +78,12 @@ const char *hcspmm_last_error(void);
  *   "pad_odd"    1 (default): large operands whose width is not a multiple of 4 (or whose rows
  *                are unaligned) run through zero-padded aligned copies; 0: scalar kernel
  *   "umma"       1: tcgen05 / TMEM dense super-window kernel (hcspmm_spmm_plan); 0: per-window paths
- *   "umma_gemm"  1: tcgen05 / TMEM Update GEMM; 0 (default): mma.sync GEMM
+ *   "umma_gemm"  Update GEMM kernel: 2 = TMA + tcgen05 persistent warp-specialised kernel, 1 = register-staged
+ *                tcgen05 kernel, 0 = mma.sync kernel (also the fallback for unaligned operands)
+ *   "gemm_round" TMA Update GEMM: 1 (default) rounder warps apply cvt.rna.tf32 to the landed Z boxes (the
+ *                reference's rounding); 0 = the tensor map's TF32 element type converts on load
+ *   "gemm_stages" cap on the TMA Update GEMM's shared-memory ring depth (0 = as many stages as fit)
+ *   "pool_keep_mb" megabytes of freed scratch the library's private stream-ordered pool keeps mapped
  *   "balance"    CUDA-core windows on the merge-path balanced kernel (equal rows + stored entries per
  *                CTA, hub rows cut into pieces that are summed in a fixed order): 1 (default) when the
  *                mean row holds >= 8 entries, 2 always, 0 never (one CTA per "wpc" 16-row windows)
@@ -170,9 +175,49 @@ int hcspmm_spmm_plan(const float *d_x, int64_t ldx, int32_t x_rows, const int32_
                      int precision, int accumulate, float *d_y, int64_t ldy, const int32_t *d_plan,
                      int32_t n_dense, int64_t total_cols, void *stream);
 
+/* ---- per-graph products of a static graph (optional) ------------------------------------------------------
+ * A GNN aggregates over the SAME graph at every layer and step, so what depends on the graph only is computed
+ * once -- by the caller's preprocess step -- and handed to every aggregation through hcspmm_aux_t:
+ *   d_splits / splits_chunk / n_splits   merge-path split points of the work-balanced kernel at diagonals
+ *                                        i * splits_chunk, i = 0 .. n_splits (n_splits = ceil((n_rows + nnz) /
+ *                                        splits_chunk); HCSPMM_SPLITS_CHUNK serves both default item sizes),
+ *                                        from hcspmm_merge_path_splits; NULL = recomputed per call
+ *   n_tc_windows                         number of windows labelled 1 (0 skips the mma.sync launch; -1 unknown)
+ *   d_plan / n_dense / total_cols        dense super-window plan (hcspmm_dense_plan_fill) or NULL
+ *   d_workspace / workspace_bytes        >= hcspmm_spmm_workspace_bytes() bytes, 16-byte aligned, for the row
+ *                                        pieces of the balanced kernel; NULL = the library's private pool
+ * hcspmm_spmm_aux(..., NULL, ...) is hcspmm_spmm.                                                              */
+#define HCSPMM_SPLITS_CHUNK 4096
+typedef struct {
+  const int32_t *d_splits;
+  int32_t splits_chunk, n_splits;
+  int32_t n_tc_windows;
+  const int32_t *d_plan;
+  int32_t n_dense;
+  int64_t total_cols;
+  void *d_workspace;
+  size_t workspace_bytes;
+} hcspmm_aux_t;
+size_t hcspmm_merge_path_count(int32_t n_rows, int64_t nnz, int32_t chunk);      /* entries of d_splits: n_splits + 1 */
+int hcspmm_merge_path_splits(const int32_t *d_rowptr, int32_t n_rows, int64_t nnz, int32_t chunk, int32_t *d_splits,
+                             void *stream);
+size_t hcspmm_spmm_workspace_bytes(int32_t n_rows, int64_t nnz, int32_t dim);
+int hcspmm_spmm_aux(const float *d_x, int64_t ldx, int32_t x_rows, const int32_t *d_rowptr,
+                    const int32_t *d_colidx, const int32_t *d_block_partition,
+                    const int32_t *d_edge_to_column, const int32_t *d_edge_to_row,
+                    const int32_t *d_hybrid_type, int32_t n_rows, int64_t nnz, int32_t dim,
+                    int precision, int accumulate, float *d_y, int64_t ldy, const hcspmm_aux_t *aux, void *stream);
+
 /* 1 if a tcgen05 kernel reported a barrier timeout since the last call (synchronises the device),
  * 0 if not, -1 on error.  Debug / test aid.                                              */
 int hcspmm_debug_umma_error(void);
+
+/* Measurement aid: the L2 -> SM gather roof.  Every warp of `ctas` CTAs (256 threads) sums `iters` pseudo-random
+ * rows of the [rows, row_floats] FP32 buffer d_buf (row_floats 256 or 512; choose rows * row_floats * 4 well below
+ * the 126 MB L2) with the SpMM's own 256-bit evict_last loads.  Bytes gathered = ctas * 8 * iters(rounded up to 8)
+ * * row_floats * 4; the caller times the launch.  bench.py reports the SpMM's `roofline` against this number.  */
+int hcspmm_debug_l2_gather(const float *d_buf, int32_t rows, int32_t row_floats, int32_t iters, int32_t ctas,
+                           float *d_sink, void *stream);
 
 /* ---- A9: LOA vertex reordering ------------------------------------------------------
  * Replaces reorder_plus_new_direct + the output loop of main, /root/reference/LOI.cpp:660-805,

@@ -324,6 +324,45 @@ def test_gemm_tcgen05(capi, m, k, n):
     assert rel_fro(got, oracle.gemm(a, b, tf32=True)) <= 1e-4
 
 
+# ---- TMA + tcgen05 persistent Update GEMM (csrc/update_gemm.cu) ---------------------------------
+@pytest.mark.parametrize("m,k,n", [(128, 32, 32), (128, 64, 256), (1000, 128, 128), (513, 100, 48), (4096, 256, 256),
+                                   (300, 36, 16), (2000, 128, 320), (77, 8, 4), (40000, 128, 128), (19000, 100, 128)])
+@pytest.mark.parametrize("rounders", [1, 0])
+def test_gemm_tma(capi, m, k, n, rounders):
+    """rounders = 1: cvt.rna in shared memory (the reference's rounding, oracle-tight); 0: the tensor map's
+    TF32 element type (hardware conversion on load, tolerance of one TF32 ulp per operand)."""
+    a, b = xmat(m, k, 1), xmat(k, n, 2)
+    old = capi.set_tuning("umma_gemm", 2)
+    old_r = capi.set_tuning("gemm_round", rounders)
+    try:
+        got = capi.gemm_tf32(dev(a), dev(b)).cpu().numpy()
+        assert capi.lib().hcspmm_debug_umma_error() == 0, "tcgen05 kernel reported a barrier timeout"
+    finally:
+        capi.set_tuning("umma_gemm", old)
+        capi.set_tuning("gemm_round", old_r)
+    assert rel_fro(got, oracle.gemm(a, b, tf32=True)) <= (1e-4 if rounders else 2e-3)
+
+
+def test_gemm_tma_strided_views(capi):
+    """Z / out as column blocks of wider matrices (lda, ldo > width) and a strided W."""
+    a_full, b_full = xmat(3000, 160, 3), xmat(128, 200, 4)
+    a, b = a_full[:, 16:144], b_full[:, 8:136]
+    d_a, d_b = dev(a_full)[:, 16:144], dev(b_full)[:, 8:136]
+    out_full = torch.zeros(3000, 256, device="cuda")
+    old = capi.set_tuning("umma_gemm", 2)
+    try:
+        with torch.cuda.device(0):
+            capi._check(capi.lib().hcspmm_gemm_tf32(d_a.data_ptr(), 160, d_b.data_ptr(), 200, 3000, 128, 128,
+                                                    out_full[:, 64:192].data_ptr(), 256,
+                                                    torch.cuda.current_stream().cuda_stream), "hcspmm_gemm_tf32")
+        torch.cuda.synchronize()
+    finally:
+        capi.set_tuning("umma_gemm", old)
+    got = out_full.cpu().numpy()
+    assert rel_fro(got[:, 64:192], oracle.gemm(np.ascontiguousarray(a), np.ascontiguousarray(b), tf32=True)) <= 1e-4
+    assert not got[:, :64].any() and not got[:, 192:].any(), "the TMA store wrote outside its column block"
+
+
 def test_spmm_odd_width_large_uses_padded_copies(capi):
     """dim = 47 on a graph large enough for the pad path (n_rows * dim >= 2^20), with a hub row."""
     from hcspmm import graphs as G
