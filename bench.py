@@ -6,9 +6,16 @@
 
 A "step" is one pass of the hot path over one batch of synthetic input: Y = A * X on the
 Reddit-shape power-law graph (232 965 vertices, ~114.6 M stored entries, dim 256, FP32).
-At N > 1 the adjacency is row-window partitioned (nnz-balanced) and every step first
-all-gathers the row-sharded X over NCCL, then runs the local SpMM -- the per-layer exchange of
-a row-partitioned GCN (strong scaling: the total work is fixed).
+At N > 1 the adjacency is row-window partitioned (nnz-balanced) and every step first exchanges
+the row-sharded X -- by default only the HALO rows a shard references, pulled over NVLink peer
+memory by our own kernels (hcspmm_peer_barrier + hcspmm_halo_pull); `--exchange gather` is the
+north star's NCCL all-gather, kept as the comparison -- then runs the local SpMM: the per-layer
+exchange of a row-partitioned GCN (strong scaling: the total work is fixed).  Every line carries a
+`parity` record: the timed path's result against FP32 torch.sparse.mm on the host and, at N > 1,
+against rows [r0, r1) of the single-GPU aggregation of the unpartitioned graph.
+`extra.sweep` (N = 1): the other widths / shapes of the metric (dim 64 / 128 / 512, the products
+and proteins shapes), each with its own roofline fraction; `extra.products` (N > 1): the
+ogbn-products-shape scaling record of SURVEY 8(e).
 
 Prints ONE JSON line (rank 0).  Keys follow the driver's contract; see DESIGN.md "Measurement".
 Nothing here reads /root/reference.  The CPU oracle / torch.sparse.mm is executed only in the
@@ -62,6 +69,7 @@ def parse():
     ap.add_argument("--tune", action="append", default=[], help="library tuning knob key=value (repeatable)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="headline only: skip extra.sweep / extra.products")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline budget per timed run")
     return ap.parse_args()
 
@@ -117,7 +125,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_spmm_baseline(rp_cpu, ci_cpu, x_cpu, seconds: float):
+def cpu_spmm_baseline(rp_cpu, ci_cpu, x_cpu, seconds: float, keep_y: bool = False):
     """torch.sparse.mm (CSR, FP32) on the host cores -- the paper's 'PyTorch CPU SpMM' baseline and the
     north star's stated reference -- on a BOUNDED sample: the first n_s rows of the same graph against
     the full X, n_s sized so one run takes about `seconds`."""
@@ -142,13 +150,17 @@ def cpu_spmm_baseline(rp_cpu, ci_cpu, x_cpu, seconds: float):
     n_s = int(torch.searchsorted(rp_cpu.to(torch.int64), torch.tensor(want_e)).clamp(16, n))
     times = []
     for _ in range(2):
-        dt, e, _ = run(n_s)
+        dt, e, y = run(n_s)
         times.append(dt)
     dt = statistics.median(times)
-    return {"value": 2.0 * e * dim / dt / 1e9, "unit": "GFLOP/s", "cores": threads, "kind": "port",
-            "sample": f"torch.sparse.mm CSR FP32 on CPU, rows [0,{n_s}) of {n} ({e} of {int(rp_cpu[-1])} "
-                      f"stored entries) x full X[{x_cpu.shape[0]},{dim}], median of 2 runs, {dt:.2f} s each",
-            "seconds": dt, "entries": e, "rows": n_s}
+    res = {"value": 2.0 * e * dim / dt / 1e9, "unit": "GFLOP/s", "cores": threads, "kind": "port",
+           "sample": f"torch.sparse.mm CSR FP32 on CPU, rows [0,{n_s}) of {n} ({e} of {int(rp_cpu[-1])} "
+                     f"stored entries) x full X[{x_cpu.shape[0]},{dim}], median of 2 runs, {dt:.2f} s each",
+           "seconds": dt, "entries": e, "rows": n_s}
+    if keep_y:          # the bench's parity leg compares the GPU result with this Y (rows [0, n_s))
+        pub = {k: v for k, v in res.items() if k not in ("seconds", "entries", "rows")}
+        return pub, y, n_s
+    return res
 
 
 def reference_kernel_arm(args):
@@ -249,14 +261,6 @@ def main():
     import HCSPMM
     from hcspmm import capi
 
-    shape = graphs.SHAPES[args.shape]
-    dim = args.dim or shape["dim"]
-    t_gen = time.perf_counter()
-    rp, ci, info = graphs.named(args.shape, device=dev, scale=args.scale)
-    torch.cuda.synchronize()
-    t_gen = time.perf_counter() - t_gen
-    n, nnz = info["n"], info["nnz"]
-
     if args.slab >= 0:
         HCSPMM.set_tuning("slab", args.slab)
     if args.long_row >= 0:
@@ -266,17 +270,95 @@ def main():
     for kv in args.tune:
         k, v = kv.split("=")
         HCSPMM.set_tuning(k, int(v))
-    HCSPMM.set_dense(bool(args.dense))
-    HCSPMM.set_classifier(args.classifier)
-    HCSPMM.set_precision(args.precision)
 
-    # row-window partition (nnz-balanced) + the exchange plan of hcspmm.dist; world == 1: the whole graph
-    from hcspmm import dist as hd
-    sg = hd.ShardedGraph(rp, ci, schedule=args.exchange, n_slabs=max(1, args.exchange_slabs), n_passes=args.exchange_passes)
+    ctx = Ctx(args, world, rank, dev)
+    # the measured L2 -> SM gather roof (hcspmm_debug_l2_gather: random 1 KB rows of an L2-resident 32 MB buffer, the
+    # SpMM's own 256-bit loads) -- the honest roof of a gather that L2 serves; HBM figures are reported beside it
+    ctx.l2_peak = capi.l2_gather_bandwidth(dev, 256, 32)
+    ctx.hbm_peak, ctx.hbm_src = measured_peak_gbs()
+
+    head = run_workload(ctx, args.shape, args.dim or graphs.SHAPES[args.shape]["dim"], args.steps, args.warmup,
+                        classifier=args.classifier, dense=args.dense, precision=args.precision, headline=True)
+    extra = {}
+    if not args.no_extra and args.shape == "reddit":
+        k, w = max(3, min(args.steps, 10)), max(3, min(args.warmup, 3))
+        if world > 1:
+            # SURVEY 8(e) / north star: scaling on the ogbn-products shape (dim 128), same exchange as the headline
+            extra["products"] = slim(run_workload(ctx, "products", 128, k, w, classifier=args.classifier, dense=False,
+                                                  precision=args.precision))
+        else:
+            sweep = []
+            for shape, dim, cls, dense in (("reddit", 64, "shipped", False), ("reddit", 128, "shipped", False),
+                                           ("reddit", 512, "shipped", False), ("products", 128, "shipped", False),
+                                           ("proteins", 256, "shipped", False), ("proteins", 256, "b200", True)):
+                sweep.append(slim(run_workload(ctx, shape, dim, k, w, classifier=cls, dense=dense, precision="tf32")))
+            extra["sweep"] = sweep
+    if rank == 0:
+        line = head
+        line["extra"] = extra
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+class Ctx:
+    def __init__(self, args, world, rank, dev):
+        self.args, self.world, self.rank, self.dev = args, world, rank, dev
+        self.l2_peak = self.hbm_peak = None
+        self.hbm_src = ""
+        self._graphs = {}
+
+    def graph(self, shape):
+        from hcspmm import graphs
+        if shape not in self._graphs:
+            self._graphs.clear()                      # one generated graph resident at a time
+            t = time.perf_counter()
+            rp, ci, info = graphs.named(shape, device=self.dev, scale=self.args.scale)
+            torch.cuda.synchronize()
+            self._graphs[shape] = (rp, ci, info, time.perf_counter() - t)
+        return self._graphs[shape]
+
+
+def slim(rec):
+    """A sub-record of the line: the numbers, without the prose."""
+    keep = ("workload", "value", "unit", "ms_per_step", "steps", "dim", "nodes", "stored_entries", "classifier", "dense_groups_tcgen05",
+            "precision", "roofline", "parity", "phases", "launches_per_step", "preprocess_ms", "step_ms")
+    out = {k: rec[k] for k in keep if k in rec}
+    cfg = rec.get("config", {})
+    for k in ("workload", "dim", "nodes", "stored_entries", "classifier", "dense_groups_tcgen05", "phases", "preprocess_ms", "exchange"):
+        if k in cfg:
+            out[k] = cfg[k]
+    return out
+
+
+def rel_fro(a, b):
+    den = float(torch.linalg.vector_norm(b.double()))
+    return float(torch.linalg.vector_norm(a.double() - b.double())) / (den if den > 0 else 1.0)
+
+
+def run_workload(ctx, shape_name, dim, steps, warmup, classifier, dense, precision, headline=False):
+    """One workload = K timed aggregations Y = A X of one synthetic shape at one width, on `world` GPUs (row-window
+    partition + exchange per step at world > 1), with its parity check and roofline."""
+    import HCSPMM
+    from hcspmm import dist as hd, graphs
+    args, world, rank, dev = ctx.args, ctx.world, ctx.rank, ctx.dev
+    if world > 1:
+        import torch.distributed as dist
+    shape = graphs.SHAPES[shape_name]
+    rp, ci, info, t_gen = ctx.graph(shape_name)
+    n, nnz = info["n"], info["nnz"]
+
+    HCSPMM.set_dense(bool(dense))               # defaults recorded per graph by the preprocess calls below
+    HCSPMM.set_classifier(classifier)
+    HCSPMM.set_precision(precision)
+    operand = "bf16" if (precision == "bf16" and world > 1) else "fp32"
+    sg = hd.ShardedGraph(rp, ci, schedule=args.exchange, n_slabs=max(1, args.exchange_slabs), n_passes=args.exchange_passes,
+                         operand=operand)
     sg.overlap_ctas = args.overlap_ctas
-    cuts, r0, r1 = sg.cuts, sg.r0, sg.r1
-    rp_l, ci_run, pre = sg.rowptr, sg.colidx, sg.pre
-    n_l, nnz_l, x_rows_run = sg.n_local, sg.nnz_local, sg.x_rows
+    r0, r1 = sg.r0, sg.r1
+    rp_l, ci_run = sg.rowptr, sg.colidx
+    n_l, nnz_l = sg.n_local, sg.nnz_local
 
     # preprocessing (reported separately, like the paper: "x one SpMM")
     torch.cuda.synchronize()
@@ -287,8 +369,9 @@ def main():
     torch.cuda.synchronize()
     prep_ms = ev0.elapsed_time(ev1)
     sg.pre = pre
-    tc_windows = int((pre[3] != 0).sum())
-    dense_groups = int(pre[4][1]) if (pre[4].device.type == "cpu" and pre[4].numel() >= 4) else 0
+    hdr = pre[4]
+    tc_windows = int(hdr[7])
+    dense_groups = int(hdr[1])
 
     g = torch.Generator(device=dev)
     g.manual_seed(1234)
@@ -297,7 +380,7 @@ def main():
     n_slabs = sg.n_slabs if (world > 1 and sg.schedule in ("slabs", "halo", "peer")) else 1
 
     def step():
-        # N > 1: exchange of the row shards of X (all-gather or halo all-to-all), then the local SpMM
+        # N > 1: exchange of the row shards of X (halo rows pulled over NVLink, or an NCCL schedule), then the local SpMM
         return sg.aggregate(x_loc if world > 1 else x_full)
 
     def barrier():
@@ -305,20 +388,20 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         y = step()
     barrier()
 
     # timed region: exactly K steps, CUDA events on the launching (current) stream
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    sampler = ClockSampler(dev.index)
+    if rank == 0 and headline:
         sampler.start()
         time.sleep(0.25)
-    kern_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kern_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     barrier()
     t0 = time.time()
     ev0.record()
-    for i in range(args.steps):
+    for i in range(steps):
         kern_ev[i][0].record()
         y = step()
         kern_ev[i][1].record()
@@ -326,13 +409,13 @@ def main():
     barrier()
     t1 = time.time()
     total_ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    clocks = sampler.stop(t0, t1) if (rank == 0 and headline) else None
     step_ms = [a.elapsed_time(b) for a, b in kern_ev]
     if world > 1:
         t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t)
-    ms_per_step = total_ms / args.steps
+    ms_per_step = total_ms / steps
     flops = 2.0 * nnz * dim
     value = flops / (ms_per_step * 1e-3) / 1e9
 
@@ -350,63 +433,105 @@ def main():
             t = torch.tensor([a.elapsed_time(b) / k], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             return float(t)
-        operand = sg.exchange(x_loc)
+        operand_t = sg.exchange(x_loc)
+        esz = 2 if operand_t.dtype == torch.bfloat16 else 4
         phases = {"exchange_only_ms": tm(lambda: sg.exchange(x_loc)),
-                  "kernel_only_ms": tm(lambda: HCSPMM.forward(operand, rp_l, ci_run, *pre)),
-                  "exchange_bytes_per_rank": int(sg.exchange_rows() * dim * 4),
+                  "kernel_only_ms": tm(lambda: sg._spmm(operand_t, rp_l, ci_run, pre)),
+                  "exchange_bytes_per_rank": int(sg.exchange_rows() * dim * esz),
                   "exchange_rows_vs_allgather": sg.exchange_rows() / max(1, (world - 1) * sg.max_rows)}
-
+        if phases["exchange_only_ms"] > 0:
+            phases["exchange_gbs_per_rank"] = phases["exchange_bytes_per_rank"] / phases["exchange_only_ms"] / 1e6
     sg.check()          # a peer barrier that timed out would have left stale rows in the operand
-    # quick full-size sanity inside the bench (not timed): X = 1 gives the row degrees exactly
-    ones = torch.ones(x_rows_run, 8, device=dev)
-    deg = HCSPMM.forward(ones, rp_l, ci_run, *pre)[0][:, 0]
-    want = (rp_l[1:] - rp_l[:-1]).float()
-    assert torch.equal(deg, want) or float((deg - want).abs().max()) <= 1e-3 * float(want.max()), \
-        "degree check failed: kernel output is wrong"
 
-    # our kernels per step: the balanced path is merge_path_splits + spmm_balanced + fixup (library rule:
-    # mean row >= 8 entries, knob "balance"), else the one hybrid kernel; BF16 adds the X conversion kernel
+    # ---- parity, outside the timed region, on the result of a real step ------------------------------------------
+    tol = 1e-2 if precision == "bf16" else (1e-3 if (tc_windows or dense_groups) else 1e-5)
+    y = step()
+    parity = {"tol": tol}
+    if world > 1:
+        # every rank holds the full graph and the full X: the partitioned aggregate (exchange included) must equal rows
+        # [r0, r1) of the SINGLE-GPU aggregation of the unpartitioned graph
+        HCSPMM.set_precision("tf32")
+        pre_full = HCSPMM.preprocess(ci, rp, n, nnz, (n + 15) // 16)
+        y_full = HCSPMM.forward(x_full, rp, ci, *pre_full)[0]
+        HCSPMM.set_precision(precision)
+        e = torch.tensor([rel_fro(y, y_full[r0:r1])], device=dev, dtype=torch.float64)
+        dist.all_reduce(e, op=dist.ReduceOp.MAX)
+        parity.update(rel_fro=float(e), vs="rows [r0, r1) of the single-GPU HCSPMM.forward of the unpartitioned graph, "
+                                          "max over ranks")
+        del pre_full, y_full
+    cpu_base = None
+    if rank == 0 and not args.no_cpu_baseline:
+        # torch.sparse.mm FP32 on the host cores: the north star's oracle at full size.  Headline at N = 1: the bounded
+        # sample that is also the reported CPU baseline; otherwise a small row sample of this rank's rows.
+        if world == 1 and headline:
+            cpu_base, y_cpu, rows = cpu_spmm_baseline(rp.cpu(), ci.cpu(), x_full.cpu(), args.cpu_seconds, keep_y=True)
+        else:
+            rows = min(n_l, 8192)
+            rp_c = rp[r0:r0 + rows + 1].cpu()
+            e0, e1 = int(rp_c[0]), int(rp_c[-1])
+            a = torch.sparse_csr_tensor((rp_c - e0).to(torch.int64), ci[e0:e1].cpu().to(torch.int64),
+                                        torch.ones(e1 - e0, dtype=torch.float32), size=(rows, n))
+            torch.set_num_threads(os.cpu_count() or 1)
+            y_cpu = torch.sparse.mm(a, x_full.cpu())
+        parity.update(cpu_rel_fro=rel_fro(y[:rows].cpu(), y_cpu), cpu_rows=int(rows),
+                      cpu_vs="torch.sparse.mm CSR FP32 on the host, first %d of rank 0's rows" % rows)
+        del y_cpu
+    ok = all(v <= tol for k_, v in parity.items() if k_ in ("rel_fro", "cpu_rel_fro"))
+    parity["ok"] = bool(ok)
+    assert ok, f"parity check failed: {parity}"
+
+    # ---- launches of OUR kernels per step (library rules; per-graph products from preprocess) -------------------
     bal_knob = HCSPMM.set_tuning("balance", 1)
     HCSPMM.set_tuning("balance", bal_knob)
     balanced = bal_knob >= 2 or (bal_knob == 1 and nnz_l >= 8 * n_l)
-    launches_per_step = (3 if balanced else 1) * n_slabs + (1 if args.precision == "bf16" else 0) * n_slabs
+    spmm_launches = (2 if balanced else 1) + (1 if (balanced and tc_windows > 0 and precision in ("tf32", "tf32x2")) else 0)
+    if dense_groups > 0 and precision == "tf32":
+        spmm_launches += 2                         # tf32_round_rows + spmm_dense_ws
+    launches_per_step = spmm_launches * n_slabs + (1 if (precision == "bf16" and (world == 1 or dim % 8)) else 0) * n_slabs
     if world > 1 and sg.schedule == "peer":
-        launches_per_step += 1 + n_slabs          # hcspmm_peer_barrier + hcspmm_halo_pull per slab
-    # roofline of the dominant kernel (the SpMM launch of a step); single-GPU figures
-    peak, peak_src = measured_peak_gbs()
-    bytes_alg = nnz_l * (4 + 4 * dim) + n_l * (4 * dim + 4)
-    bytes_min = 4 * nnz_l + 4 * (n_l + 1) + 4 * (n + n_l) * dim
-    # N = 1: the step IS the SpMM; N > 1: this rank's local SpMM timed on its own (phases, max over ranks)
+        launches_per_step += 1 + n_slabs + (1 if operand == "bf16" and dim % 8 == 0 else 0)   # barrier + pull(s) (+ f32->bf16 of own rows)
+
+    # ---- roofline of the dominant kernel (the SpMM launch of a step) ------------------------------------------------
+    esz_x = 2 if precision == "bf16" else 4
+    bytes_alg = nnz_l * (4 + esz_x * dim) + n_l * (4 * dim + 4)
+    bytes_min = 4 * nnz_l + 4 * (n_l + 1) + esz_x * min(n, sg.x_rows) * dim + 4 * n_l * dim
     kern_ms = statistics.mean(step_ms) if world == 1 else (phases or {}).get("kernel_only_ms")
-    traffic = None
+    traffic, traffic_src = None, None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = tj.get(f"{args.shape}_dim{dim}_{args.classifier}") if world == 1 else None
+        ent = tj.get(f"{shape_name}_dim{dim}_{classifier}{'_dense' if dense_groups else ''}") if world == 1 else None
+        if isinstance(ent, dict):
+            traffic, traffic_src = ent.get("bytes"), ent.get("source")
+        elif ent is not None:
+            traffic = ent
     except Exception:
         pass
     roofline = None
     if kern_ms:
         ach = bytes_alg / (kern_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": traffic, "peak_source": peak_src,
-                    "kernel": "spmm_balanced_kernel (+ merge_path_splits_kernel, spmm_balanced_fixup_kernel: the step)"
-                              if balanced else "spmm_hybrid_kernel",
-                    "kernel_ms": kern_ms, "algorithmic_bytes": bytes_alg,
-                    "compulsory_bytes": bytes_min, "compulsory_frac": bytes_min / (kern_ms * 1e-3) / 1e9 / peak,
-                    "frac_of_nominal_8TBs": ach / 8000.0,
+        kernel = ("spmm_dense_ws_kernel (tcgen05) + spmm_balanced_kernel for the remaining windows" if dense_groups else
+                  "spmm_balanced_kernel (+ spmm_balanced_fixup_kernel: the step)" if balanced else "spmm_hybrid_kernel")
+        roofline = {"bound": "l2", "achieved": ach, "peak": ctx.l2_peak, "unit": "GB/s", "frac": ach / ctx.l2_peak,
+                    "traffic": traffic, "traffic_source": traffic_src,
+                    "peak_source": "measured in this run: hcspmm_debug_l2_gather, random 1 KB rows of an L2-resident 32 MB "
+                                   "buffer with the SpMM's 256-bit evict_last loads",
+                    "why_l2": "the gather is served by L2 (ncu: 82 % sector hit rate at the Reddit shape, XBAR->L1 bytes = "
+                              "algorithmic bytes); against the HBM copy peak the same number reads hbm_alg_frac > 1",
+                    "kernel": kernel, "kernel_ms": kern_ms, "algorithmic_bytes": bytes_alg,
+                    "hbm_peak": ctx.hbm_peak, "hbm_peak_source": ctx.hbm_src,
+                    "hbm_alg_frac": ach / ctx.hbm_peak,
+                    "hbm_actual_frac": (traffic / (kern_ms * 1e-3) / 1e9 / ctx.hbm_peak) if traffic else None,
+                    "compulsory_bytes": bytes_min, "compulsory_frac": bytes_min / (kern_ms * 1e-3) / 1e9 / ctx.hbm_peak,
                     "scope": "whole graph, one GPU" if world == 1 else
-                             "rank 0's row shard on one GPU (local SpMM timed alone, max over ranks)"}
+                             "this rank's row shard on one GPU (local SpMM timed alone, max over ranks)"}
 
-    # e2e: the reference-facing module with HOST buffers, H2D of X and D2H of Y inside the timed region
+    # ---- e2e (headline only): the reference-facing module with HOST buffers ------------------------------------------
     e2e = None
-    if not args.no_e2e:
+    if headline and not args.no_e2e:
         rows_in = n if world == 1 else n_l
         xh = torch.empty(rows_in, dim, pin_memory=True)
         xh.copy_(x_full if world == 1 else x_loc)
         yh = torch.empty(n_l, dim, pin_memory=True)
-
-        # Three streams, double-buffered device X / Y: H2D(i+1) | kernel(i) | D2H(i-1) overlap; every
-        # step's copies are inside the timed region.
         cur = torch.cuda.current_stream(dev)
         s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
         xd = [torch.empty(rows_in, dim, device=dev) for _ in range(2)]
@@ -438,7 +563,7 @@ def main():
 
         e2e_run(2)
         barrier()
-        k2 = max(4, min(args.steps, 10))
+        k2 = max(4, steps)
         ev0.record()
         e2e_run(k2)
         ev1.record()
@@ -449,46 +574,46 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e_ms = float(t)
         e2e = {"value": flops / (e_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": e_ms, "steps": k2,
-               "pipeline": "pinned host X -> H2D stream | HCSPMM.forward | D2H stream -> pinned host Y, double buffered",
+               "kind": "THROUGHPUT of a double-buffered pipeline (H2D of step i+1 | kernels of step i | D2H of step i-1 on three "
+                       "streams), every step's copies inside the timed region; the latency of one isolated step is "
+                       "H2D + kernel + D2H in series",
+               "pipeline": "pinned host X -> H2D stream | HCSPMM.forward | D2H stream -> pinned host Y",
                "h2d_bytes_per_step": rows_in * dim * 4 * world if world > 1 else rows_in * dim * 4,
                "d2h_bytes_per_step": n * dim * 4}
 
-    cpu_base = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_base = cpu_spmm_baseline(rp.cpu(), ci.cpu(), x_full.cpu(), args.cpu_seconds)
-        for k in ("seconds", "entries", "rows"):
-            cpu_base.pop(k, None)
-
-    if rank == 0:
-        line = {"metric": "spmm_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"{args.shape}-shape power-law graph, single-kernel SpMM Y=A*X "
-                                       f"(BASELINE.json configs[1])" if args.shape == "reddit" else f"{args.shape}-shape SpMM",
-                           "nodes": n, "stored_entries": nnz, "dim": dim, "classifier": args.classifier,
-                           "precision_tc_windows": args.precision, "tc_windows": tc_windows, "dense_groups_tcgen05": dense_groups,
-                           "windows": (n_l + 15) // 16, "partition": f"row windows, nnz-balanced, {world} shard(s)",
-                           "exchange": ({"gather": "NCCL all_gather_into_tensor of the row shards of X per step",
-                                         "slabs": "NCCL all_gather_into_tensor in %d feature slabs pipelined with the SpMM" % n_slabs,
-                                         "halo": "halo rows only: pack + NCCL all_to_all_single per step, %d feature slab(s)" % n_slabs,
-                                         "peer": "halo rows only, pulled from the owners' memory over NVLink by hcspmm_halo_pull "
-                                                 "after hcspmm_peer_barrier, %d feature slab(s), %d source pass(es)"
-                                                 % (n_slabs, 2 if sg.passes is not None else 1)}
-                                        [sg.schedule]) if world > 1 else "none",
-                           "phases": phases,
-                           "l2": "inputs larger than L2 (X %.0f MB + CSR %.0f MB vs 126 MB), no flush" %
-                                 (n * dim * 4 / 1e6, nnz * 4 / 1e6),
-                           "preprocess_ms": prep_ms, "graph_gen_s": t_gen,
-                           "generator": "R-MAT(0.57,0.19,0.19,0.05) folded mod N, symmetrised, de-duplicated, "
-                                        "ids permuted, seed %d" % shape["seed"]},
-                "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e, "clocks": clocks,
-                "gpu_launches": args.steps * launches_per_step, "launches_per_step": launches_per_step,
-                "step_ms": {"min": min(step_ms), "median": statistics.median(step_ms), "max": max(step_ms)}}
-        print(json.dumps(line))
     if world > 1:
         sg.close()
-        dist.destroy_process_group()
-    return 0
+    workload = (f"{shape_name}-shape graph, single-kernel SpMM Y=A*X, dim {dim}" +
+                (" (BASELINE.json configs[1])" if shape_name == "reddit" and dim == 256 else ""))
+    gens = {"rmat": "R-MAT(0.57,0.19,0.19,0.05) folded mod N, symmetrised, de-duplicated, ids permuted, seed %d",
+            "sbm": "stochastic block model: 16-aligned communities of 512 vertices (p_in 0.55) + 15 random neighbours per "
+                   "vertex, ids NOT permuted, seed %d",
+            "ring": "ring + one random perfect matching (every degree 3), seed %d"}
+    exchange_desc = {"gather": "NCCL all_gather_into_tensor of the row shards of X per step (the north star's schedule; kept as "
+                               "the comparison: --exchange gather)",
+                     "slabs": "NCCL all_gather_into_tensor in %d feature slabs pipelined with the SpMM" % n_slabs,
+                     "halo": "halo rows only: pack + NCCL all_to_all_single per step, %d feature slab(s)" % n_slabs,
+                     "peer": "halo rows only (%s), pulled from the owners' memory over NVLink by hcspmm_halo_pull after "
+                             "hcspmm_peer_barrier, %d feature slab(s), %d source pass(es) -- moves fewer bytes than the north "
+                             "star's all-gather (exchange_rows_vs_allgather)" % (operand, n_slabs, 2 if sg.passes is not None else 1)}
+    line = {"metric": "spmm_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "bf16-stored X, f32 accumulate" if precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": workload, "nodes": n, "stored_entries": nnz, "dim": dim, "classifier": classifier,
+                       "precision": precision, "tc_windows_label1": tc_windows, "dense_groups_tcgen05": dense_groups,
+                       "windows": (n_l + 15) // 16, "partition": f"row windows, nnz-balanced, {world} shard(s)",
+                       "exchange": exchange_desc[sg.schedule] if world > 1 else "none",
+                       "phases": phases,
+                       "l2": "inputs larger than L2 (X %.0f MB + CSR %.0f MB vs 126 MB), no flush" %
+                             (n * dim * 4 / 1e6, nnz * 4 / 1e6),
+                       "preprocess_ms": prep_ms, "graph_gen_s": t_gen,
+                       "generator": gens[shape["kind"]] % shape["seed"]},
+            "roofline": roofline, "parity": parity, "cpu_baseline": cpu_base, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": steps * launches_per_step, "launches_per_step": launches_per_step,
+            "step_ms": {"min": min(step_ms), "median": statistics.median(step_ms), "max": max(step_ms)}}
+    del sg, x_full, x_loc, y
+    torch.cuda.empty_cache()
+    return line
 
 
 if __name__ == "__main__":

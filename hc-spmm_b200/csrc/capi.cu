@@ -17,7 +17,7 @@ void set_error(const char *fmt, ...) {
 }
 
 Tuning &tuning() {
-  static Tuning t = {1024, 0, 1, 1, 0, 0, 1, 2, 1, 1, 1, 0, 0, 64, 1, 0, 2048};
+  static Tuning t = {1024, 0, 1, 1, 0, 1, 1, 2, 1, 1, 1, 0, 0, 64, 1, 0, 2048, 10000, 1, 1};
   return t;
 }
 
@@ -57,6 +57,7 @@ int launch_spmm(const float *, int64_t, int32_t, const int32_t *, const int32_t 
                 const int32_t *, const int32_t *, const int32_t *, int32_t, int64_t, int32_t, int,
                 int, float *, int64_t, const hcspmm_aux_t *, cudaStream_t);
 int launch_merge_path_splits(const int32_t *, int32_t, int64_t, int32_t, int32_t *, cudaStream_t);
+int launch_f32_to_bf16(const float *, int64_t, int32_t, int32_t, void *, int64_t, cudaStream_t);
 size_t balanced_workspace_bytes(int32_t, int64_t, int32_t);
 int launch_gemm_tf32(const float *, int64_t, const float *, int64_t, int32_t, int32_t, int32_t,
                      float *, int64_t, cudaStream_t);
@@ -79,6 +80,12 @@ bool dense_supported(const float *, const float *, int64_t, int32_t);
 int launch_spmm_dense(const float *, int64_t, int32_t, int32_t, int32_t, const int32_t *, int32_t, int64_t, int, float *,
                       int64_t, float *, int *, cudaStream_t);
 const int32_t *dense_plan_labels(const int32_t *, int32_t, int32_t, int64_t);
+void dense_plan_arrays(const int32_t *, int32_t, int32_t, int64_t, const int **, const int **, const int **, const unsigned **);
+bool dense_tma_supported(const float *, int64_t, const float *, int64_t, int32_t);
+size_t dense_tma_scratch_floats(int32_t, int32_t);
+int launch_spmm_dense_tma(const float *, int64_t, int32_t, int32_t, int32_t, const int *, const int *, const int *,
+                          const unsigned *, int32_t, int, float *, int64_t, const float *, int64_t, int32_t, float *, int64_t,
+                          float *, int *, cudaStream_t);
 size_t loa_workspace_bytes(int32_t n, int64_t nnz, int32_t max_degree);
 int launch_loa(const int32_t *, const int32_t *, const int32_t *, const int32_t *, int32_t, int64_t, int32_t,
                int32_t *, int32_t *, int32_t *, void *, size_t, cudaStream_t);
@@ -130,6 +137,9 @@ int hcspmm_set_tuning(const char *key, int value) {
   else if (key && !strcmp(key, "gemm_round")) slot = &tuning().gemm_round;
   else if (key && !strcmp(key, "gemm_stages")) slot = &tuning().gemm_stages;
   else if (key && !strcmp(key, "pool_keep_mb")) slot = &tuning().pool_keep_mb;
+  else if (key && !strcmp(key, "barrier_timeout_ms")) slot = &tuning().barrier_timeout_ms;
+  else if (key && !strcmp(key, "dense_tma")) slot = &tuning().dense_tma;
+  else if (key && !strcmp(key, "fuse_update")) slot = &tuning().fuse_update;
   if (!slot) return -1;
   int old = *slot;
   *slot = value;
@@ -167,6 +177,11 @@ size_t hcspmm_merge_path_count(int32_t n_rows, int64_t nnz, int32_t chunk) {
 int hcspmm_merge_path_splits(const int32_t *d_rowptr, int32_t n_rows, int64_t nnz, int32_t chunk, int32_t *d_splits,
                              void *stream) {
   return launch_merge_path_splits(d_rowptr, n_rows, nnz, chunk, d_splits, (cudaStream_t)stream);
+}
+
+int hcspmm_f32_to_bf16(const float *d_x, int64_t ldx, int32_t rows, int32_t dim, void *d_out, int64_t ld_out,
+                       void *stream) {
+  return launch_f32_to_bf16(d_x, ldx, rows, dim, d_out, ld_out, (cudaStream_t)stream);
 }
 
 size_t hcspmm_spmm_workspace_bytes(int32_t n_rows, int64_t nnz, int32_t dim) {
@@ -241,16 +256,28 @@ int hcspmm_spmm_aux(const float *d_x, int64_t ldx, int32_t x_rows, const int32_t
   if (!dense)
     return launch_spmm(d_x, ldx, x_rows, d_rowptr, d_colidx, d_block_partition, d_edge_to_column, d_edge_to_row,
                        d_hybrid_type, n_rows, nnz, dim, precision, accumulate, d_y, ldy, aux, (cudaStream_t)stream);
-  float *xr = nullptr;
-  cudaError_t err = scratch_alloc((void **)&xr, sizeof(float) * (size_t)x_rows * dblock, (cudaStream_t)stream);
-  if (err != cudaSuccess) { set_error("spmm_plan: scratch: %s", cudaGetErrorString(err)); return (int)err; }
   int rc = 0;
-  for (int32_t c0 = 0; c0 < dim && rc == 0; c0 += dblock) {
-    const int32_t w = dim - c0 < dblock ? dim - c0 : dblock;
-    rc = launch_spmm_dense(d_x + c0, ldx, x_rows, n_rows, w, d_plan, n_dense, total_cols, accumulate, d_y + c0, ldy, xr,
-                           umma_error_flag(), (cudaStream_t)stream);
+  if (tuning().dense_tma && dense_tma_supported(d_x, ldx, d_y, ldy, dblock)) {
+    // TMA gather4 kernel: the tensor map converts FP32 -> TF32 on load, no rounded copy of X
+    const int *sw_ids, *sw_off, *cols;
+    const unsigned *masks;
+    dense_plan_arrays(d_plan, n_rows, n_dense, total_cols, &sw_ids, &sw_off, &cols, &masks);
+    for (int32_t c0 = 0; c0 < dim && rc == 0; c0 += dblock) {
+      const int32_t w = dim - c0 < dblock ? dim - c0 : dblock;
+      rc = launch_spmm_dense_tma(d_x + c0, ldx, x_rows, n_rows, w, sw_ids, sw_off, cols, masks, n_dense, accumulate,
+                                 d_y + c0, ldy, nullptr, 0, 0, nullptr, 0, nullptr, umma_error_flag(), (cudaStream_t)stream);
+    }
+  } else {
+    float *xr = nullptr;
+    cudaError_t err = scratch_alloc((void **)&xr, sizeof(float) * (size_t)x_rows * dblock, (cudaStream_t)stream);
+    if (err != cudaSuccess) { set_error("spmm_plan: scratch: %s", cudaGetErrorString(err)); return (int)err; }
+    for (int32_t c0 = 0; c0 < dim && rc == 0; c0 += dblock) {
+      const int32_t w = dim - c0 < dblock ? dim - c0 : dblock;
+      rc = launch_spmm_dense(d_x + c0, ldx, x_rows, n_rows, w, d_plan, n_dense, total_cols, accumulate, d_y + c0, ldy, xr,
+                             umma_error_flag(), (cudaStream_t)stream);
+    }
+    scratch_free(xr, (cudaStream_t)stream);
   }
-  scratch_free(xr, (cudaStream_t)stream);
   if (rc == 0) {
     hcspmm_aux_t rest = *aux;
     rest.n_tc_windows = -1;   // the plan's labels differ from the caller's count
@@ -297,6 +324,43 @@ int hcspmm_spmm_gemm(const float *d_x, int64_t ldx, int32_t x_rows, const int32_
   int rc = launch_spmm(d_x, ldx, x_rows, d_rowptr, d_colidx, d_block_partition, d_edge_to_column,
                        d_edge_to_row, d_hybrid_type, n_rows, nnz, dim, precision, 0, d_z, ldz,
                        nullptr, (cudaStream_t)stream);
+  if (rc) return rc;
+  return hcspmm_gemm_tf32(d_z, ldz, d_w, ldw, n_rows, dim, hidden, d_out, ldo, stream);
+}
+
+int hcspmm_spmm_gemm_aux(const float *d_x, int64_t ldx, int32_t x_rows, const int32_t *d_rowptr,
+                         const int32_t *d_colidx, const int32_t *d_block_partition,
+                         const int32_t *d_edge_to_column, const int32_t *d_edge_to_row,
+                         const int32_t *d_hybrid_type, int32_t n_rows, int64_t nnz, int32_t dim,
+                         int precision, const float *d_w, int64_t ldw, int32_t hidden, float *d_out,
+                         int64_t ldo, float *d_z, int64_t ldz, const hcspmm_aux_t *aux, void *stream) {
+  if (!d_z || !d_out || !d_w) {
+    set_error("spmm_gemm: null pointer argument");
+    return HCSPMM_E_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool fuse = aux && aux->d_plan && aux->n_dense > 0 && aux->plan_full && tuning().umma && tuning().dense_tma &&
+                    tuning().fuse_update && precision == HCSPMM_PRECISION_TF32 && d_x && hidden > 0 && hidden <= 256 &&
+                    dim <= 256 && ldw >= hidden && ldo >= hidden && dense_tma_supported(d_x, ldx, d_z, ldz, dim);
+  if (fuse) {
+    // ONE kernel: the aggregate of each super-window is multiplied by W before it leaves tensor memory
+    const int *sw_ids, *sw_off, *cols;
+    const unsigned *masks;
+    dense_plan_arrays(aux->d_plan, n_rows, aux->n_dense, aux->total_cols, &sw_ids, &sw_off, &cols, &masks);
+    if ((long long)aux->n_dense * 128 < n_rows) {   // super-windows without entries: their rows of Z and out are zero
+      CUDA_TRY(cudaMemset2DAsync(d_z, sizeof(float) * ldz, 0, sizeof(float) * dim, n_rows, st));
+      CUDA_TRY(cudaMemset2DAsync(d_out, sizeof(float) * ldo, 0, sizeof(float) * hidden, n_rows, st));
+    }
+    float *wt = nullptr;
+    cudaError_t e = scratch_alloc((void **)&wt, sizeof(float) * dense_tma_scratch_floats(dim, hidden), st);
+    if (e != cudaSuccess) { set_error("spmm_gemm: scratch: %s", cudaGetErrorString(e)); return (int)e; }
+    const int rc = launch_spmm_dense_tma(d_x, ldx, x_rows, n_rows, dim, sw_ids, sw_off, cols, masks, aux->n_dense, 0, d_z,
+                                         ldz, d_w, ldw, hidden, d_out, ldo, wt, umma_error_flag(), st);
+    scratch_free(wt, st);
+    return rc;
+  }
+  int rc = hcspmm_spmm_aux(d_x, ldx, x_rows, d_rowptr, d_colidx, d_block_partition, d_edge_to_column, d_edge_to_row,
+                           d_hybrid_type, n_rows, nnz, dim, precision, 0, d_z, ldz, aux, stream);
   if (rc) return rc;
   return hcspmm_gemm_tf32(d_z, ldz, d_w, ldw, n_rows, dim, hidden, d_out, ldo, stream);
 }

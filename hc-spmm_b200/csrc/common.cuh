@@ -33,6 +33,9 @@ struct Tuning {
   int gemm_round;  // TMA Update GEMM: 1 = rounder warps cvt.rna the Z boxes in shared memory, 0 = TF32-typed tensor map
   int gemm_stages; // TMA Update GEMM: cap on the shared-memory ring depth (0 = as many as fit)
   int pool_keep_mb; // scratch pool: megabytes of freed blocks kept across synchronisations
+  int barrier_timeout_ms; // hcspmm_peer_barrier: how long a rank waits for a peer before flagging *d_err
+  int dense_tma;   // 1: dense super-windows on the TMA gather4 kernel (dense_tma.cu), 0: cp.async kernels (dense.cu)
+  int fuse_update; // 1: Aggregation + Update as one kernel when the dense plan covers the graph
 };
 Tuning &tuning();
 

@@ -648,6 +648,12 @@ int launch_spmm_dense(const float *x, int64_t ldx, int32_t x_rows, int32_t n_row
   return 0;
 }
 
+void dense_plan_arrays(const int32_t *plan, int32_t n_rows, int32_t n_dense, int64_t total_cols, const int **sw_ids,
+                       const int **sw_off, const int **cols, const unsigned **masks) {
+  PlanView v = view_plan(plan, n_rows, n_dense, total_cols);
+  *sw_ids = v.sw_ids; *sw_off = v.sw_off; *cols = v.cols; *masks = v.masks;
+}
+
 const int32_t *dense_plan_labels(const int32_t *plan, int32_t n_rows, int32_t n_dense, int64_t total_cols) {
   return view_plan(plan, n_rows, n_dense, total_cols).ht2;
 }

@@ -9,8 +9,9 @@
 //     process per GPU, any launcher; the own rows are written in place and are what the peers read;
 //   * hcspmm_peer_barrier: one tiny kernel; thread s stores this rank's epoch into peer s's flag
 //     array (system-scope release) and spins on the local flag of peer s (acquire), so after it every
-//     peer's shard written before ITS barrier is visible.  Spins are bounded (~10 s) and report through
-//     *d_err instead of hanging the device;
+//     peer's shard written before ITS barrier is visible.  Spins are bounded (knob "barrier_timeout_ms",
+//     default 10 s) and report through *d_err (1 + the missing peer) instead of hanging the device: the
+//     result of an aggregation whose barrier timed out is undefined, and the host layer raises on it;
 //   * hcspmm_halo_pull: operand row i (owner s = segment of i, row src_row[i] there) is copied with
 //     128-bit loads from peer_x[s]; eight rows in flight per warp cover the NVLink latency.
 // Buffers are used alternately (two per width) by the caller, so one barrier per aggregation suffices:
@@ -21,20 +22,29 @@
 
 namespace hcspmm {
 
-__global__ void peer_barrier_kernel(int *const *flag_ptrs, int rank, int world, int epoch, int *err) {
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__global__ void peer_barrier_kernel(int *const *flag_ptrs, int rank, int world, int epoch, int *err,
+                                    unsigned long long timeout_ns) {
   const int s = threadIdx.x;
   if (s >= world) return;
   __threadfence_system();
   int *remote = flag_ptrs[s] + rank;   // peer s's flag for me
   asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
   const int *local = flag_ptrs[rank] + s;   // my flag for peer s
-  const long long t0 = clock64();
-  int v;
+  const unsigned long long t0 = global_ns();
+  int v, spins = 0;
   do {
     asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(local) : "memory");
     if (v - epoch >= 0) break;
-    if (clock64() - t0 > 20000000000LL) {   // ~10 s at 2 GHz: a peer never arrived
-      if (err) atomicExch(err, 1);
+    if ((++spins & 1023) == 0 && global_ns() - t0 > timeout_ns) {
+      // a peer never arrived: what the following pull reads is UNDEFINED.  *err may live in pinned host memory
+      // (hcspmm.peer does that) so the host sees it without a synchronisation and raises at its next call.
+      if (err) { *reinterpret_cast<volatile int *>(err) = 1 + s; __threadfence_system(); }
       break;
     }
     __nanosleep(64);
@@ -148,8 +158,10 @@ int hcspmm_peer_barrier(int32_t *const *d_flag_ptrs, int32_t rank, int32_t world
     set_error("peer_barrier: bad argument");
     return HCSPMM_E_INVALID;
   }
+  const unsigned long long timeout_ns =
+      (unsigned long long)(tuning().barrier_timeout_ms > 0 ? tuning().barrier_timeout_ms : 10000) * 1000000ull;
   peer_barrier_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(reinterpret_cast<int *const *>(d_flag_ptrs), rank, world, epoch,
-                                                        d_err);
+                                                        d_err, timeout_ns);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("peer_barrier: %s", cudaGetErrorString(e)); return (int)e; }
   return 0;

@@ -958,7 +958,7 @@ __global__ void unpad_rows_kernel(const float *__restrict__ src, int dpad, int d
 
 // X (FP32, leading dim ldx) -> dense BF16 copy [rows, dim], round to nearest even
 __global__ void f32_to_bf16_rows_kernel(const float *__restrict__ x, long long ldx, int dim2, uint32_t *__restrict__ xb,
-                                        long long total2) {
+                                        long long ldb2, long long total2) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total2; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / dim2;
     const int c = (int)(i - r * dim2) * 2;
@@ -967,7 +967,7 @@ __global__ void f32_to_bf16_rows_kernel(const float *__restrict__ x, long long l
     // RNE on the upper 16 bits (NaN / Inf pass through the truncation unchanged enough for a gather-sum)
     const uint32_t rlo = ((ulo & 0x7f800000u) == 0x7f800000u) ? ulo : ulo + 0x7fffu + ((ulo >> 16) & 1u);
     const uint32_t rhi = ((uhi & 0x7f800000u) == 0x7f800000u) ? uhi : uhi + 0x7fffu + ((uhi >> 16) & 1u);
-    xb[i] = (rlo >> 16) | (rhi & 0xffff0000u);
+    xb[r * ldb2 + (c >> 1)] = (rlo >> 16) | (rhi & 0xffff0000u);
   }
 }
 
@@ -1125,6 +1125,22 @@ static cudaError_t run_balanced(const SpmmParams &p, long long nnz, bool v8, boo
   return err;
 }
 
+// out[r, 0..dim) (bfloat16, row pitch ld_out elements) = RNE(x[r, 0..dim)): how a rank writes its own rows into a
+// BF16 exchange operand
+int launch_f32_to_bf16(const float *x, int64_t ldx, int32_t rows, int32_t dim, void *out, int64_t ld_out,
+                       cudaStream_t stream) {
+  if (rows <= 0 || dim <= 0) return 0;
+  if (!x || !out || (dim & 1) || (ld_out & 1) || ld_out < dim || ldx < dim || (reinterpret_cast<uintptr_t>(out) & 3)) {
+    set_error("f32_to_bf16: dim and ld_out must be even, out 4-byte aligned");
+    return HCSPMM_E_INVALID;
+  }
+  const long long total2 = (long long)rows * (dim / 2);
+  f32_to_bf16_rows_kernel<<<1184, 256, 0, stream>>>(x, ldx, dim / 2, reinterpret_cast<uint32_t *>(out), ld_out / 2, total2);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) { set_error("f32_to_bf16: %s", cudaGetErrorString(err)); return (int)err; }
+  return 0;
+}
+
 int launch_merge_path_splits(const int32_t *rowptr, int32_t n_rows, int64_t nnz, int32_t chunk, int32_t *splits,
                              cudaStream_t stream) {
   if (!rowptr || !splits || n_rows < 0 || nnz < 0 || chunk < 64) { set_error("merge_path_splits: bad argument"); return HCSPMM_E_INVALID; }
@@ -1161,7 +1177,7 @@ int launch_spmm(const float *x, int64_t ldx, int32_t x_rows, const int32_t *rowp
     set_error("spmm: leading dimension smaller than dim");
     return HCSPMM_E_INVALID;
   }
-  if (precision < 0 || precision > HCSPMM_PRECISION_BF16) {
+  if (precision < 0 || precision > HCSPMM_PRECISION_BF16_STORED) {
     set_error("spmm: unknown precision %d", precision);
     return HCSPMM_E_INVALID;
   }
@@ -1170,6 +1186,16 @@ int launch_spmm(const float *x, int64_t ldx, int32_t x_rows, const int32_t *rowp
   // Y; anything else is computed in FP32 (which is within the BF16 tolerance a fortiori).
   const bool y_vec = (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (ldy & 3) == 0;
   if (precision == HCSPMM_PRECISION_BF16 && !((dim & 7) == 0 && y_vec)) precision = HCSPMM_PRECISION_FP32;
+  // BF16_STORED: d_x already holds bfloat16 rows (ldx counted in bfloat16 elements) -- the multi-GPU operand the
+  // halo exchange moved at half the bytes; no conversion pass, the same gather as BF16
+  const bool stored16 = precision == HCSPMM_PRECISION_BF16_STORED;
+  if (stored16) {
+    if (!((dim & 7) == 0 && y_vec && (ldx & 7) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0)) {
+      set_error("spmm: BF16-stored X needs dim and ldx multiples of 8 and 16-byte aligned X / Y");
+      return HCSPMM_E_ALIGN;
+    }
+    precision = HCSPMM_PRECISION_BF16;
+  }
   const bool labels = ht != nullptr && precision != HCSPMM_PRECISION_FP32 && precision != HCSPMM_PRECISION_BF16;
   if (labels && (!bp || (nnz > 0 && (!etc || !etr)))) {
     set_error("spmm: hybrid_type given without blockPartition/edgeToColumn/edgeToRow");
@@ -1194,12 +1220,16 @@ int launch_spmm(const float *x, int64_t ldx, int32_t x_rows, const int32_t *rowp
   cudaError_t err;
   if (precision == HCSPMM_PRECISION_BF16) {
     uint32_t *xb = nullptr;
-    err = scratch_alloc((void **)&xb, sizeof(uint16_t) * (size_t)x_rows * dim, stream);
-    if (err != cudaSuccess) { set_error("spmm bf16: cudaMallocAsync: %s", cudaGetErrorString(err)); return (int)err; }
-    const long long total2 = (long long)x_rows * (dim / 2);
-    f32_to_bf16_rows_kernel<<<1184, 256, 0, stream>>>(x, ldx, dim / 2, xb, total2);
-    p.x = reinterpret_cast<const float *>(xb);
-    p.ldx = dim / 2;
+    if (stored16) {
+      p.ldx = ldx / 2;   // float units
+    } else {
+      err = scratch_alloc((void **)&xb, sizeof(uint16_t) * (size_t)x_rows * dim, stream);
+      if (err != cudaSuccess) { set_error("spmm bf16: scratch: %s", cudaGetErrorString(err)); return (int)err; }
+      const long long total2 = (long long)x_rows * (dim / 2);
+      f32_to_bf16_rows_kernel<<<1184, 256, 0, stream>>>(x, ldx, dim / 2, xb, dim / 2, total2);
+      p.x = reinterpret_cast<const float *>(xb);
+      p.ldx = dim / 2;
+    }
     int slab = tuning().slab > 0 ? (tuning().slab + 31) / 32 * 32 : 512;
     if (slab > 512) slab = 512;
     if (slab > dim) slab = dim;
@@ -1218,7 +1248,7 @@ int launch_spmm(const float *x, int64_t ldx, int32_t x_rows, const int32_t *rowp
     else if (slab <= 128) err = launch_hybrid_bf16<16, 1>(p, grid, smem, stream);
     else if (slab <= 256) err = launch_hybrid_bf16<32, 1>(p, grid, smem, stream);
     else err = launch_hybrid_bf16<32, 2>(p, grid, smem, stream);
-    scratch_free(xb, stream);
+    if (xb) scratch_free(xb, stream);
     if (err != cudaSuccess) { set_error("spmm bf16 launch: %s", cudaGetErrorString(err)); return (int)err; }
     return 0;
   }

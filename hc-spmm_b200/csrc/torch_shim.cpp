@@ -19,14 +19,25 @@
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/extension.h>
 
+#include <string.h>
+
 #include <vector>
 
 #include "../../include/hcspmm.h"
 
 namespace {
 
-constexpr int32_t kPlanMagic = 0x48435044;   // row_nzr[0] when col_nzr carries a dense plan
-bool g_dense = false;                        // build / use tcgen05 dense super-window plans
+// Per-graph products travel in the two tensors the reference returns as one-element placeholders
+// (hybrid_all_kernel.cu:405) and that its callers only store and pass back:
+//   row_nzr  HOST int32[kHdrWords]  header (so that forward() needs no device synchronisation to read it)
+//   col_nzr  DEVICE int32           [dense plan words | merge-path split points]
+// The selector / precision / dense settings in force when preprocess() ran are recorded in the header and are
+// what forward*() uses for THAT graph: set_classifier / set_precision / set_dense only set the defaults for
+// graphs preprocessed afterwards, so two graphs (or two threads) never see each other's settings.
+constexpr int32_t kPlanMagic = 0x48435044;
+enum { H_MAGIC = 0, H_NDENSE, H_TOTALCOLS, H_NROWS, H_VERSION, H_PRECISION, H_DENSE, H_NTC, H_SPLITS_CHUNK, H_NSPLITS,
+       H_SPLITS_OFF, H_CLASSIFIER, H_PLAN_FULL, kHdrWords = 16 };
+bool g_dense = false;                        // defaults for the next preprocess()
 int g_classifier = HCSPMM_CLASSIFIER_SHIPPED;
 int g_precision = HCSPMM_PRECISION_TF32;
 bool g_bug_compat = false;
@@ -109,13 +120,15 @@ std::vector<torch::Tensor> preprocess(torch::Tensor edgeList, torch::Tensor node
                              ht.data_ptr<int32_t>(), ws.data_ptr(), ws_bytes,
                              at::cuda::getCurrentCUDAStream().stream()),
            "preprocess");
-  // row_nzr / col_nzr are one-element placeholders in the reference (:405) -- opaque to the caller,
-  // who only passes them back.  With set_dense(True) and a selector that labels tensor-core windows
-  // they carry the tcgen05 dense plan instead: col_nzr = the plan (device), row_nzr = its sizes (HOST
-  // int32 tensor, so that forward() needs no device synchronisation to read them).
-  auto row_nzr = torch::zeros({1}, opts), col_nzr = torch::zeros({1}, opts);
+  // header + per-graph products (see the top of this file)
+  auto stream = at::cuda::getCurrentCUDAStream().stream();
+  auto row_nzr = torch::zeros({kHdrWords}, torch::TensorOptions().dtype(torch::kInt32));
+  int32_t *h = row_nzr.data_ptr<int32_t>();
+  h[H_MAGIC] = kPlanMagic; h[H_NROWS] = (int32_t)num_nodes; h[H_VERSION] = 2; h[H_PRECISION] = g_precision;
+  h[H_DENSE] = g_dense ? 1 : 0; h[H_CLASSIFIER] = g_classifier;
+  h[H_NTC] = edge_num > 0 ? (int32_t)ht.eq(1).sum().item<int64_t>() : 0;
+  torch::Tensor plan;
   if (g_dense && edge_num > 0 && g_classifier != HCSPMM_CLASSIFIER_SHIPPED && g_classifier != HCSPMM_CLASSIFIER_ALL_CUDA) {
-    auto stream = at::cuda::getCurrentCUDAStream().stream();
     const size_t pws = hcspmm_dense_plan_workspace_bytes((int32_t)num_nodes, edge_num);
     auto pw = torch::empty({(int64_t)pws}, opts.dtype(torch::kUInt8));
     int32_t counts[2] = {0, 0};
@@ -125,34 +138,79 @@ std::vector<torch::Tensor> preprocess(torch::Tensor edgeList, torch::Tensor node
              "dense_plan_count");
     if (counts[0] > 0) {
       const size_t words = hcspmm_dense_plan_words((int32_t)num_nodes, counts[0], counts[1]);
-      col_nzr = torch::zeros({(int64_t)words}, opts);
+      plan = torch::zeros({(int64_t)words}, opts);
       check_rc(hcspmm_dense_plan_fill(edgeList.data_ptr<int32_t>(), etr.data_ptr<int32_t>(), (int32_t)num_nodes, edge_num,
-                                      pw.data_ptr(), counts[0], counts[1], col_nzr.data_ptr<int32_t>(), words, stream),
+                                      pw.data_ptr(), counts[0], counts[1], plan.data_ptr<int32_t>(), words, stream),
                "dense_plan_fill");
-      row_nzr = torch::tensor({kPlanMagic, counts[0], counts[1], (int32_t)num_nodes},
-                              torch::TensorOptions().dtype(torch::kInt32));
+      h[H_NDENSE] = counts[0]; h[H_TOTALCOLS] = counts[1];
+      // does the plan cover every 128-row super-window that has entries?  (then *_fused is one kernel)
+      auto edges = torch::arange(0, num_nodes + 128, 128, opts.dtype(torch::kInt64)).clamp_max(num_nodes);
+      auto rp64 = nodePointer.index_select(0, edges);
+      const int64_t busy = rp64.slice(0, 1).gt(rp64.slice(0, 0, -1)).sum().item<int64_t>();
+      h[H_PLAN_FULL] = busy == counts[0] ? 1 : 0;
     }
   }
+  // merge-path split points of the work-balanced kernel (static per graph)
+  const int64_t plan_words = plan.defined() ? plan.numel() : 0;
+  const int64_t n_split_words = (int64_t)hcspmm_merge_path_count((int32_t)num_nodes, edge_num, HCSPMM_SPLITS_CHUNK);
+  auto col_nzr = torch::empty({plan_words + n_split_words}, opts);
+  if (plan_words > 0) col_nzr.narrow(0, 0, plan_words).copy_(plan);
+  check_rc(hcspmm_merge_path_splits(nodePointer.data_ptr<int32_t>(), (int32_t)num_nodes, edge_num, HCSPMM_SPLITS_CHUNK,
+                                    col_nzr.data_ptr<int32_t>() + plan_words, stream),
+           "merge_path_splits");
+  h[H_SPLITS_CHUNK] = HCSPMM_SPLITS_CHUNK; h[H_NSPLITS] = (int32_t)(n_split_words - 1); h[H_SPLITS_OFF] = (int32_t)plan_words;
   return {bp, etc, etr, ht, row_nzr, col_nzr};
 }
 
-// one aggregation through the C ABI: with a dense plan when row_nzr / col_nzr carry one
+// the graph's own products, when row_nzr / col_nzr carry them (header written by preprocess())
+struct AuxView {
+  bool ok = false;
+  hcspmm_aux_t aux;
+  int precision = HCSPMM_PRECISION_TF32;
+  torch::Tensor ws;   // keeps the workspace alive for the duration of the call
+};
+
+AuxView make_aux(const torch::Tensor &input, const Graph &g, const torch::Tensor &row_nzr, const torch::Tensor &col_nzr,
+                 int64_t dim) {
+  AuxView v;
+  memset(&v.aux, 0, sizeof(v.aux));
+  v.precision = g_precision;
+  if (!(row_nzr.defined() && row_nzr.device().is_cpu() && row_nzr.scalar_type() == torch::kInt32 &&
+        row_nzr.numel() >= kHdrWords && row_nzr.data_ptr<int32_t>()[H_MAGIC] == kPlanMagic &&
+        row_nzr.data_ptr<int32_t>()[H_VERSION] == 2 && row_nzr.data_ptr<int32_t>()[H_NROWS] == g.n_rows &&
+        col_nzr.defined() && col_nzr.is_cuda() && col_nzr.scalar_type() == torch::kInt32 && col_nzr.is_contiguous() &&
+        col_nzr.device() == input.device()))
+    return v;
+  const int32_t *h = row_nzr.data_ptr<int32_t>();
+  const int32_t *blob = col_nzr.data_ptr<int32_t>();
+  v.ok = true;
+  v.precision = h[H_PRECISION];
+  v.aux.n_tc_windows = h[H_NTC];
+  if (h[H_NSPLITS] > 0 && col_nzr.numel() >= (int64_t)h[H_SPLITS_OFF] + h[H_NSPLITS] + 1) {
+    v.aux.d_splits = blob + h[H_SPLITS_OFF]; v.aux.splits_chunk = h[H_SPLITS_CHUNK]; v.aux.n_splits = h[H_NSPLITS];
+  }
+  if (h[H_DENSE] && h[H_NDENSE] > 0) {
+    v.aux.d_plan = blob; v.aux.n_dense = h[H_NDENSE]; v.aux.total_cols = h[H_TOTALCOLS]; v.aux.plan_full = h[H_PLAN_FULL];
+  }
+  if (g.nnz >= 8LL * g.n_rows) {   // the balanced kernel's row pieces, from the caching allocator
+    const size_t ws_bytes = hcspmm_spmm_workspace_bytes(g.n_rows, g.nnz, (int32_t)dim);
+    v.ws = torch::empty({(int64_t)ws_bytes}, input.options().dtype(torch::kUInt8));
+    v.aux.d_workspace = v.ws.data_ptr(); v.aux.workspace_bytes = ws_bytes;
+  }
+  return v;
+}
+
+// one aggregation through the C ABI
 void run_spmm(const torch::Tensor &input, const Graph &g, const torch::Tensor &row_nzr, const torch::Tensor &col_nzr,
-              float *out, int64_t ldy, int accumulate, const char *what) {
+              float *out, int64_t ldy, int accumulate, const char *what, bool bf16_stored = false) {
   const int64_t dim = input.size(1);
   auto stream = at::cuda::getCurrentCUDAStream().stream();
-  if (g_dense && row_nzr.defined() && row_nzr.device().is_cpu() && row_nzr.scalar_type() == torch::kInt32 &&
-      row_nzr.numel() >= 4 && row_nzr.data_ptr<int32_t>()[0] == kPlanMagic && col_nzr.is_cuda() &&
-      col_nzr.scalar_type() == torch::kInt32 && row_nzr.data_ptr<int32_t>()[3] == g.n_rows) {
-    const int32_t *h = row_nzr.data_ptr<int32_t>();
-    check_rc(hcspmm_spmm_plan(input.data_ptr<float>(), input.stride(0), (int32_t)input.size(0), g.rowptr, g.colidx, g.bp,
-                              g.etc, g.etr, g.ht, g.n_rows, g.nnz, (int32_t)dim, g_precision, accumulate, out, ldy,
-                              col_nzr.data_ptr<int32_t>(), h[1], h[2], stream),
-             what);
-    return;
-  }
-  check_rc(hcspmm_spmm(input.data_ptr<float>(), input.stride(0), (int32_t)input.size(0), g.rowptr, g.colidx, g.bp, g.etc,
-                       g.etr, g.ht, g.n_rows, g.nnz, (int32_t)dim, g_precision, accumulate, out, ldy, stream),
+  // a BF16-stored operand (multi-GPU exchange buffer) is passed as its raw rows; ldx counts bfloat16 elements
+  const float *xptr = reinterpret_cast<const float *>(input.data_ptr());
+  AuxView v = make_aux(input, g, row_nzr, col_nzr, dim);
+  check_rc(hcspmm_spmm_aux(xptr, input.stride(0), (int32_t)input.size(0), g.rowptr, g.colidx, g.bp, g.etc, g.etr, g.ht,
+                           g.n_rows, g.nnz, (int32_t)dim, bf16_stored ? HCSPMM_PRECISION_BF16_STORED : v.precision,
+                           accumulate, out, ldy, v.ok ? &v.aux : nullptr, stream),
            what);
 }
 
@@ -176,7 +234,7 @@ std::vector<torch::Tensor> spmm_forward(torch::Tensor input, torch::Tensor nodeP
 torch::Tensor spmm_strided(torch::Tensor input, torch::Tensor nodePointer, torch::Tensor edgeList,
                            torch::Tensor blockPartition, torch::Tensor edgeToColumn,
                            torch::Tensor edgeToRow, torch::Tensor hybrid_type, torch::Tensor out,
-                           bool accumulate) {
+                           bool accumulate, c10::optional<torch::Tensor> row_nzr, c10::optional<torch::Tensor> col_nzr) {
   TORCH_CHECK(input.is_cuda() && input.scalar_type() == torch::kFloat32 && input.dim() == 2 &&
               (input.stride(1) == 1 || input.size(1) == 1), "input must be a 2-D float32 CUDA tensor with unit column stride");
   TORCH_CHECK(out.is_cuda() && out.scalar_type() == torch::kFloat32 && out.dim() == 2 &&
@@ -186,11 +244,41 @@ torch::Tensor spmm_strided(torch::Tensor input, torch::Tensor nodePointer, torch
   TORCH_CHECK(out.size(0) == g.n_rows && out.size(1) == input.size(1), "out must be [num_nodes, dim]");
   c10::cuda::CUDAGuard guard(input.device());
   const int64_t dim = input.size(1);
-  check_rc(hcspmm_spmm(input.data_ptr<float>(), input.stride(0), (int32_t)input.size(0), g.rowptr, g.colidx, g.bp,
-                       g.etc, g.etr, g.ht, g.n_rows, g.nnz, (int32_t)dim, g_precision,
-                       accumulate ? 1 : 0, out.data_ptr<float>(), out.stride(0),
-                       at::cuda::getCurrentCUDAStream().stream()),
-           "spmm_strided");
+  (void)dim;
+  run_spmm(input, g, row_nzr.has_value() ? *row_nzr : torch::Tensor(), col_nzr.has_value() ? *col_nzr : torch::Tensor(),
+           out.data_ptr<float>(), out.stride(0), accumulate ? 1 : 0, "spmm_strided");
+  return out;
+}
+
+// out (+)= A * X for an X ALREADY stored as bfloat16 (the multi-GPU exchange operand whose halo rows travelled at
+// half the bytes): FP32 accumulate on the CUDA-core path, no conversion pass.
+torch::Tensor spmm_bf16(torch::Tensor input, torch::Tensor nodePointer, torch::Tensor edgeList,
+                        torch::Tensor blockPartition, torch::Tensor edgeToColumn, torch::Tensor edgeToRow,
+                        torch::Tensor hybrid_type, torch::Tensor out, bool accumulate,
+                        c10::optional<torch::Tensor> row_nzr, c10::optional<torch::Tensor> col_nzr) {
+  TORCH_CHECK(input.is_cuda() && input.scalar_type() == torch::kBFloat16 && input.dim() == 2 && input.stride(1) == 1,
+              "input must be a 2-D bfloat16 CUDA tensor with unit column stride");
+  TORCH_CHECK(out.is_cuda() && out.scalar_type() == torch::kFloat32 && out.dim() == 2 && out.stride(1) == 1 &&
+              out.device() == input.device(), "out must be a 2-D float32 CUDA tensor on the input's device");
+  Graph g = check_graph(input, nodePointer, edgeList, blockPartition, edgeToColumn, edgeToRow, hybrid_type, true);
+  TORCH_CHECK(out.size(0) == g.n_rows && out.size(1) == input.size(1), "out must be [num_nodes, dim]");
+  c10::cuda::CUDAGuard guard(input.device());
+  run_spmm(input, g, row_nzr.has_value() ? *row_nzr : torch::Tensor(), col_nzr.has_value() ? *col_nzr : torch::Tensor(),
+           out.data_ptr<float>(), out.stride(0), accumulate ? 1 : 0, "spmm_bf16", true);
+  return out;
+}
+
+// out[r, :] (bfloat16 view, any row pitch) = round-to-nearest-even of input[r, :]
+torch::Tensor f32_to_bf16_into(torch::Tensor input, torch::Tensor out) {
+  TORCH_CHECK(input.is_cuda() && input.scalar_type() == torch::kFloat32 && input.dim() == 2 && input.stride(1) == 1,
+              "input must be a 2-D float32 CUDA tensor with unit column stride");
+  TORCH_CHECK(out.is_cuda() && out.scalar_type() == torch::kBFloat16 && out.dim() == 2 && out.stride(1) == 1 &&
+              out.device() == input.device() && out.size(0) == input.size(0) && out.size(1) == input.size(1),
+              "out must be a bfloat16 CUDA tensor of the input's shape");
+  c10::cuda::CUDAGuard guard(input.device());
+  check_rc(hcspmm_f32_to_bf16(input.data_ptr<float>(), input.stride(0), (int32_t)input.size(0), (int32_t)input.size(1),
+                              out.data_ptr(), out.stride(0), at::cuda::getCurrentCUDAStream().stream()),
+           "f32_to_bf16");
   return out;
 }
 
@@ -211,10 +299,13 @@ std::vector<torch::Tensor> fused_impl(const torch::Tensor &input, const Graph &g
   auto w = dense_weights(weights, input);
   const int64_t dim = input.size(1), hidden = w.size(1);
   auto z = torch::empty({g.n_rows, dim}, input.options());
-  // Z = A X, then out = Z W: exactly what hcspmm_spmm_gemm does, with the plan-aware aggregation
-  run_spmm(input, g, row_nzr, col_nzr, z.data_ptr<float>(), dim, 0, what);
-  check_rc(hcspmm_gemm_tf32(z.data_ptr<float>(), dim, w.data_ptr<float>(), hidden, g.n_rows, (int32_t)dim,
-                            (int32_t)hidden, out.data_ptr<float>(), hidden, at::cuda::getCurrentCUDAStream().stream()),
+  // Z = A X and out = Z W: ONE kernel when the graph's dense plan covers it (hcspmm_spmm_gemm_aux), otherwise the
+  // plan-aware aggregation followed by the TMA Update GEMM
+  AuxView v = make_aux(input, g, row_nzr, col_nzr, dim);
+  check_rc(hcspmm_spmm_gemm_aux(input.data_ptr<float>(), input.stride(0), (int32_t)input.size(0), g.rowptr, g.colidx, g.bp,
+                                g.etc, g.etr, g.ht, g.n_rows, g.nnz, (int32_t)dim, v.precision, w.data_ptr<float>(), hidden,
+                                (int32_t)hidden, out.data_ptr<float>(), out.stride(0), z.data_ptr<float>(), dim,
+                                v.ok ? &v.aux : nullptr, at::cuda::getCurrentCUDAStream().stream()),
            what);
   return {out, z};
 }
@@ -281,7 +372,6 @@ std::string set_precision(const std::string &mode) {
 bool set_dense(bool on) {
   bool old = g_dense;
   g_dense = on;
-  hcspmm_set_tuning("umma", on ? 1 : 0);
   return old;
 }
 
@@ -293,8 +383,7 @@ bool set_bug_compat(bool on) {
 
 int64_t set_tuning(const std::string &key, int64_t value) {
   int old = hcspmm_set_tuning(key.c_str(), (int)value);
-  TORCH_CHECK(old != -1 || key == "slab" || key == "long_row" || key == "vec8" || key == "short_row" || key == "wpc" || key == "umma" || key == "pad_odd" || key == "umma_gemm" || key == "dense_ws" || key == "occupancy3" || key == "balance" || key == "chunk" || key == "warp_split" || key == "pull_ctas",
-              "unknown tuning key '", key, "'");
+  TORCH_CHECK(old != -1, "unknown tuning key '", key, "'");
   return old;
 }
 
@@ -323,8 +412,15 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("backward_final_fused_64", &spmm_forward_final_fused, "HCSPMM SPMM backward final fused 64 (CUDA)");
   m.def("backward_GIN_final_fused", &spmm_forward_fused, "HCSPMM SPMM backward for GIN final fused (CUDA)");
   // additions (not in the reference)
-  m.def("spmm_strided", &spmm_strided, "out (+)= A @ input; input / out may be row-strided views");
-  m.def("spmm_accumulate", &spmm_strided, "alias of spmm_strided");
+  m.def("spmm_strided", &spmm_strided, "out (+)= A @ input; input / out may be row-strided views",
+        pybind11::arg("input"), pybind11::arg("nodePointer"), pybind11::arg("edgeList"), pybind11::arg("blockPartition"),
+        pybind11::arg("edgeToColumn"), pybind11::arg("edgeToRow"), pybind11::arg("hybrid_type"), pybind11::arg("out"),
+        pybind11::arg("accumulate"), pybind11::arg("row_nzr") = pybind11::none(), pybind11::arg("col_nzr") = pybind11::none());
+  m.def("spmm_bf16", &spmm_bf16, "out (+)= A @ input for a bfloat16-stored input (exchange operand)",
+        pybind11::arg("input"), pybind11::arg("nodePointer"), pybind11::arg("edgeList"), pybind11::arg("blockPartition"),
+        pybind11::arg("edgeToColumn"), pybind11::arg("edgeToRow"), pybind11::arg("hybrid_type"), pybind11::arg("out"),
+        pybind11::arg("accumulate"), pybind11::arg("row_nzr") = pybind11::none(), pybind11::arg("col_nzr") = pybind11::none());
+  m.def("f32_to_bf16_into", &f32_to_bf16_into, "out (bfloat16 view) = RNE(input)");
   m.def("gemm_tf32", &gemm_tf32, "a @ b with TF32 tensor-core product");
   m.def("set_classifier", &set_classifier, "shipped | intended | b200 | all_cuda | all_tc; returns the previous mode");
   m.def("set_precision", &set_precision, "tf32 | tf32x2 | fp32 | bf16; returns the previous mode");

@@ -235,6 +235,10 @@ update_gemm_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
   if (wid == 1) umma::tmem_dealloc(tmem_base, 2u * (uint32_t)p.acc_cols);
 }
 
+void launch_update_gemm_wt(const float *w, int64_t ldw, int k, int n, int k_pad, int n_pad, float *wt, cudaStream_t stream) {
+  update_gemm_wt_kernel<<<(k_pad * n_pad + 255) / 256, 256, 0, stream>>>(w, ldw, k, n, k_pad, n_pad, wt);
+}
+
 // ---- host side -------------------------------------------------------------------------------------
 static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -250,9 +254,11 @@ static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
   return fn;
 }
 
-// 2-D FP32 tensor [rows][cols], row pitch ld floats; box = box_rows x box_cols (box_cols * 4 <= 128 when swizzled)
+// 2-D FP32 tensor [rows][cols], row pitch ld floats; box = box_rows x box_cols (box_cols * 4 <= 128 when swizzled).
+// swizzle: 0 none, 1 = SWIZZLE_128B (16-byte atoms: K-major tcgen05 operands), 2 = SWIZZLE_128B_ATOM_32B (the
+// MN-major 32-bit operand layout, tcgen05 "SWIZZLE_128B_BASE32B").  tf32_type: the TMA unit converts FP32 -> TF32.
 bool make_tensor_map_2d(CUtensorMap *map, const void *base, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_cols,
-                        uint32_t box_rows, int swizzle128, int tf32_type) {
+                        uint32_t box_rows, int swizzle, int tf32_type) {
   PFN_cuTensorMapEncodeTiled_v12000 enc = tensor_map_encoder();
   if (!enc) return false;
   cuuint64_t dims[2] = {cols, rows};
@@ -261,7 +267,8 @@ bool make_tensor_map_2d(CUtensorMap *map, const void *base, uint64_t cols, uint6
   cuuint32_t estr[2] = {1, 1};
   const CUresult r = enc(map, tf32_type ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                          const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                         swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                      : (swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_NONE),
                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }

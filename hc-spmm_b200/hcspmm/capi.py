@@ -15,7 +15,7 @@ from .build import LIB_PATH
 
 BLK_H, BLK_W = 16, 8
 CLASSIFIERS = {"shipped": 0, "intended": 1, "b200": 2, "all_cuda": 3, "all_tc": 4}
-PRECISIONS = {"tf32": 0, "tf32x2": 1, "fp32": 2, "bf16": 3}
+PRECISIONS = {"tf32": 0, "tf32x2": 1, "fp32": 2, "bf16": 3, "bf16_stored": 4}
 
 EXPORTS = [
     "hcspmm_version", "hcspmm_last_error", "hcspmm_set_tuning",
@@ -25,6 +25,8 @@ EXPORTS = [
     "hcspmm_graph_get_preprocess", "hcspmm_graph_destroy",
     "hcspmm_peer_alloc", "hcspmm_peer_open", "hcspmm_peer_close", "hcspmm_peer_free", "hcspmm_peer_barrier",
     "hcspmm_halo_pull", "hcspmm_debug_l2_gather",
+    "hcspmm_merge_path_count", "hcspmm_merge_path_splits", "hcspmm_spmm_workspace_bytes", "hcspmm_spmm_aux",
+    "hcspmm_f32_to_bf16", "hcspmm_spmm_gemm_aux",
 ]
 
 _lib = None
@@ -34,6 +36,13 @@ _vp, _i32, _i64, _int, _sz = (ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, c
 
 class HcspmmError(RuntimeError):
     pass
+
+
+class Aux(ctypes.Structure):
+    """hcspmm_aux_t (include/hcspmm.h): per-graph products handed to every aggregation."""
+    _fields_ = [("d_splits", ctypes.c_void_p), ("splits_chunk", ctypes.c_int32), ("n_splits", ctypes.c_int32),
+                ("n_tc_windows", ctypes.c_int32), ("d_plan", ctypes.c_void_p), ("n_dense", ctypes.c_int32),
+                ("plan_full", ctypes.c_int32), ("total_cols", ctypes.c_int64), ("d_workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t)]
 
 
 def lib() -> ctypes.CDLL:
@@ -77,6 +86,16 @@ def lib() -> ctypes.CDLL:
         L.hcspmm_peer_barrier.argtypes = [_vp, _i32, _i32, _i32, _vp, _vp]
         L.hcspmm_halo_pull.argtypes = [_vp, _i64, _vp, _vp, _i32, ctypes.c_uint64, _i32, _i32, _i32, _i32, _vp, _i64, _vp]
         L.hcspmm_debug_l2_gather.argtypes = [_vp, _i32, _i32, _i32, _i32, _vp, _vp]
+        L.hcspmm_merge_path_count.restype = _sz
+        L.hcspmm_merge_path_count.argtypes = [_i32, _i64, _i32]
+        L.hcspmm_merge_path_splits.argtypes = [_vp, _i32, _i64, _i32, _vp, _vp]
+        L.hcspmm_spmm_workspace_bytes.restype = _sz
+        L.hcspmm_spmm_workspace_bytes.argtypes = [_i32, _i64, _i32]
+        L.hcspmm_spmm_aux.argtypes = [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _int, _int,
+                                      _vp, _i64, ctypes.POINTER(Aux), _vp]
+        L.hcspmm_f32_to_bf16.argtypes = [_vp, _i64, _i32, _i32, _vp, _i64, _vp]
+        L.hcspmm_spmm_gemm_aux.argtypes = [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _int, _vp, _i64,
+                                           _i32, _vp, _i64, _vp, _i64, ctypes.POINTER(Aux), _vp]
         _lib = L
     return _lib
 
@@ -136,6 +155,86 @@ def spmm(x: torch.Tensor, rowptr, colidx, bp=None, etc=None, etr=None, ht=None, 
                                  _ptr(etc), _ptr(etr), _ptr(ht), n, colidx.numel(), d, prec,
                                  1 if accumulate else 0, _ptr(out), out.stride(0), _stream(x)),
                "hcspmm_spmm")
+    return out
+
+
+SPLITS_CHUNK = 4096      # HCSPMM_SPLITS_CHUNK
+
+
+class GraphAux:
+    """The per-graph products of hcspmm_aux_t for a device CSR: merge-path split points (computed once), the count of
+    windows labelled 1 and a reusable workspace -- what HCSPMM.preprocess() packs into its two opaque tensors."""
+
+    def __init__(self, rowptr: torch.Tensor, colidx: torch.Tensor, ht: torch.Tensor | None = None, plan=None):
+        n, nnz = rowptr.numel() - 1, colidx.numel()
+        self.n, self.nnz = n, nnz
+        with torch.cuda.device(rowptr.device):
+            cnt = lib().hcspmm_merge_path_count(n, nnz, SPLITS_CHUNK)
+            self.splits = torch.empty(cnt, dtype=torch.int32, device=rowptr.device)
+            _check(lib().hcspmm_merge_path_splits(_ptr(rowptr), n, nnz, SPLITS_CHUNK, _ptr(self.splits), _stream(rowptr)),
+                   "hcspmm_merge_path_splits")
+        self.n_tc = int((ht == 1).sum()) if ht is not None else -1
+        self.plan = plan
+        self.plan_full = 0
+        if plan is not None and plan.n_dense > 0:        # does the plan cover every super-window that has entries?
+            edges = torch.arange(0, n + 128, 128, device=rowptr.device).clamp_(max=n)
+            self.plan_full = int(int((rowptr[edges[1:]] > rowptr[edges[:-1]]).sum()) == plan.n_dense)
+        self._ws = {}
+
+    def struct(self, dim: int, device) -> Aux:
+        if dim not in self._ws:
+            nbytes = lib().hcspmm_spmm_workspace_bytes(self.n, self.nnz, dim)
+            self._ws[dim] = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        ws = self._ws[dim]
+        a = Aux()
+        a.d_splits, a.splits_chunk, a.n_splits = self.splits.data_ptr(), SPLITS_CHUNK, self.splits.numel() - 1
+        a.n_tc_windows = self.n_tc
+        if self.plan is not None:
+            a.d_plan, a.n_dense, a.total_cols = self.plan.plan.data_ptr(), self.plan.n_dense, self.plan.total_cols
+            a.plan_full = self.plan_full
+        a.d_workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        return a
+
+
+def spmm_aux(x: torch.Tensor, rowptr, colidx, bp, etc, etr, ht, aux: GraphAux, precision="tf32",
+             out: torch.Tensor | None = None, accumulate: bool = False):
+    """hcspmm_spmm_aux on device tensors (x: FP32, or bfloat16 with precision "bf16_stored")."""
+    n, d = rowptr.numel() - 1, x.shape[1]
+    if out is None:
+        out = torch.empty((n, d), dtype=torch.float32, device=x.device)
+    prec = PRECISIONS[precision] if isinstance(precision, str) else int(precision)
+    a = aux.struct(d, x.device)
+    with torch.cuda.device(x.device):
+        _check(lib().hcspmm_spmm_aux(_ptr(x), x.stride(0), x.shape[0], _ptr(rowptr), _ptr(colidx), _ptr(bp), _ptr(etc),
+                                     _ptr(etr), _ptr(ht), n, colidx.numel(), d, prec, 1 if accumulate else 0, _ptr(out),
+                                     out.stride(0), ctypes.byref(a), _stream(x)),
+               "hcspmm_spmm_aux")
+    return out
+
+
+def spmm_gemm_aux(x, rowptr, colidx, bp, etc, etr, ht, w: torch.Tensor, aux: GraphAux, precision="tf32"):
+    """hcspmm_spmm_gemm_aux -> (out [n, hidden], z [n, dim]); one fused kernel when the dense plan covers the graph."""
+    assert x.is_cuda and x.is_contiguous() and w.is_cuda and w.is_contiguous()
+    n, d, h = rowptr.numel() - 1, x.shape[1], w.shape[1]
+    out = torch.empty((n, h), dtype=torch.float32, device=x.device)
+    z = torch.empty((n, d), dtype=torch.float32, device=x.device)
+    prec = PRECISIONS[precision] if isinstance(precision, str) else int(precision)
+    a = aux.struct(d, x.device)
+    with torch.cuda.device(x.device):
+        _check(lib().hcspmm_spmm_gemm_aux(_ptr(x), d, x.shape[0], _ptr(rowptr), _ptr(colidx), _ptr(bp), _ptr(etc),
+                                          _ptr(etr), _ptr(ht), n, colidx.numel(), d, prec, _ptr(w), h, h,
+                                          _ptr(out), h, _ptr(z), d, ctypes.byref(a), _stream(x)),
+               "hcspmm_spmm_gemm_aux")
+    return out, z
+
+
+def f32_to_bf16(x: torch.Tensor, out: torch.Tensor | None = None):
+    """hcspmm_f32_to_bf16: round-to-nearest-even copy of FP32 rows into a bfloat16 tensor (any row pitch)."""
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _check(lib().hcspmm_f32_to_bf16(_ptr(x), x.stride(0), x.shape[0], x.shape[1], _ptr(out), out.stride(0),
+                                        _stream(x)), "hcspmm_f32_to_bf16")
     return out
 
 

@@ -50,9 +50,13 @@ def _default_spmm():
     import HCSPMM
 
     def run(x, rowptr, colidx, pre, out=None, accumulate=False):
+        if x.dtype == torch.bfloat16:            # BF16-stored exchange operand
+            if out is None:
+                out = torch.empty(rowptr.numel() - 1, x.shape[1], device=x.device)
+            return HCSPMM.spmm_bf16(x, rowptr, colidx, *pre[:4], out, accumulate, *pre[4:6])
         if out is None:
             return HCSPMM.forward(x, rowptr, colidx, *pre)[0]
-        return HCSPMM.spmm_strided(x, rowptr, colidx, *pre[:4], out, accumulate)
+        return HCSPMM.spmm_strided(x, rowptr, colidx, *pre[:4], out, accumulate, *pre[4:6])
 
     def prep(colidx, rowptr):
         n = rowptr.numel() - 1
@@ -63,13 +67,20 @@ def _default_spmm():
 
 class ShardedGraph:
     def __init__(self, rowptr: torch.Tensor, colidx: torch.Tensor, group=None, schedule: str = "gather",
-                 n_slabs: int = 1, spmm=None, preprocess=None, cuts=None, n_passes: int = 1):
+                 n_slabs: int = 1, spmm=None, preprocess=None, cuts=None, n_passes: int = 1,
+                 operand: str = "fp32"):
         """rowptr / colidx: the FULL graph's CSR on this rank's device (identical on every rank).
         cuts: reuse another ShardedGraph's row cuts (the transposed graph for backward must be
         partitioned like the forward one).
         n_passes = 2 ("peer" schedule only): the shard is cut by SOURCE into two CSRs -- own rows + the nearer half
         of the owners, and the farther half -- and aggregated in two accumulating SpMM passes, the second
-        half of the pull travelling (few CTAs, high-priority stream) while the first pass computes."""
+        half of the pull travelling (few CTAs, high-priority stream) while the first pass computes.
+        operand = "bf16" ("peer" schedule, widths that are multiples of 8): the exchange operand is stored as
+        bfloat16 -- every rank rounds its own rows once (RNE), the halo travels at half the bytes and the local
+        SpMM gathers bfloat16 rows with FP32 accumulation: the BF16 precision mode of the single-GPU path
+        (north star: 1e-2 against FP32), end to end.  "fp32" (default) is exact."""
+        assert operand in ("fp32", "bf16")
+        self.operand = operand
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -166,6 +177,7 @@ class ShardedGraph:
         if self.world == 1:
             return self._spmm(x_local.contiguous(), self.rowptr, self.colidx, self.pre)
         if self.peer is not None:
+            self.peer.check()            # pinned-host flag, no synchronisation: a barrier of an EARLIER step timed out
             return self._aggregate_peer(x_local)
         if self.halo is not None:
             return self._aggregate_halo(x_local)
@@ -189,7 +201,7 @@ class ShardedGraph:
         if self.peer is not None:
             cat, dpad = self._peer_stage(x_local)
             self._pull_halo(cat, dpad)
-            return cat if dpad == dim else cat[:, :dim]
+            return cat if dpad == dim else cat[:, :dim]   # bfloat16 rows when operand = "bf16"
         if self.halo is not None:
             h = self.halo
             key = ("halo", dim, dev, dt)
@@ -214,7 +226,8 @@ class ShardedGraph:
     def check(self):
         """Raise if a peer barrier ever timed out (a rank did not reach an exchange): results would be stale."""
         if self.peer is not None:                                # collective: every rank raises, or none does
-            flag = self.peer.err.clone()
+            torch.cuda.synchronize(self.peer.device)
+            flag = self.peer.err.to(self.peer.device)
             dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
             if int(flag.item()) != 0:
                 raise RuntimeError("peer barrier timed out on some rank: a rank did not reach an exchange")
@@ -246,10 +259,13 @@ class ShardedGraph:
 
     def _peer_stage(self, x_local: torch.Tensor):
         """Write the shard into the own-rows segment of this width's next operand buffer (peer-visible) and pass
-        the barrier: afterwards every rank's shard of this aggregation can be pulled.  -> (operand, padded width)."""
+        the barrier: afterwards every rank's shard of this aggregation can be pulled.  -> (operand, padded width).
+        With operand = "bf16" (and a width that is a multiple of 8) the buffer holds bfloat16 rows."""
         dim, dev = x_local.shape[1], x_local.device
-        dpad = (dim + 7) // 8 * 8                                 # 32-byte rows: the 256-bit gather path
-        key = ("peer", dpad)
+        b16 = self.operand == "bf16" and dim % 8 == 0
+        dpad = dim if b16 else (dim + 7) // 8 * 8                 # 32-byte FP32 rows: the 256-bit gather path
+        esz = 2 if b16 else 4
+        key = ("peer", dpad, b16)
         h = self.halo
         if key not in self._bufs:
             pm, slots = self.peer, []
@@ -257,26 +273,39 @@ class ShardedGraph:
             firsts = [None] * self.world                         # every rank's own-segment offset in ITS operand
             dist.all_gather_object(firsts, own0, group=self.group)
             for _ in range(2):                                   # alternate: see csrc/peer.cu header
-                ptr, ptrs = pm.shared(h["rows"] * dpad * 4)
-                table = torch.tensor([p + f * dpad * 4 for p, f in zip(ptrs, firsts)], dtype=torch.int64, device=dev)
-                slots.append((pm.tensor(ptr, (h["rows"], dpad)), table))
+                ptr, ptrs = pm.shared(h["rows"] * dpad * esz)
+                table = torch.tensor([p + f * dpad * esz for p, f in zip(ptrs, firsts)], dtype=torch.int64, device=dev)
+                t = pm.tensor(ptr, (h["rows"], dpad), torch.int16).view(torch.bfloat16) if b16 else \
+                    pm.tensor(ptr, (h["rows"], dpad))
+                slots.append((t, table))
             self._bufs[key] = dict(slots=slots, turn=0, own0=own0)
         b = self._bufs[key]
         cat, self._peer_tab = b["slots"][b["turn"]]
         b["turn"] ^= 1
-        cat[b["own0"]: b["own0"] + self.n_local, :dim].copy_(x_local)     # pad columns stay zero
+        own = cat[b["own0"]: b["own0"] + self.n_local]
+        if b16:
+            import HCSPMM
+            HCSPMM.f32_to_bf16_into(x_local, own)                # one rounding per row, on its owner
+        else:
+            own[:, :dim].copy_(x_local)                          # pad columns stay zero
         self.peer.barrier()
         return cat, dpad
 
     def _pull_halo(self, cat, dpad, col0=0, width=None, mask=None):
         h = self.halo                                            # own rows are already in place: own bit clear
         mask = (((1 << self.world) - 1) & ~(1 << self.rank)) if mask is None else mask
+        if cat.dtype == torch.bfloat16:                          # the pull moves bytes: count a row in float units
+            assert col0 % 2 == 0 and (width is None or width % 2 == 0)
+            raw = cat.view(torch.float32)
+            self._pull(self._peer_tab, dpad // 2, h["src_row"], h["seg"], self.world, raw, col0 // 2,
+                       None if width is None else width // 2, mask, self.rank + 1)
+            return
         self._pull(self._peer_tab, dpad, h["src_row"], h["seg"], self.world, cat, col0, width, mask, self.rank + 1)
 
     def _aggregate_peer(self, x_local: torch.Tensor) -> torch.Tensor:
         dim, dev = x_local.shape[1], x_local.device
         cat, dpad = self._peer_stage(x_local.float())
-        n_slabs = self.n_slabs if dpad >= 32 * self.n_slabs else 1
+        n_slabs = self.n_slabs if (dpad >= 32 * self.n_slabs and cat.dtype == torch.float32) else 1
         if self.passes is not None:
             p0, p1 = self.passes
             y = torch.empty(self.n_local, dpad, device=dev)

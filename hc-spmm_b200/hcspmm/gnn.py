@@ -19,6 +19,7 @@ reference, all deliberate:
 from __future__ import annotations
 
 import time
+import weakref
 from dataclasses import dataclass
 from typing import Optional
 
@@ -65,6 +66,7 @@ def prepare(row_pointers: torch.Tensor, column_index: torch.Tensor, symmetric: b
         t_rp[1:] = torch.cumsum(cnt, 0)
         t_rp = t_rp.to(torch.int32)
         g.t = Graph(t_rp, t_cols, *HCSPMM.preprocess(t_cols, t_rp, n, nnz, (n + 15) // 16))
+        use_transpose(g)          # a directed graph must never backpropagate through A
     return g
 
 
@@ -85,18 +87,28 @@ _ROUTES = {
     "HCSPMMFunction_GINFinal":   ("post", "forward_GIN_final_fused", None, "forward_fixed32"),
 }
 
-_BACKWARD_GRAPH = {}   # id(row_pointers) -> transposed Graph, registered by use_transpose()
+# row_pointers address -> (weak reference to that row_pointers tensor, transposed Graph).  The reference's call
+# signature has no slot for A^T, so the Functions find it through the forward graph's row_pointers; the weak
+# reference ties an entry to the LIFETIME of that tensor: once the graph is freed the entry is dead, and an
+# unrelated graph the caching allocator later places at the same address never inherits a stale A^T.
+_BACKWARD_GRAPH = {}
 
 
 def use_transpose(g: Graph) -> None:
-    """Make every Function aggregate with g.t in backward for graphs whose row_pointers is g's."""
+    """Make every Function aggregate with g.t in backward for the graph whose row_pointers is g's
+    (prepare(symmetric=False) does this itself)."""
     if g.t is not None:
-        _BACKWARD_GRAPH[g.row_pointers.data_ptr()] = g.t
+        key = g.row_pointers.data_ptr()
+        _BACKWARD_GRAPH[key] = (weakref.ref(g.row_pointers, lambda _r, k=key: _BACKWARD_GRAPH.pop(k, None)), g.t)
 
 
 def _bwd_args(gt):
-    t = _BACKWARD_GRAPH.get(gt[0].data_ptr())
-    return t.args() if t is not None else gt
+    hit = _BACKWARD_GRAPH.get(gt[0].data_ptr())
+    if hit is not None:
+        owner = hit[0]()
+        if owner is not None and owner.data_ptr() == gt[0].data_ptr() and owner.numel() == gt[0].numel():
+            return hit[1].args()
+    return gt
 
 
 def _make_function(name: str):

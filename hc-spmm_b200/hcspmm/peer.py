@@ -32,7 +32,10 @@ class PeerMemory:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self._owned, self._opened = [], []
         self.epoch = 0
-        self.err = torch.zeros(1, dtype=torch.int32, device=device)
+        # timeout flag of the barrier kernel in PINNED HOST memory (device-visible at the same address under UVA):
+        # the kernel writes it, check() reads it with a plain load -- no synchronisation, so it is tested at every
+        # aggregation (hcspmm.dist) and a timed-out barrier stops the job instead of training on stale rows
+        self.err = torch.zeros(1, dtype=torch.int32).pin_memory()
         _, self._flag_ptrs = self.shared(max(64, self.world) * 4)
         self.flag_table = torch.tensor(self._flag_ptrs, dtype=torch.int64, device=device)
 
@@ -72,7 +75,7 @@ class PeerMemory:
         return ptr.value, ptrs
 
     def tensor(self, ptr: int, shape, dtype=torch.float32) -> torch.Tensor:
-        typestr = {torch.float32: "<f4", torch.int32: "<i4"}[dtype]
+        typestr = {torch.float32: "<f4", torch.int32: "<i4", torch.int16: "<i2"}[dtype]
         return torch.as_tensor(_Raw(ptr, shape, typestr), device=self.device)
 
     def barrier(self):
@@ -85,8 +88,9 @@ class PeerMemory:
                         "hcspmm_peer_barrier")
 
     def check(self):
-        if int(self.err.item()) != 0:
-            raise capi.HcspmmError("peer barrier timed out: a rank did not reach the exchange")
+        v = int(self.err[0])
+        if v != 0:
+            raise capi.HcspmmError(f"peer barrier timed out waiting for rank {v - 1}: results since then are undefined")
 
     def close(self):
         L = capi.lib()

@@ -63,6 +63,10 @@ extern "C" {
  *            dominant stream -- and accumulated in FP32 on the CUDA-core path for every window
  *            (north star: 1e-2 against FP32 torch.sparse).  Needs dim % 8 == 0, else computed in FP32. */
 #define HCSPMM_PRECISION_BF16    3
+/*   BF16_STORED : as BF16, but d_x ALREADY holds bfloat16 rows (ldx counted in bfloat16 elements; dim and ldx
+ *            multiples of 8, 16-byte aligned): the operand of a multi-GPU aggregation whose halo rows travelled
+ *            as bfloat16 (hcspmm_f32_to_bf16 writes a rank's own rows into it).  No conversion pass.           */
+#define HCSPMM_PRECISION_BF16_STORED 4
 
 int hcspmm_version(void);
 const char *hcspmm_last_error(void);
@@ -80,9 +84,13 @@ const char *hcspmm_last_error(void);
  *   "umma"       1: tcgen05 / TMEM dense super-window kernel (hcspmm_spmm_plan); 0: per-window paths
  *   "umma_gemm"  Update GEMM kernel: 2 = TMA + tcgen05 persistent warp-specialised kernel, 1 = register-staged
  *                tcgen05 kernel, 0 = mma.sync kernel (also the fallback for unaligned operands)
+ *   "dense_tma"  1 (default): dense super-windows on the TMA gather4 + tcgen05 kernel (csrc/dense_tma.cu: no rounded
+ *                copy of X, optional fused Update); 0: the cp.async kernels of csrc/dense.cu
+ *   "fuse_update" 1 (default): hcspmm_spmm_gemm_aux fuses the Update product when the plan covers the graph
  *   "gemm_round" TMA Update GEMM: 1 (default) rounder warps apply cvt.rna.tf32 to the landed Z boxes (the
  *                reference's rounding); 0 = the tensor map's TF32 element type converts on load
  *   "gemm_stages" cap on the TMA Update GEMM's shared-memory ring depth (0 = as many stages as fit)
+ *   "barrier_timeout_ms" how long hcspmm_peer_barrier waits for a peer (default 10000) before it sets *d_err
  *   "pool_keep_mb" megabytes of freed scratch the library's private stream-ordered pool keeps mapped
  *   "balance"    CUDA-core windows on the merge-path balanced kernel (equal rows + stored entries per
  *                CTA, hub rows cut into pieces that are summed in a fixed order): 1 (default) when the
@@ -183,7 +191,9 @@ int hcspmm_spmm_plan(const float *d_x, int64_t ldx, int32_t x_rows, const int32_
  *                                        splits_chunk); HCSPMM_SPLITS_CHUNK serves both default item sizes),
  *                                        from hcspmm_merge_path_splits; NULL = recomputed per call
  *   n_tc_windows                         number of windows labelled 1 (0 skips the mma.sync launch; -1 unknown)
- *   d_plan / n_dense / total_cols        dense super-window plan (hcspmm_dense_plan_fill) or NULL
+ *   d_plan / n_dense / total_cols        dense super-window plan (hcspmm_dense_plan_fill) or NULL; plan_full = 1 when
+ *                                        the plan covers every row that has stored entries (then the fused entry
+ *                                        point below runs Aggregation + Update as ONE kernel)
  *   d_workspace / workspace_bytes        >= hcspmm_spmm_workspace_bytes() bytes, 16-byte aligned, for the row
  *                                        pieces of the balanced kernel; NULL = the library's private pool
  * hcspmm_spmm_aux(..., NULL, ...) is hcspmm_spmm.                                                              */
@@ -194,6 +204,7 @@ typedef struct {
   int32_t n_tc_windows;
   const int32_t *d_plan;
   int32_t n_dense;
+  int32_t plan_full;     /* 1: every row with stored entries lies in a dense super-window of the plan */
   int64_t total_cols;
   void *d_workspace;
   size_t workspace_bytes;
@@ -207,6 +218,18 @@ int hcspmm_spmm_aux(const float *d_x, int64_t ldx, int32_t x_rows, const int32_t
                     const int32_t *d_edge_to_column, const int32_t *d_edge_to_row,
                     const int32_t *d_hybrid_type, int32_t n_rows, int64_t nnz, int32_t dim,
                     int precision, int accumulate, float *d_y, int64_t ldy, const hcspmm_aux_t *aux, void *stream);
+
+/* hcspmm_spmm_gemm with the graph's products.  When the dense plan covers the whole graph (plan_full), dim is a
+ * multiple of 16 <= 256, hidden <= 256 and precision is TF32, Z = A X and out = Z W are ONE kernel
+ * (csrc/dense_tma.cu): the aggregate of a 128-row super-window stays in tensor memory, is rounded there and is the
+ * A operand of the Update tcgen05.mma -- the reference's fusion (hybrid_all_kernel.cu:1809-1837) at tcgen05 tile
+ * size.  Otherwise: aggregation (plan-aware), then the TMA Update GEMM.  Knobs: "dense_tma", "fuse_update".     */
+int hcspmm_spmm_gemm_aux(const float *d_x, int64_t ldx, int32_t x_rows, const int32_t *d_rowptr,
+                         const int32_t *d_colidx, const int32_t *d_block_partition,
+                         const int32_t *d_edge_to_column, const int32_t *d_edge_to_row,
+                         const int32_t *d_hybrid_type, int32_t n_rows, int64_t nnz, int32_t dim,
+                         int precision, const float *d_w, int64_t ldw, int32_t hidden,
+                         float *d_out, int64_t ldo, float *d_z, int64_t ldz, const hcspmm_aux_t *aux, void *stream);
 
 /* 1 if a tcgen05 kernel reported a barrier timeout since the last call (synchronises the device),
  * 0 if not, -1 on error.  Debug / test aid.                                              */
@@ -246,7 +269,10 @@ int hcspmm_loa_reorder(const int32_t *d_rowptr, const int32_t *d_colidx, const i
  *   hcspmm_peer_close / hcspmm_peer_free
  *   hcspmm_peer_barrier  stream-ordered barrier across the ranks: d_flag_ptrs[s] is rank s's int32[world]
  *                        flag array (peer-mapped); epoch must increase by one per call on every rank.
- *                        A peer that does not arrive within ~10 s sets *d_err = 1 instead of hanging.
+ *                        A peer that does not arrive within "barrier_timeout_ms" sets *d_err = 1 + that peer's
+ *                        rank instead of hanging; d_err may be pinned host memory (the host then sees it
+ *                        without a synchronisation).  Everything computed after a timed-out barrier is
+ *                        UNDEFINED: callers must check *d_err and stop.
  *   hcspmm_halo_pull     d_dst[i, col0 .. col0+width) = d_peer_x[s][d_src_row[i], col0 .. col0+width) for the
  *                        operand rows i in [d_seg[s], d_seg[s+1]) of every owner s whose bit is set in
  *                        owner_mask (the caller leaves its own bit clear: its rows are written in place).
@@ -264,6 +290,10 @@ int hcspmm_peer_barrier(int32_t *const *d_flag_ptrs, int32_t rank, int32_t world
 int hcspmm_halo_pull(const float *const *d_peer_x, int64_t lds, const int32_t *d_src_row, const int32_t *d_seg,
                      int32_t world, uint64_t owner_mask, int32_t first_owner, int32_t rows, int32_t col0, int32_t width,
                      float *d_dst, int64_t ldd, void *stream);
+
+/* d_out[r, 0..dim) (bfloat16, row pitch ld_out elements) = round-to-nearest-even of d_x[r, 0..dim). */
+int hcspmm_f32_to_bf16(const float *d_x, int64_t ldx, int32_t rows, int32_t dim, void *d_out, int64_t ld_out,
+                       void *stream);
 
 /* ---- host-buffer convenience (what a non-torch caller binds) ----------------------
  * A graph handle owns device copies of the CSR and of the preprocessing products.

@@ -64,7 +64,9 @@ def test_preprocess_and_forward_like_gnn_model(H, name):
     rp, ci = GRAPHS[name]
     n = rp.size - 1
     pre = prep(H, rp, ci)
-    assert len(pre) == 6 and all(t.dtype == torch.int32 and t.is_cuda for t in pre)
+    assert len(pre) == 6 and all(t.dtype == torch.int32 for t in pre)
+    # the four reference arrays and the per-graph blob live on the device; row_nzr is the HOST header of the blob
+    assert all(t.is_cuda for t in pre[:4]) and pre[5].is_cuda and not pre[4].is_cuda
     want = oracle.preprocess(ci, rp, oracle.MODE_SHIPPED)
     for got, w in zip(pre[:4], want):
         assert np.array_equal(got.cpu().numpy(), w)
@@ -214,14 +216,15 @@ def test_reference_fused_matches(H, REF):
 
 
 def test_dense_plan_travels_in_row_nzr_col_nzr(H):
-    """set_dense(True): preprocess() returns the tcgen05 dense plan in the two opaque tensors, forward*()
-    picks it up; with set_dense(False) the same tensors are ignored (per-window paths)."""
+    """set_dense(True): preprocess() returns the tcgen05 dense plan in the two opaque tensors and forward*() picks it
+    up.  The setting is recorded PER GRAPH at preprocess time: flipping the default afterwards changes nothing for
+    this graph, and a graph preprocessed with the default off carries no plan."""
     rp, ci = GRAPHS["sbm_1024"]
     n = 1024
     H.set_dense(True)
     try:
         pre = prep(H, rp, ci, "all_tc")
-        assert pre[4].device.type == "cpu" and int(pre[4][1]) == 8 and pre[5].numel() > 16
+        assert pre[4].device.type == "cpu" and int(pre[4][1]) == 8 and int(pre[4][6]) == 1 and pre[5].numel() > 16
         g = torch.Generator().manual_seed(7)
         x, w = torch.randn(n, 64, generator=g), torch.randn(64, 32, generator=g)
         tf32 = oracle.spmm(rp, ci, oracle.tf32_round(x.numpy()), precision=1)
@@ -232,8 +235,12 @@ def test_dense_plan_travels_in_row_nzr_col_nzr(H):
         assert rel_fro(o2.cpu().numpy(), oracle.gemm(tf32, w.numpy(), tf32=True)) <= 1e-4
         # shipped selector: no tensor-core windows, hence no plan
         pre0 = prep(H, rp, ci, "shipped")
-        assert pre0[4].is_cuda and pre0[5].numel() == 1
+        assert int(pre0[4][1]) == 0 and int(pre0[4][7]) == 0        # no dense groups, no label-1 windows
     finally:
         H.set_dense(False)
-    out = H.forward(x.cuda(), dev(rp), dev(ci), *pre)[0]      # plan present but the path is switched off
+    out = H.forward(x.cuda(), dev(rp), dev(ci), *pre)[0]      # this graph keeps the plan it was preprocessed with
+    assert rel_fro(out.cpu().numpy(), tf32) <= 2e-5
+    pre1 = prep(H, rp, ci, "all_tc")                            # default off again: no plan, per-window tensor-core path
+    assert int(pre1[4][1]) == 0 and int(pre1[4][6]) == 0
+    out = H.forward(x.cuda(), dev(rp), dev(ci), *pre1)[0]
     assert rel_fro(out.cpu().numpy(), tf32) <= 2e-5

@@ -324,6 +324,55 @@ def test_gemm_tcgen05(capi, m, k, n):
     assert rel_fro(got, oracle.gemm(a, b, tf32=True)) <= 1e-4
 
 
+# ---- per-graph products (hcspmm_aux_t) and the BF16-stored operand ------------------------------
+@pytest.mark.parametrize("name", ["rmat_1000", "rmat_hub_4096", "dense_2048", "holes_777", "rect_72x100000"])
+@pytest.mark.parametrize("dim", [64, 256])
+def test_spmm_aux_is_the_same_computation(capi, name, dim):
+    """Precomputed merge-path split points (base chunk 4096, read with stride 1 at dim 256 and stride 2 at dim 64) and
+    a caller workspace change nothing: bit-identical to hcspmm_spmm, and within FP32 tolerance of the oracle."""
+    rp, ci = GRAPHS[name]
+    x_rows = 100000 if name.startswith("rect") else rp.size - 1
+    x = xmat(x_rows, dim, seed=5)
+    pre = capi.preprocess(dev(ci), dev(rp), "shipped")
+    old = capi.set_tuning("balance", 2)
+    try:
+        plain = capi.spmm(dev(x), dev(rp), dev(ci), *pre)
+        aux = capi.GraphAux(dev(rp), dev(ci), pre[3])
+        assert aux.n_tc == int((pre[3] == 1).sum())
+        got = capi.spmm_aux(dev(x), dev(rp), dev(ci), *pre, aux)
+        again = capi.spmm_aux(dev(x), dev(rp), dev(ci), *pre, aux)
+    finally:
+        capi.set_tuning("balance", old)
+    assert torch.equal(got, plain) and torch.equal(again, plain)
+    assert rel_fro(got.cpu().numpy(), oracle.spmm(rp, ci, x, precision=1)) <= TOL_FP32
+
+
+def test_f32_to_bf16_is_round_to_nearest_even(capi):
+    x = torch.randn(1000, 96, generator=torch.Generator().manual_seed(3))
+    x[0, :4] = torch.tensor([float("inf"), -float("inf"), 0.0, -0.0])
+    got = capi.f32_to_bf16(x.cuda())
+    assert torch.equal(got.cpu().view(torch.int16), x.to(torch.bfloat16).view(torch.int16))
+    wide = torch.zeros(1000, 128, dtype=torch.bfloat16, device="cuda")     # strided destination (operand segment)
+    capi.f32_to_bf16(x.cuda(), wide[:, 16:112])
+    assert torch.equal(wide[:, 16:112].cpu().view(torch.int16), x.to(torch.bfloat16).view(torch.int16))
+    assert not wide[:, :16].any() and not wide[:, 112:].any()
+
+
+@pytest.mark.parametrize("name", ["rmat_hub_4096", "uniform_777", "rect_72x100000"])
+def test_spmm_bf16_stored_operand(capi, name):
+    """A bfloat16-stored X (the multi-GPU exchange operand) gives exactly the BF16 precision mode's result."""
+    rp, ci = GRAPHS[name]
+    x_rows = 100000 if name.startswith("rect") else rp.size - 1
+    x = xmat(x_rows, 128, seed=6)
+    pre = capi.preprocess(dev(ci), dev(rp), "shipped")
+    want = capi.spmm(dev(x), dev(rp), dev(ci), *pre, precision="bf16")
+    xb = capi.f32_to_bf16(dev(x))
+    aux = capi.GraphAux(dev(rp), dev(ci), pre[3])
+    got = capi.spmm_aux(xb, dev(rp), dev(ci), *pre, aux, precision="bf16_stored")
+    assert torch.equal(got, want)
+    assert rel_fro(got.cpu().numpy(), oracle.spmm(rp, ci, x, precision=1)) <= 1e-2
+
+
 # ---- TMA + tcgen05 persistent Update GEMM (csrc/update_gemm.cu) ---------------------------------
 @pytest.mark.parametrize("m,k,n", [(128, 32, 32), (128, 64, 256), (1000, 128, 128), (513, 100, 48), (4096, 256, 256),
                                    (300, 36, 16), (2000, 128, 320), (77, 8, 4), (40000, 128, 128), (19000, 100, 128)])
@@ -386,15 +435,17 @@ def test_spmm_odd_width_large_uses_padded_copies(capi):
 
 
 # ---- tcgen05 dense super-window path -----------------------------------------------------------
-@pytest.mark.parametrize("warp_specialised", [0, 1])
+@pytest.mark.parametrize("warp_specialised", [0, 1, 2])
 @pytest.mark.parametrize("name", ["sbm_1024", "rmat_1000", "band2_320", "holes_777", "dense_2048"])
 def test_spmm_dense_superwindows_tcgen05(capi, name, warp_specialised):
+    """warp_specialised: 2 = TMA gather4 kernel (default), 1 / 0 = the cp.async kernels of dense.cu."""
     rp, ci = GRAPHS[name]
     n = rp.size - 1
     d_rp, d_ci = dev(rp), dev(ci)
     bp, etc, etr, ht = capi.preprocess(d_ci, d_rp, "all_tc")
     old = capi.set_tuning("umma", 1)
-    old_ws = capi.set_tuning("dense_ws", warp_specialised)
+    old_ws = capi.set_tuning("dense_ws", min(warp_specialised, 1))
+    old_tma = capi.set_tuning("dense_tma", 1 if warp_specialised == 2 else 0)
     try:
         plan = capi.DensePlan(d_rp, d_ci, etr, ht, min_reuse=0.0)
         assert plan.n_dense == sum(1 for s in range((n + 127) // 128) if rp[min(128 * s + 128, n)] > rp[128 * s])
@@ -416,6 +467,67 @@ def test_spmm_dense_superwindows_tcgen05(capi, name, warp_specialised):
     finally:
         capi.set_tuning("umma", old)
         capi.set_tuning("dense_ws", old_ws)
+        capi.set_tuning("dense_tma", old_tma)
+
+
+@pytest.mark.parametrize("dim,hidden", [(64, 32), (128, 128), (256, 256), (48, 47), (16, 256), (256, 16), (96, 100)])
+@pytest.mark.parametrize("name", ["sbm_1024", "dense_2048"])
+def test_fused_aggregation_update_on_tcgen05(capi, name, dim, hidden):
+    """hcspmm_spmm_gemm_aux with a plan that covers the graph: ONE kernel computes Z = A X (TMA gather4 + tcgen05) and
+    out = rna(Z) rna(W) from the TMEM-resident aggregate.  Z equals the unfused dense path bit for bit; out equals
+    the oracle's TF32 GEMM of that Z."""
+    rp, ci = GRAPHS[name]
+    n = rp.size - 1
+    d_rp, d_ci = dev(rp), dev(ci)
+    bp, etc, etr, ht = capi.preprocess(d_ci, d_rp, "all_tc")
+    plan = capi.DensePlan(d_rp, d_ci, etr, ht, min_reuse=0.0)
+    aux = capi.GraphAux(d_rp, d_ci, ht, plan)
+    assert aux.plan_full == 1
+    x, w = xmat(n, dim, seed=dim), xmat(dim, hidden, seed=hidden + 1)
+    out, z = capi.spmm_gemm_aux(dev(x), d_rp, d_ci, bp, etc, etr, ht, dev(w), aux)
+    assert capi.lib().hcspmm_debug_umma_error() == 0
+    z_plain = capi.spmm_aux(dev(x), d_rp, d_ci, bp, etc, etr, ht, aux)
+    assert torch.equal(z, z_plain)
+    tf32 = oracle.spmm(rp, ci, oracle.tf32_round(x), precision=1)
+    assert rel_fro(z.cpu().numpy(), tf32) <= 2e-5
+    assert rel_fro(out.cpu().numpy(), oracle.gemm(z.cpu().numpy(), w, tf32=True)) <= 1e-4
+    old = capi.set_tuning("fuse_update", 0)                     # the unfused route gives the same numbers
+    try:
+        out2, z2 = capi.spmm_gemm_aux(dev(x), d_rp, d_ci, bp, etc, etr, ht, dev(w), aux)
+    finally:
+        capi.set_tuning("fuse_update", old)
+    assert torch.equal(z2, z) and rel_fro(out2.cpu().numpy(), out.cpu().numpy()) <= 1e-5
+
+
+def test_fused_update_falls_back_when_the_plan_is_partial(capi):
+    rp, ci = GRAPHS["sbm_1024"]
+    d_rp, d_ci = dev(rp), dev(ci)
+    bp, etc, etr, _ = capi.preprocess(d_ci, d_rp, "all_tc")
+    ht = np.ones(64, np.int32)
+    ht[40:48] = 0                                               # super-window 5 stays on the CUDA cores
+    plan = capi.DensePlan(d_rp, d_ci, etr, dev(ht), min_reuse=0.0)
+    aux = capi.GraphAux(d_rp, d_ci, dev(ht), plan)
+    assert plan.n_dense == 7 and aux.plan_full == 0
+    x, w = xmat(1024, 64, seed=2), xmat(64, 32, seed=3)
+    out, z = capi.spmm_gemm_aux(dev(x), d_rp, d_ci, bp, etc, etr, dev(ht), dev(w), aux)
+    want = oracle.spmm(rp, ci, x, hybrid_type=ht, precision=0)
+    assert rel_fro(z.cpu().numpy(), want) <= 2e-5
+    assert rel_fro(out.cpu().numpy(), oracle.gemm(z.cpu().numpy(), w, tf32=True)) <= 1e-4
+
+
+def test_dense_tma_rectangular_operand_ids_outside_x_contribute_zero(capi):
+    """Column ids >= x_rows (row shards keep global ids) are gathered as out-of-bounds rows: the TMA unit fills zeros."""
+    rp, ci = GRAPHS["sbm_1024"]
+    d_rp, d_ci = dev(rp), dev(ci)
+    bp, etc, etr, ht = capi.preprocess(d_ci, d_rp, "all_tc")
+    plan = capi.DensePlan(d_rp, d_ci, etr, ht, min_reuse=0.0)
+    x = xmat(1024, 64, seed=9)
+    x_short = x[:900]
+    x_zero = x.copy()
+    x_zero[900:] = 0
+    got = capi.spmm_plan(dev(x_short), d_rp, d_ci, bp, etc, etr, ht, plan).cpu().numpy()
+    assert capi.lib().hcspmm_debug_umma_error() == 0
+    assert rel_fro(got, oracle.spmm(rp, ci, oracle.tf32_round(x_zero), precision=1)) <= 2e-5
 
 
 def test_spmm_dense_plan_mixed_labels(capi):
