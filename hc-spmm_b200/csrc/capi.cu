@@ -85,7 +85,7 @@ bool dense_tma_supported(const float *, int64_t, const float *, int64_t, int32_t
 size_t dense_tma_scratch_floats(int32_t, int32_t);
 int launch_spmm_dense_tma(const float *, int64_t, int32_t, int32_t, int32_t, const int *, const int *, const int *,
                           const unsigned *, int32_t, int, float *, int64_t, const float *, int64_t, int32_t, float *, int64_t,
-                          float *, int *, cudaStream_t);
+                          float *, float *, int *, cudaStream_t);
 size_t loa_workspace_bytes(int32_t n, int64_t nnz, int32_t max_degree);
 int launch_loa(const int32_t *, const int32_t *, const int32_t *, const int32_t *, int32_t, int64_t, int32_t,
                int32_t *, int32_t *, int32_t *, void *, size_t, cudaStream_t);
@@ -257,27 +257,32 @@ int hcspmm_spmm_aux(const float *d_x, int64_t ldx, int32_t x_rows, const int32_t
     return launch_spmm(d_x, ldx, x_rows, d_rowptr, d_colidx, d_block_partition, d_edge_to_column, d_edge_to_row,
                        d_hybrid_type, n_rows, nnz, dim, precision, accumulate, d_y, ldy, aux, (cudaStream_t)stream);
   int rc = 0;
-  if (tuning().dense_tma && dense_tma_supported(d_x, ldx, d_y, ldy, dblock)) {
-    // TMA gather4 kernel: the tensor map converts FP32 -> TF32 on load, no rounded copy of X
+  // "dense_tma": 0 / 1 the kernels of dense.cu (1, default: the fused entry point still uses dense_tma.cu);
+  //              2 dense_tma.cu with cp.async gathers; 3 dense_tma.cu with TMA gather4 (no copy of X)
+  const int mode = tuning().dense_tma >= 2 ? tuning().dense_tma - 1 : 0;
+  float *xr = nullptr;
+  if (mode != 2 || !dense_tma_supported(d_x, ldx, d_y, ldy, dblock)) {
+    cudaError_t err = scratch_alloc((void **)&xr, sizeof(float) * (size_t)x_rows * dblock, (cudaStream_t)stream);
+    if (err != cudaSuccess) { set_error("spmm_plan: scratch: %s", cudaGetErrorString(err)); return (int)err; }
+  }
+  if (mode >= 1 && dense_tma_supported(d_x, ldx, d_y, ldy, dblock)) {
     const int *sw_ids, *sw_off, *cols;
     const unsigned *masks;
     dense_plan_arrays(d_plan, n_rows, n_dense, total_cols, &sw_ids, &sw_off, &cols, &masks);
     for (int32_t c0 = 0; c0 < dim && rc == 0; c0 += dblock) {
       const int32_t w = dim - c0 < dblock ? dim - c0 : dblock;
       rc = launch_spmm_dense_tma(d_x + c0, ldx, x_rows, n_rows, w, sw_ids, sw_off, cols, masks, n_dense, accumulate,
-                                 d_y + c0, ldy, nullptr, 0, 0, nullptr, 0, nullptr, umma_error_flag(), (cudaStream_t)stream);
+                                 d_y + c0, ldy, nullptr, 0, 0, nullptr, 0, nullptr, xr, umma_error_flag(),
+                                 (cudaStream_t)stream);
     }
   } else {
-    float *xr = nullptr;
-    cudaError_t err = scratch_alloc((void **)&xr, sizeof(float) * (size_t)x_rows * dblock, (cudaStream_t)stream);
-    if (err != cudaSuccess) { set_error("spmm_plan: scratch: %s", cudaGetErrorString(err)); return (int)err; }
     for (int32_t c0 = 0; c0 < dim && rc == 0; c0 += dblock) {
       const int32_t w = dim - c0 < dblock ? dim - c0 : dblock;
       rc = launch_spmm_dense(d_x + c0, ldx, x_rows, n_rows, w, d_plan, n_dense, total_cols, accumulate, d_y + c0, ldy, xr,
                              umma_error_flag(), (cudaStream_t)stream);
     }
-    scratch_free(xr, (cudaStream_t)stream);
   }
+  if (xr) scratch_free(xr, (cudaStream_t)stream);
   if (rc == 0) {
     hcspmm_aux_t rest = *aux;
     rest.n_tc_windows = -1;   // the plan's labels differ from the caller's count
@@ -351,12 +356,14 @@ int hcspmm_spmm_gemm_aux(const float *d_x, int64_t ldx, int32_t x_rows, const in
       CUDA_TRY(cudaMemset2DAsync(d_z, sizeof(float) * ldz, 0, sizeof(float) * dim, n_rows, st));
       CUDA_TRY(cudaMemset2DAsync(d_out, sizeof(float) * ldo, 0, sizeof(float) * hidden, n_rows, st));
     }
-    float *wt = nullptr;
+    float *wt = nullptr, *xr = nullptr;
     cudaError_t e = scratch_alloc((void **)&wt, sizeof(float) * dense_tma_scratch_floats(dim, hidden), st);
-    if (e != cudaSuccess) { set_error("spmm_gemm: scratch: %s", cudaGetErrorString(e)); return (int)e; }
+    if (e == cudaSuccess && tuning().dense_tma != 3) e = scratch_alloc((void **)&xr, sizeof(float) * (size_t)x_rows * dim, st);
+    if (e != cudaSuccess) { if (wt) scratch_free(wt, st); set_error("spmm_gemm: scratch: %s", cudaGetErrorString(e)); return (int)e; }
     const int rc = launch_spmm_dense_tma(d_x, ldx, x_rows, n_rows, dim, sw_ids, sw_off, cols, masks, aux->n_dense, 0, d_z,
-                                         ldz, d_w, ldw, hidden, d_out, ldo, wt, umma_error_flag(), st);
+                                         ldz, d_w, ldw, hidden, d_out, ldo, wt, xr, umma_error_flag(), st);
     scratch_free(wt, st);
+    if (xr) scratch_free(xr, st);
     return rc;
   }
   int rc = hcspmm_spmm_aux(d_x, ldx, x_rows, d_rowptr, d_colidx, d_block_partition, d_edge_to_column, d_edge_to_row,

@@ -228,6 +228,11 @@ __global__ void tf32_round_rows_kernel(const float *__restrict__ x, long long ld
   }
 }
 
+void launch_tf32_round_rows(const float *x, int64_t ldx, int32_t x_rows, int32_t dim, float *xr, cudaStream_t stream) {
+  const long long total4 = (long long)x_rows * (dim / 4);
+  tf32_round_rows_kernel<<<1184, 256, 0, stream>>>(x, ldx, dim / 4, xr, total4);
+}
+
 // ---- the dense kernel ------------------------------------------------------------------------------
 struct DenseParams {
   const float *xr;   // TF32-rounded X, dense [x_rows, dim]

@@ -31,17 +31,26 @@ bool make_tensor_map_2d(CUtensorMap *map, const void *base, uint64_t cols, uint6
 
 constexpr int DT_SW_H = 128;
 constexpr int DT_KC = 32;                       // condensed columns per stage
-constexpr int DT_PROD_WARPS = 2, DT_EXP_WARPS = 8, DT_EPI_WARPS = 4;
+// GATHER = 0: X rows by TMA gather4 (warps 0-1), 8 expander warps.  GATHER = 1: X rows by 16-byte cp.async from 16
+// expander warps (each also builds its share of the 0/1 tile), from a TF32-rounded copy of X; warp 0 still moves the
+// plan's index chunks and the W^T k-blocks with TMA.  Measured (proteins shape, D = 256): gather4 moves 512 bytes per
+// TMA operation and the TMA unit serves one operation per ~46 cycles per SM, so 64 operations per 32 KB stage bound the
+// kernel at 1.24 ms, where 2048 cp.async pieces from 512 threads reach 0.64 ms -- GATHER = 1 is the default.
+constexpr int DT_PROD_WARPS = 2, DT_EPI_WARPS = 4;
 constexpr int DT_WARP_MMA = DT_PROD_WARPS;      // 2
 constexpr int DT_WARP_EXP = DT_WARP_MMA + 1;    // 3
-constexpr int DT_WARP_EPI = DT_WARP_EXP + DT_EXP_WARPS;   // 11
-constexpr int DT_THREADS = 32 * (DT_WARP_EPI + DT_EPI_WARPS);   // 480
+__host__ __device__ constexpr int dt_exp_warps(int gather) { return gather ? 16 : 8; }
+__host__ __device__ constexpr int dt_warp_epi(int gather) { return DT_WARP_EXP + dt_exp_warps(gather); }
+__host__ __device__ constexpr int dt_threads(int gather) { return 32 * (dt_warp_epi(gather) + DT_EPI_WARPS); }
+__host__ __device__ constexpr uint32_t dt_full_count(int gather) {
+  return gather ? 1u + 2u * dt_exp_warps(1) * 32u : (uint32_t)DT_PROD_WARPS + dt_exp_warps(0) * 32u;
+}
 constexpr int DT_IDX = 512;                     // condensed columns per index chunk (2 KB ids + 8 KB masks)
 constexpr int DT_MAX_STAGES = 6;
 constexpr uint32_t DT_A_BYTES = DT_SW_H * 128;  // 16 KB
-constexpr uint32_t DT_FULL_COUNT = DT_PROD_WARPS + DT_EXP_WARPS * 32;
 
 struct DenseTmaParams {
+  const float *xr;       // GATHER = 1: TF32-rounded dense copy of X [x_rows, dim]
   int x_rows, dim, n_rows, n_dense, accumulate;
   const int *sw_ids, *sw_off, *cols;
   const unsigned *masks;
@@ -132,9 +141,18 @@ __device__ __forceinline__ Walk walk_next(Walk w, const DenseTmaParams &p) {
 }
 }  // namespace dt
 
-__global__ void __launch_bounds__(DT_THREADS, 1)
+__device__ __forceinline__ void dt_cp_async_arrive_noinc(uint64_t *bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(umma::smem_u32(bar)) : "memory");
+}
+
+template <int GATHER>
+__global__ void __launch_bounds__(dt_threads(GATHER), 1)
 spmm_dense_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                       const DenseTmaParams p) {
+  constexpr int DT_EXP_WARPS = dt_exp_warps(GATHER);
+  constexpr int DT_WARP_EPI = dt_warp_epi(GATHER);
+  constexpr uint32_t DT_FULL_COUNT = dt_full_count(GATHER);
+  constexpr uint32_t DT_IEMPTY_COUNT = DT_PROD_WARPS + DT_EXP_WARPS * 32;
   extern __shared__ __align__(1024) uint8_t dt_smem[];
   __shared__ __align__(8) uint64_t bar_full[DT_MAX_STAGES], bar_empty[DT_MAX_STAGES];
   __shared__ __align__(8) uint64_t bar_ifull[2], bar_iempty[2];
@@ -161,14 +179,14 @@ spmm_dense_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     for (int s = 0; s < S; ++s) { umma::mbar_init(&bar_full[s], DT_FULL_COUNT); umma::mbar_init(&bar_empty[s], 1); }
     for (int a = 0; a < 2; ++a) {
       umma::mbar_init(&bar_ifull[a], 1);
-      umma::mbar_init(&bar_iempty[a], DT_FULL_COUNT);
+      umma::mbar_init(&bar_iempty[a], DT_IEMPTY_COUNT);
       umma::mbar_init(&bar_zfull[a], 1);
       umma::mbar_init(&bar_zready[a], DT_EPI_WARPS * 32);
       umma::mbar_init(&bar_ofull[a], 1);
       umma::mbar_init(&bar_free[a], DT_EPI_WARPS * 32);
     }
     umma::fence_barrier_init();
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x) : "memory");
+    if (GATHER == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x) : "memory");
     if (fused) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
   }
   if (wid == DT_WARP_MMA) umma::tmem_alloc(&tmem_slot, (uint32_t)p.tmem_cols);
@@ -194,17 +212,25 @@ spmm_dense_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
       if (wid == 0 && w.valid) issue_idx(w, 0);
       while (w.valid) {
         const dt::Walk nx = dt::walk_next(w, p);
-        if (wid == 0 && nx.valid) {       // prefetch the next index chunk into the other slot
-          ok = umma::mbar_wait(&bar_iempty[(q + 1) & 1u], (((q + 1) >> 1) & 1u) ^ 1u) && ok;
-          issue_idx(nx, q + 1);
-        }
         ok = umma::mbar_wait(&bar_ifull[q & 1u], (q >> 1) & 1u) && ok;
         const int nst = w.ucols / DT_KC;
         const int f0 = w.ch * (DT_IDX / DT_KC), f1 = min(nst, f0 + DT_IDX / DT_KC);
         const int *cs = cols_s + (q & 1u) * DT_IDX;
+        bool prefetched = !(wid == 0 && nx.valid);
         for (int f = f0; f < f1; ++f, ++g) {
           const uint32_t s = g % S;
           ok = umma::mbar_wait(&bar_empty[s], ((g / S) & 1u) ^ 1u) && ok;
+          if (!prefetched && f - f0 > S) {
+            // the next index chunk goes into the slot chunk q-1 used: its consumers are at most S stages behind
+            // this thread, so by now the wait does not block and the ring never drains at a chunk boundary
+            ok = umma::mbar_wait(&bar_iempty[(q + 1) & 1u], (((q + 1) >> 1) & 1u) ^ 1u) && ok;
+            issue_idx(nx, q + 1);
+            prefetched = true;
+          }
+          if (GATHER == 1) {
+            if (wid == 0) dt::arrive(&bar_full[s]);       // the expanders gather; this arrival keeps the count uniform
+            continue;
+          }
           const uint32_t sb = smem_base + s * stage_bytes + DT_A_BYTES;
           dt::expect_tx(&bar_full[s], b_bytes / DT_PROD_WARPS);
           const int kb = (f - f0) * DT_KC;
@@ -213,7 +239,7 @@ spmm_dense_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
             const int ka = wid * (DT_KC / 4 / DT_PROD_WARPS) + kq;       // this warp's 4-row k-atoms
             const int4 c4 = *reinterpret_cast<const int4 *>(cs + kb + ka * 4);
             // padding (-1) and ids outside the operand (rectangular shards) read row x_rows: out of bounds,
-            // the TMA unit fills zeros (their mask bits are cleared by the expanders as well)
+            // the TMA unit fills zeros
             const int r0 = (unsigned)c4.x < (unsigned)p.x_rows ? c4.x : p.x_rows;
             const int r1 = (unsigned)c4.y < (unsigned)p.x_rows ? c4.y : p.x_rows;
             const int r2 = (unsigned)c4.z < (unsigned)p.x_rows ? c4.z : p.x_rows;
@@ -221,6 +247,10 @@ spmm_dense_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
             for (int na = 0; na < natoms; ++na)
               dt::gather4(sb + ka * b_sbo + na * 512, &tm_x, na * 32, r0, r1, r2, r3, &bar_full[s]);
           }
+        }
+        if (!prefetched) {
+          ok = umma::mbar_wait(&bar_iempty[(q + 1) & 1u], (((q + 1) >> 1) & 1u) ^ 1u) && ok;
+          issue_idx(nx, q + 1);
         }
         dt::arrive(&bar_iempty[q & 1u]);
         ++q;
@@ -232,7 +262,7 @@ spmm_dense_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
             if (wid == 0) {
               dt::expect_tx(&bar_full[s], w_bytes);
               dt::load_2d(smem_base + s * stage_bytes + DT_A_BYTES, &tm_w, kb * DT_KC, 0, &bar_full[s]);
-            } else {
+            } else if (GATHER == 0) {
               dt::arrive(&bar_full[s]);
             }
           }
@@ -256,6 +286,8 @@ spmm_dense_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         for (int s0 = 0; s0 < nst; ++s0, ++g) {
           const uint32_t s = g % S;
           ok = umma::mbar_wait(&bar_full[s], (g / S) & 1u) && ok;
+          // (GATHER = 1: the expanders' cp.async / st.shared writes are generic-proxy writes: order them before the
+          // tensor core's async-proxy reads on the consumer side too)
           umma::fence_proxy_async_smem();
           umma::tc_fence_after_sync();
           const uint32_t sa = smem_base + s * stage_bytes, sb = sa + DT_A_BYTES;
@@ -291,13 +323,33 @@ spmm_dense_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     }
     __syncwarp();
   } else if (wid < DT_WARP_EPI) {
-    // ===================== expanders: the 0/1 operand tile of every stage =====================
-    const int et = tid - DT_WARP_EXP * 32;               // 0 .. 255
-    const int row = et & (DT_SW_H - 1), half = et >> 7;  // this thread's row and which 16 of the stage's 32 columns
+    // ===================== expanders: the 0/1 operand tile of every stage (GATHER = 1: and the X rows) ==========
+    constexpr int NE = DT_EXP_WARPS * 32;                 // 256 or 512 threads
+    constexpr int KS = DT_KC * DT_SW_H / NE;              // condensed columns of its row a thread expands: 16 or 8
+    const int et = tid - DT_WARP_EXP * 32;
+    const int row = et & (DT_SW_H - 1), part = et >> 7;
     const int word = row >> 5, bit = row & 31;
-    uint32_t a_off[4];
+    uint32_t a_off[KS / 4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) a_off[c] = umma::kmajor_off(row, half * 16 + c * 4);
+    for (int c = 0; c < KS / 4; ++c) a_off[c] = umma::kmajor_off(row, part * KS + c * 4);
+    // GATHER = 1: the 16-byte pieces of the stage's 32 gathered rows this thread copies
+    constexpr int B_PER = GATHER ? DT_KC * 64 / NE : 1;
+    const int row_pieces = D / 4;
+    int b_kr[B_PER], b_ch[B_PER];
+    uint32_t b_off[B_PER];
+    if (GATHER == 1) {
+#pragma unroll
+      for (int i = 0; i < B_PER; ++i) {
+        const int pid = et + i * NE;
+        if (pid < DT_KC * row_pieces) {
+          b_kr[i] = pid / row_pieces;
+          b_ch[i] = pid - b_kr[i] * row_pieces;
+          b_off[i] = umma::mnmajor_chunk_off(b_kr[i], b_ch[i], 512, b_sbo);
+        } else {
+          b_kr[i] = -1; b_ch[i] = 0; b_off[i] = 0;
+        }
+      }
+    }
     dt::Walk w = dt::walk_first(p);
     uint32_t g = 0, q = 0;
     while (w.valid) {
@@ -308,22 +360,34 @@ spmm_dense_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
       const unsigned *ms = masks_s + (size_t)(q & 1u) * DT_IDX * 4;
       for (int f = f0; f < f1; ++f, ++g) {
         const uint32_t s = g % S;
-        const int kb = (f - f0) * DT_KC + half * 16;
+        const int kb0 = (f - f0) * DT_KC, kb = kb0 + part * KS;
         // the stage's masks and ids first (shared-memory broadcasts), then the ring slot
-        float v[16];
+        float v[KS];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const unsigned m = ms[(kb + k) * 4 + word];
-          const bool on = ((m >> bit) & 1u) && (unsigned)cs[kb + k] < (unsigned)p.x_rows;
-          v[k] = on ? 1.f : 0.f;
+        for (int k = 0; k < KS; ++k) {
+          // (ids outside the operand need no masking here: their gathered rows are zero-filled)
+          v[k] = ((ms[(kb + k) * 4 + word] >> bit) & 1u) ? 1.f : 0.f;
         }
         ok = umma::mbar_wait(&bar_empty[s], ((g / S) & 1u) ^ 1u) && ok;
         uint8_t *sa = gen + s * stage_bytes;
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < KS / 4; ++c)
           *reinterpret_cast<float4 *>(sa + a_off[c]) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
         umma::fence_proxy_async_smem();
         dt::arrive(&bar_full[s]);
+        if (GATHER == 1) {
+          uint8_t *sb = sa + DT_A_BYTES;
+#pragma unroll
+          for (int i = 0; i < B_PER; ++i) {
+            if (b_kr[i] >= 0) {
+              const int col = cs[kb0 + b_kr[i]];
+              const bool valid = (unsigned)col < (unsigned)p.x_rows;
+              const float *src = valid ? p.xr + (long long)col * D + b_ch[i] * 4 : p.xr;
+              cp_async_16(sb + b_off[i], src, valid ? 16 : 0);
+            }
+          }
+          dt_cp_async_arrive_noinc(&bar_full[s]);          // second arrival: when this thread's copies have landed
+        }
       }
       dt::arrive(&bar_iempty[q & 1u]);
       ++q;
@@ -332,10 +396,12 @@ spmm_dense_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
           const uint32_t s = g % S;
           ok = umma::mbar_wait(&bar_empty[s], ((g / S) & 1u) ^ 1u) && ok;
           dt::arrive(&bar_full[s]);
+          if (GATHER == 1) dt::arrive(&bar_full[s]);
         }
       }
       w = dt::walk_next(w, p);
     }
+    if (GATHER == 1) asm volatile("cp.async.wait_all;" ::: "memory");
   } else {
     // ===================== epilogue =====================
     const int lq = wid & 3;                             // the TMEM lane quarter this warp may access
@@ -430,12 +496,19 @@ size_t dense_tma_scratch_floats(int32_t dim, int32_t hidden) {
 }
 
 // Z rows of the plan's super-windows (+)= A X; with hidden > 0 also out = rna(Z) rna(W) for those rows (hidden <= 256).
+// xr_scratch != nullptr selects GATHER = 1: X is first rounded to TF32 into xr_scratch ([x_rows * dim] floats) and
+// gathered with cp.async; nullptr selects the TMA gather4 variant (no copy of X).
+void launch_tf32_round_rows(const float *x, int64_t ldx, int32_t x_rows, int32_t dim, float *xr, cudaStream_t stream);
+
 int launch_spmm_dense_tma(const float *x, int64_t ldx, int32_t x_rows, int32_t n_rows, int32_t dim, const int *sw_ids,
                           const int *sw_off, const int *cols, const unsigned *masks, int32_t n_dense, int accumulate,
                           float *z, int64_t ldz, const float *w, int64_t ldw, int32_t hidden, float *out, int64_t ldo,
-                          float *wt_scratch, int *d_err, cudaStream_t stream) {
+                          float *wt_scratch, float *xr_scratch, int *d_err, cudaStream_t stream) {
   if (n_dense <= 0) return 0;
   DenseTmaParams p;
+  p.xr = xr_scratch;
+  const int gather = xr_scratch != nullptr ? 1 : 0;
+  if (gather) launch_tf32_round_rows(x, ldx, x_rows, dim, xr_scratch, stream);
   p.x_rows = x_rows; p.dim = dim; p.n_rows = n_rows; p.n_dense = n_dense; p.accumulate = accumulate;
   p.sw_ids = sw_ids; p.sw_off = sw_off; p.cols = cols; p.masks = masks; p.z = z; p.ldz = ldz;
   p.hidden = hidden > 0 ? hidden : 0;
@@ -478,13 +551,15 @@ int launch_spmm_dense_tma(const float *x, int64_t ldx, int32_t x_rows, int32_t n
   } else {
     tm_w = tm_x;
   }
-  cudaError_t err = cudaFuncSetAttribute(spmm_dense_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t err = gather ? cudaFuncSetAttribute(spmm_dense_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                           : cudaFuncSetAttribute(spmm_dense_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) { set_error("spmm_dense_tma attr: %s", cudaGetErrorString(err)); return (int)err; }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = n_dense < sms ? n_dense : sms;
-  spmm_dense_tma_kernel<<<grid, DT_THREADS, smem, stream>>>(tm_x, tm_w, p);
+  if (gather) spmm_dense_tma_kernel<1><<<grid, dt_threads(1), smem, stream>>>(tm_x, tm_w, p);
+  else spmm_dense_tma_kernel<0><<<grid, dt_threads(0), smem, stream>>>(tm_x, tm_w, p);
   err = cudaGetLastError();
   if (err != cudaSuccess) { set_error("spmm_dense_tma launch: %s", cudaGetErrorString(err)); return (int)err; }
   return 0;

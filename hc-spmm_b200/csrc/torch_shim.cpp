@@ -416,6 +416,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         pybind11::arg("input"), pybind11::arg("nodePointer"), pybind11::arg("edgeList"), pybind11::arg("blockPartition"),
         pybind11::arg("edgeToColumn"), pybind11::arg("edgeToRow"), pybind11::arg("hybrid_type"), pybind11::arg("out"),
         pybind11::arg("accumulate"), pybind11::arg("row_nzr") = pybind11::none(), pybind11::arg("col_nzr") = pybind11::none());
+  m.def("spmm_accumulate", &spmm_strided, "alias of spmm_strided",
+        pybind11::arg("input"), pybind11::arg("nodePointer"), pybind11::arg("edgeList"), pybind11::arg("blockPartition"),
+        pybind11::arg("edgeToColumn"), pybind11::arg("edgeToRow"), pybind11::arg("hybrid_type"), pybind11::arg("out"),
+        pybind11::arg("accumulate"), pybind11::arg("row_nzr") = pybind11::none(), pybind11::arg("col_nzr") = pybind11::none());
   m.def("spmm_bf16", &spmm_bf16, "out (+)= A @ input for a bfloat16-stored input (exchange operand)",
         pybind11::arg("input"), pybind11::arg("nodePointer"), pybind11::arg("edgeList"), pybind11::arg("blockPartition"),
         pybind11::arg("edgeToColumn"), pybind11::arg("edgeToRow"), pybind11::arg("hybrid_type"), pybind11::arg("out"),

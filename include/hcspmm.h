@@ -84,8 +84,14 @@ const char *hcspmm_last_error(void);
  *   "umma"       1: tcgen05 / TMEM dense super-window kernel (hcspmm_spmm_plan); 0: per-window paths
  *   "umma_gemm"  Update GEMM kernel: 2 = TMA + tcgen05 persistent warp-specialised kernel, 1 = register-staged
  *                tcgen05 kernel, 0 = mma.sync kernel (also the fallback for unaligned operands)
- *   "dense_tma"  1 (default): dense super-windows on the TMA gather4 + tcgen05 kernel (csrc/dense_tma.cu: no rounded
- *                copy of X, optional fused Update); 0: the cp.async kernels of csrc/dense.cu
+ *   "dense_tma"  which kernel multiplies dense super-windows.  csrc/dense_tma.cu is the five-role kernel (TMA for
+ *                the plan's index chunks and W^T, dedicated epilogue warps, optional FUSED Update); csrc/dense.cu holds
+ *                the earlier producer/issuer kernels.  1 (default): dense.cu for plain aggregation (measured fastest,
+ *                proteins shape dim 256: 0.64 ms), dense_tma.cu with cp.async gathers behind the fused entry point
+ *                (0.62 ms for Z and out together, against 0.70 ms unfused); 2: dense_tma.cu with cp.async gathers for
+ *                both; 3: dense_tma.cu gathering X rows with TMA gather4 from a TF32-typed tensor map (no rounded copy
+ *                of X, but the TMA unit serves one 512-byte gather4 per ~46 cycles: 1.28 ms); 0: dense.cu only, the
+ *                fused entry point runs aggregation and Update GEMM back to back
  *   "fuse_update" 1 (default): hcspmm_spmm_gemm_aux fuses the Update product when the plan covers the graph
  *   "gemm_round" TMA Update GEMM: 1 (default) rounder warps apply cvt.rna.tf32 to the landed Z boxes (the
  *                reference's rounding); 0 = the tensor map's TF32 element type converts on load

@@ -33,20 +33,23 @@ for shape, _ in cases:
         x = torch.randn(n, dim, device=dev)
         w = torch.randn(dim, hidden, device=dev)
         rec = {"shape": shape, "dim": dim, "hidden": hidden, "n_dense": plan.n_dense, "total_cols": plan.total_cols}
-        for name, tma, ws in (("cp.async single-role", 0, 0), ("cp.async warp-specialised", 0, 1), ("tma gather4", 1, 1)):
+        for name, tma, ws in (("dense.cu single-role", 0, 0), ("dense.cu warp-specialised", 0, 1),
+                              ("dense_tma.cu cp.async gather", 2, 1), ("dense_tma.cu tma gather4", 3, 1)):
             capi.set_tuning("dense_tma", tma); capi.set_tuning("dense_ws", ws)
             rec["spmm_ms " + name] = t(lambda: capi.spmm_aux(x, rp, ci, bp, etc, etr, ht, aux))
-        capi.set_tuning("dense_tma", 1)
-        for name, fuse in (("unfused (dense SpMM, then TMA GEMM)", 0), ("fused (one kernel)", 1)):
-            capi.set_tuning("fuse_update", fuse)
-            rec["spmm_gemm_ms " + name] = t(lambda: capi.spmm_gemm_aux(x, rp, ci, bp, etc, etr, ht, w, aux))
-        capi.set_tuning("fuse_update", 1)
+        for tma in (0, 1, 2, 3):
+            capi.set_tuning("dense_tma", tma)
+            for name, fuse in (("unfused", 0), ("fused", 1)):
+                capi.set_tuning("fuse_update", fuse)
+                rec[f"spmm_gemm_ms dense_tma={tma} {name}"] = t(lambda: capi.spmm_gemm_aux(x, rp, ci, bp, etc, etr, ht, w, aux))
+        capi.set_tuning("fuse_update", 1); capi.set_tuning("dense_tma", 1)
         rec["gemm_only_ms"] = t(lambda: capi.gemm_tf32(x, w))
         aux0 = capi.GraphAux(rp, ci, ht)
         rec["spmm_ms cuda cores (no plan)"] = t(lambda: capi.spmm_aux(x, rp, ci, bp, etc, etr, ht, aux0))
         flops_exec = 2.0 * 128 * plan.total_cols * dim
-        rec["executed_tflops tma"] = flops_exec / rec["spmm_ms tma gather4"] / 1e9
-        rec["useful_gflops tma"] = 2.0 * nnz * dim / rec["spmm_ms tma gather4"] / 1e6
+        best = min(v for k, v in rec.items() if k.startswith("spmm_ms dense"))
+        rec["executed_tflops best dense"] = flops_exec / best / 1e9
+        rec["useful_gflops best dense"] = 2.0 * nnz * dim / best / 1e6
         print(json.dumps(rec))
         out.append(rec)
 print("umma err", capi.lib().hcspmm_debug_umma_error())

@@ -435,17 +435,18 @@ def test_spmm_odd_width_large_uses_padded_copies(capi):
 
 
 # ---- tcgen05 dense super-window path -----------------------------------------------------------
-@pytest.mark.parametrize("warp_specialised", [0, 1, 2])
+@pytest.mark.parametrize("warp_specialised", [0, 1, 2, 3])
 @pytest.mark.parametrize("name", ["sbm_1024", "rmat_1000", "band2_320", "holes_777", "dense_2048"])
 def test_spmm_dense_superwindows_tcgen05(capi, name, warp_specialised):
-    """warp_specialised: 2 = TMA gather4 kernel (default), 1 / 0 = the cp.async kernels of dense.cu."""
+    """warp_specialised: 2 = five-role kernel of dense_tma.cu with cp.async gathers (default), 3 = the same kernel
+    with TMA gather4, 1 / 0 = the kernels of dense.cu."""
     rp, ci = GRAPHS[name]
     n = rp.size - 1
     d_rp, d_ci = dev(rp), dev(ci)
     bp, etc, etr, ht = capi.preprocess(d_ci, d_rp, "all_tc")
     old = capi.set_tuning("umma", 1)
     old_ws = capi.set_tuning("dense_ws", min(warp_specialised, 1))
-    old_tma = capi.set_tuning("dense_tma", 1 if warp_specialised == 2 else 0)
+    old_tma = capi.set_tuning("dense_tma", {2: 2, 3: 3}.get(warp_specialised, 0))
     try:
         plan = capi.DensePlan(d_rp, d_ci, etr, ht, min_reuse=0.0)
         assert plan.n_dense == sum(1 for s in range((n + 127) // 128) if rp[min(128 * s + 128, n)] > rp[128 * s])
@@ -472,7 +473,8 @@ def test_spmm_dense_superwindows_tcgen05(capi, name, warp_specialised):
 
 @pytest.mark.parametrize("dim,hidden", [(64, 32), (128, 128), (256, 256), (48, 47), (16, 256), (256, 16), (96, 100)])
 @pytest.mark.parametrize("name", ["sbm_1024", "dense_2048"])
-def test_fused_aggregation_update_on_tcgen05(capi, name, dim, hidden):
+@pytest.mark.parametrize("gather", [2, 3])
+def test_fused_aggregation_update_on_tcgen05(capi, name, dim, hidden, gather):
     """hcspmm_spmm_gemm_aux with a plan that covers the graph: ONE kernel computes Z = A X (TMA gather4 + tcgen05) and
     out = rna(Z) rna(W) from the TMEM-resident aggregate.  Z equals the unfused dense path bit for bit; out equals
     the oracle's TF32 GEMM of that Z."""
@@ -484,19 +486,23 @@ def test_fused_aggregation_update_on_tcgen05(capi, name, dim, hidden):
     aux = capi.GraphAux(d_rp, d_ci, ht, plan)
     assert aux.plan_full == 1
     x, w = xmat(n, dim, seed=dim), xmat(dim, hidden, seed=hidden + 1)
-    out, z = capi.spmm_gemm_aux(dev(x), d_rp, d_ci, bp, etc, etr, ht, dev(w), aux)
-    assert capi.lib().hcspmm_debug_umma_error() == 0
-    z_plain = capi.spmm_aux(dev(x), d_rp, d_ci, bp, etc, etr, ht, aux)
-    assert torch.equal(z, z_plain)
-    tf32 = oracle.spmm(rp, ci, oracle.tf32_round(x), precision=1)
-    assert rel_fro(z.cpu().numpy(), tf32) <= 2e-5
-    assert rel_fro(out.cpu().numpy(), oracle.gemm(z.cpu().numpy(), w, tf32=True)) <= 1e-4
-    old = capi.set_tuning("fuse_update", 0)                     # the unfused route gives the same numbers
+    old_g = capi.set_tuning("dense_tma", gather)                # 2: cp.async gathers, 3: TMA gather4
     try:
-        out2, z2 = capi.spmm_gemm_aux(dev(x), d_rp, d_ci, bp, etc, etr, ht, dev(w), aux)
+        out, z = capi.spmm_gemm_aux(dev(x), d_rp, d_ci, bp, etc, etr, ht, dev(w), aux)
+        assert capi.lib().hcspmm_debug_umma_error() == 0
+        z_plain = capi.spmm_aux(dev(x), d_rp, d_ci, bp, etc, etr, ht, aux)
+        assert torch.equal(z, z_plain)
+        tf32 = oracle.spmm(rp, ci, oracle.tf32_round(x), precision=1)
+        assert rel_fro(z.cpu().numpy(), tf32) <= 2e-5
+        assert rel_fro(out.cpu().numpy(), oracle.gemm(z.cpu().numpy(), w, tf32=True)) <= 1e-4
+        old = capi.set_tuning("fuse_update", 0)                     # the unfused route gives the same numbers
+        try:
+            out2, z2 = capi.spmm_gemm_aux(dev(x), d_rp, d_ci, bp, etc, etr, ht, dev(w), aux)
+        finally:
+            capi.set_tuning("fuse_update", old)
+        assert torch.equal(z2, z) and rel_fro(out2.cpu().numpy(), out.cpu().numpy()) <= 1e-5
     finally:
-        capi.set_tuning("fuse_update", old)
-    assert torch.equal(z2, z) and rel_fro(out2.cpu().numpy(), out.cpu().numpy()) <= 1e-5
+        capi.set_tuning("dense_tma", old_g)
 
 
 def test_fused_update_falls_back_when_the_plan_is_partial(capi):
