@@ -56,7 +56,7 @@ def parse():
     ap.add_argument("--slab", type=int, default=-1, help="feature-slab width (-1 = library default)")
     ap.add_argument("--long-row", type=int, default=-1)
     ap.add_argument("--vec8", type=int, default=-1, help="256-bit gathers: 1 on, 0 off (-1 = library default)")
-    ap.add_argument("--exchange", default="auto", choices=["auto", "gather", "slabs", "halo", "peer"],
+    ap.add_argument("--exchange", default="auto", choices=["auto", "gather", "slabs", "halo", "peer", "push"],
                     help="N > 1: all-gather of X, all-gather pipelined in feature slabs, halo rows only (NCCL all-to-all), "
                          "peer = halo rows pulled over NVLink peer memory by our own kernel (auto picks this)")
     ap.add_argument("--exchange-passes", type=int, default=1, choices=[1, 2],
@@ -488,8 +488,8 @@ def run_workload(ctx, shape_name, dim, steps, warmup, classifier, dense, precisi
     if dense_groups > 0 and precision == "tf32":
         spmm_launches += 2                         # tf32_round_rows + spmm_dense_ws
     launches_per_step = spmm_launches * n_slabs + (1 if (precision == "bf16" and (world == 1 or dim % 8)) else 0) * n_slabs
-    if world > 1 and sg.schedule == "peer":
-        launches_per_step += 1 + n_slabs + (1 if operand == "bf16" and dim % 8 == 0 else 0)   # barrier + pull(s) (+ f32->bf16 of own rows)
+    if world > 1 and sg.schedule in ("peer", "push"):
+        launches_per_step += 1 + n_slabs + (1 if operand == "bf16" and dim % 8 == 0 else 0)   # barrier + pull(s) / push (+ f32->bf16 of own rows)
 
     # ---- roofline of the dominant kernel (the SpMM launch of a step) ------------------------------------------------
     esz_x = 2 if precision == "bf16" else 4
@@ -507,7 +507,26 @@ def run_workload(ctx, shape_name, dim, steps, warmup, classifier, dense, precisi
     except Exception:
         pass
     roofline = None
-    if kern_ms:
+    if kern_ms and dense_groups > 0 and world == 1:
+        # dense super-windows: the tensor pipe is the roof.  EXECUTED flops = 2 * 128 * (condensed columns, padded to
+        # 32) * dim per super-window (useful = 2 * nnz * dim is `value`); peak = half the measured cuBLAS BF16 burst
+        # figure (TF32 issues at half the BF16 rate on tcgen05; MEASURED_PEAKS.json holds BF16 only)
+        total_cols = int(hdr[2])
+        exec_tflops = 2.0 * 128 * total_cols * dim / (kern_ms * 1e-3) / 1e12
+        try:
+            tf32_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"]) / 2
+            psrc = "measured cuBLAS BF16 burst (MEASURED_PEAKS.json) / 2: TF32 issues at half the BF16 rate"
+        except Exception:
+            tf32_peak, psrc = 1590.0 / 2, "fallback BF16 figure (B200_PROFILING.md) / 2"
+        roofline = {"bound": "tensor", "achieved": exec_tflops, "peak": tf32_peak, "unit": "TFLOP/s", "frac": exec_tflops / tf32_peak,
+                    "traffic": traffic, "traffic_source": traffic_src, "peak_source": psrc,
+                    "kernel": "spmm_dense_ws_kernel (tcgen05.mma kind::tf32, M128 N=dim K8), whole step incl. tf32_round_rows",
+                    "kernel_ms": kern_ms, "executed_flops": 2.0 * 128 * total_cols * dim, "useful_flops": flops,
+                    "executed_over_useful": 128.0 * total_cols / max(1, nnz),
+                    "gathered_bytes": total_cols * dim * 4, "gather_gbs": total_cols * dim * 4 / (kern_ms * 1e-3) / 1e9,
+                    "hbm_peak": ctx.hbm_peak, "compulsory_bytes": bytes_min,
+                    "compulsory_frac": bytes_min / (kern_ms * 1e-3) / 1e9 / ctx.hbm_peak, "scope": "whole graph, one GPU"}
+    elif kern_ms:
         ach = bytes_alg / (kern_ms * 1e-3) / 1e9
         kernel = ("spmm_dense_ws_kernel (tcgen05) + spmm_balanced_kernel for the remaining windows" if dense_groups else
                   "spmm_balanced_kernel (+ spmm_balanced_fixup_kernel: the step)" if balanced else "spmm_hybrid_kernel")
@@ -595,7 +614,9 @@ def run_workload(ctx, shape_name, dim, steps, warmup, classifier, dense, precisi
                      "halo": "halo rows only: pack + NCCL all_to_all_single per step, %d feature slab(s)" % n_slabs,
                      "peer": "halo rows only (%s), pulled from the owners' memory over NVLink by hcspmm_halo_pull after "
                              "hcspmm_peer_barrier, %d feature slab(s), %d source pass(es) -- moves fewer bytes than the north "
-                             "star's all-gather (exchange_rows_vs_allgather)" % (operand, n_slabs, 2 if sg.passes is not None else 1)}
+                             "star's all-gather (exchange_rows_vs_allgather)" % (operand, n_slabs, 2 if sg.passes is not None else 1),
+                     "push": "halo rows only (%s), written into the consumers' operand buffers over NVLink by their owner "
+                             "(hcspmm_halo_push), then hcspmm_peer_barrier" % operand}
     line = {"metric": "spmm_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": steps,
             "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16-stored X, f32 accumulate" if precision == "bf16" else "f32", "data": "synthetic",

@@ -4,9 +4,13 @@
   python benchmarks/gcn_epoch.py [--shape products --hidden 128 --feat 100 --classes 47 --layers 2]
   torchrun --nproc-per-node N benchmarks/gcn_epoch.py ...
 
-Row-partitioned training (hcspmm.dist): every rank owns a nnz-balanced range of 16-row windows of A and
-the matching rows of X / labels; each layer = local Update GEMM + all-gather + local hybrid SpMM.
-Prints one JSON line: median epoch ms (forward + backward + Adam) over --epochs after --warmup, max over ranks.
+Row-partitioned training (hcspmm.dist.DistGCN): every rank owns a nnz-balanced range of 16-row windows of A and
+the matching rows of X / labels.  A layer is routed like the reference's autograd Functions (GNN_model.py:61-232):
+the row-local Update GEMM on the library's TMA + tcgen05 kernel, the Aggregation = halo exchange over NVLink peer
+memory + local hybrid SpMM, and the reference's FUSED entry points (forward_fixed32_fused: GCN backward, GIN forward)
+where it uses them.  Prints one JSON line: median epoch ms (forward + backward + Adam) over --epochs after --warmup,
+max over ranks.  At N > 1 rank 0 also trains the SAME model on the unpartitioned graph (outside the timed epochs) and
+the line carries the loss difference, epoch by epoch.
 """
 import argparse
 import json
@@ -29,12 +33,13 @@ def main():
     ap.add_argument("--layers", type=int, default=2)
     ap.add_argument("--epochs", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--schedule", default="auto", choices=["auto", "gather", "slabs", "halo", "peer"])
+    ap.add_argument("--schedule", default="auto", choices=["auto", "gather", "slabs", "halo", "peer", "push"])
     ap.add_argument("--slabs", type=int, default=1)
     ap.add_argument("--classifier", default="shipped")
     ap.add_argument("--model", default="gcn", choices=["gcn", "gin"],
                     help="gcn: X' = A (X W) (GNN_model.py:61-162); gin: X' = (A X) W (GNN_model.py:166-232)")
-    ap.add_argument("--dense", action="store_true", help="tcgen05 dense super-window plans (single GPU)")
+    ap.add_argument("--dense", action="store_true", help="tcgen05 dense super-window plans")
+    ap.add_argument("--operand", default="fp32", choices=["fp32", "bf16"], help="N > 1: exchange operand storage")
     ap.add_argument("--fp32-matmul", action="store_true",
                     help="Update GEMMs (torch.mm) in full FP32; default TF32 like the reference's stack "
                          "(PyTorch 1.8: allow_tf32 on by default; its fused kernels use wmma TF32, :1809-1837)")
@@ -52,18 +57,38 @@ def main():
     HCSPMM.set_dense(bool(args.dense))
     HCSPMM.set_classifier(args.classifier)
     rp, ci, info = graphs.named(args.shape, device=dev, scale=args.scale)
-    g = hd.ShardedGraph(rp, ci, schedule=args.schedule, n_slabs=args.slabs)
-    del rp, ci
+    g = hd.ShardedGraph(rp, ci, schedule=args.schedule, n_slabs=args.slabs, operand=args.operand)
     # the SAME problem at every N: global features / labels from one seed, then this rank's rows
     # (A is binary and unnormalised like the reference's; features are scaled so the logits start O(1))
     gen = torch.Generator(device=dev).manual_seed(100)
     mean_deg = max(1.0, info["nnz"] / info["n"])
-    x = (torch.randn(info["n"], args.feat, device=dev, generator=gen) / mean_deg ** 2)[g.r0:g.r1].contiguous()
-    y = torch.randint(0, args.classes, (info["n"],), device=dev, generator=gen)[g.r0:g.r1].contiguous()
-    model = hd.DistGCN(g, args.feat, args.hidden, args.classes, num_layers=args.layers, seed=0,
-                       order={"gcn": "auto", "gin": "aggregate_first"}[args.model]).to(dev)
+    x_all = torch.randn(info["n"], args.feat, device=dev, generator=gen) / mean_deg ** 2
+    y_all = torch.randint(0, args.classes, (info["n"],), device=dev, generator=gen)
+    x, y = x_all[g.r0:g.r1].contiguous(), y_all[g.r0:g.r1].contiguous()
+    order = {"gcn": "auto", "gin": "aggregate_first"}[args.model]
+
+    # the single-GPU reference of the same training (rank 0, unpartitioned graph), for the loss comparison
+    ref_losses = None
+    if world > 1:
+        if rank == 0:
+            g1 = hd.ShardedGraph(rp, ci, single=True)
+            m1 = hd.DistGCN(g1, args.feat, args.hidden, args.classes, num_layers=args.layers, seed=0, order=order).to(dev)
+            o1 = torch.optim.Adam(m1.parameters(), lr=0.01)
+            ref_losses = []
+            for ep in range(args.warmup + args.epochs):
+                o1.zero_grad()
+                l1 = m1.loss(x_all, y_all)
+                l1.backward()
+                o1.step()
+                ref_losses.append(float(l1))
+            del g1, m1, o1
+        dist.barrier()
+    del rp, ci, x_all, y_all
+    torch.cuda.empty_cache()
+
+    model = hd.DistGCN(g, args.feat, args.hidden, args.classes, num_layers=args.layers, seed=0, order=order).to(dev)
     opt = torch.optim.Adam(model.parameters(), lr=0.01)
-    times, losses = [], []
+    times, losses, all_losses = [], [], []
     for ep in range(args.warmup + args.epochs):
         if world > 1:
             dist.barrier()
@@ -82,6 +107,7 @@ def main():
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dist.all_reduce(l)
+        all_losses.append(float(l))
         if ep >= args.warmup:
             times.append(float(t))
             losses.append(float(l))
@@ -119,8 +145,18 @@ def main():
                                      "stored_entries": info["nnz"], "feat": args.feat, "hidden": args.hidden,
                                      "classes": args.classes, "schedule": g.schedule, "slabs": g.n_slabs,
                                      "exchange_rows_vs_allgather": (g.exchange_rows() / max(1, (world - 1) * g.max_rows)) if world > 1 else None,
-                                     "classifier": args.classifier, "update_gemm": "fp32" if args.fp32_matmul else "tf32 (torch.mm, allow_tf32)"},
-                          "phases": phases, "loss_first": losses[0], "loss_last": losses[-1]}))
+                                     "classifier": args.classifier, "operand": args.operand,
+                                     "update_gemm": "HCSPMM.gemm_tf32 (cvt.rna TF32, FP32 accumulate); weight gradients torch.mm " +
+                                                    ("fp32" if args.fp32_matmul else "tf32")},
+                          "phases": phases, "loss_first": losses[0], "loss_last": losses[-1],
+                          "loss_trace": all_losses[:3] + all_losses[-2:],
+                          "loss_vs_single_gpu": None if ref_losses is None else {
+                              "max_abs_diff": max(abs(a_ - b_) for a_, b_ in zip(all_losses, ref_losses)),
+                              "max_rel_diff": max(abs(a_ - b_) / max(abs(b_), 1e-12) for a_, b_ in zip(all_losses, ref_losses)),
+                              "epochs_compared": len(ref_losses), "single_gpu_trace": ref_losses[:3] + ref_losses[-2:],
+                              "how": "rank 0 trains the same model (same seeds) on the unpartitioned graph; every epoch's loss compared"},
+                          "routing": "hcspmm.dist.DistGCN: Update GEMMs on HCSPMM.gemm_tf32 (TMA + tcgen05), aggregations through "
+                                     "HCSPMM.forward / forward_fixed32_fused on the exchanged operand"}))
     if world > 1:
         g.close()
         dist.destroy_process_group()

@@ -17,7 +17,7 @@ void set_error(const char *fmt, ...) {
 }
 
 Tuning &tuning() {
-  static Tuning t = {1024, 0, 1, 1, 0, 1, 1, 2, 1, 1, 1, 0, 0, 64, 1, 0, 2048, 10000, 1, 1};
+  static Tuning t = {1024, 0, 1, 1, 0, 1, 1, 2, 1, 1, 1, 0, 0, 64, 1, 0, 2048, 10000, 1, 1, 8};
   return t;
 }
 
@@ -58,6 +58,8 @@ int launch_spmm(const float *, int64_t, int32_t, const int32_t *, const int32_t 
                 int, float *, int64_t, const hcspmm_aux_t *, cudaStream_t);
 int launch_merge_path_splits(const int32_t *, int32_t, int64_t, int32_t, int32_t *, cudaStream_t);
 int launch_f32_to_bf16(const float *, int64_t, int32_t, int32_t, void *, int64_t, cudaStream_t);
+void launch_pad_rows(const float *, int64_t, int32_t, int32_t, float *, int32_t, cudaStream_t);
+void launch_unpad_rows(const float *, int32_t, int32_t, int32_t, float *, int64_t, cudaStream_t);
 size_t balanced_workspace_bytes(int32_t, int64_t, int32_t);
 int launch_gemm_tf32(const float *, int64_t, const float *, int64_t, int32_t, int32_t, int32_t,
                      float *, int64_t, cudaStream_t);
@@ -98,6 +100,10 @@ struct hcspmm_graph {
   int32_t n_rows, x_rows, n_windows;
   int64_t nnz;
   int32_t *rowptr, *colidx, *bp, *etc, *etr, *ht;
+  int32_t *splits;       // per-graph products (hcspmm_aux_t): merge-path split points, label-1 window count,
+  int32_t n_splits, n_tc; // and the balanced kernel's workspace (sized with the X / Y buffers)
+  void *ws;
+  size_t ws_bytes;
   float *x, *y;
   int32_t buf_dim;
   cudaStream_t stream;
@@ -140,6 +146,7 @@ int hcspmm_set_tuning(const char *key, int value) {
   else if (key && !strcmp(key, "barrier_timeout_ms")) slot = &tuning().barrier_timeout_ms;
   else if (key && !strcmp(key, "dense_tma")) slot = &tuning().dense_tma;
   else if (key && !strcmp(key, "fuse_update")) slot = &tuning().fuse_update;
+  else if (key && !strcmp(key, "dense_min_rowlen")) slot = &tuning().dense_min_rowlen;
   if (!slot) return -1;
   int old = *slot;
   *slot = value;
@@ -205,14 +212,35 @@ int hcspmm_gemm_tf32(const float *d_a, int64_t lda, const float *d_b, int64_t ld
   if (!d_a || !d_b || !d_out) { set_error("gemm_tf32: null pointer argument"); return HCSPMM_E_INVALID; }
   if (m <= 0 || n <= 0) return 0;
   // 2 (default): TMA + tcgen05 persistent kernel; 1: register-staged tcgen05 kernel; 0: mma.sync kernel
-  if (tuning().umma_gemm >= 2 && lda >= k && ldb >= n && ldo >= n &&
-      update_gemm_tma_supported(d_a, lda, d_b, ldb, d_out, ldo, m, k, n)) {
-    float *wt = nullptr;
-    cudaError_t e = scratch_alloc((void **)&wt, sizeof(float) * update_gemm_scratch_floats(k, n), (cudaStream_t)stream);
-    if (e != cudaSuccess) { set_error("gemm_tf32: scratch: %s", cudaGetErrorString(e)); return (int)e; }
-    const int rc = launch_update_gemm_tma(d_a, lda, d_b, ldb, m, k, n, d_out, ldo, wt, umma_error_flag(), (cudaStream_t)stream);
-    scratch_free(wt, (cudaStream_t)stream);
-    return rc;
+  if (tuning().umma_gemm >= 2 && lda >= k && ldb >= n && ldo >= n && k > 0) {
+    // TMA needs 16-byte aligned rows.  Operands that are not (47 classes: lda or ldo = 47) go through zero-padded
+    // scratch copies -- one extra streaming pass each, after which the product runs at the HBM roofline instead of
+    // on the mma.sync kernel at a third of it (only worth it for tall operands).
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool a_ok = (lda & 3) == 0 && (reinterpret_cast<uintptr_t>(d_a) & 15) == 0;
+    const bool o_ok = (ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0;
+    const bool tall = (long long)m * (k + n) >= (1 << 20);
+    if ((a_ok && o_ok) || tall) {
+      const int32_t kp = (k + 3) / 4 * 4, np = (n + 3) / 4 * 4;
+      float *wt = nullptr, *ap = nullptr, *op = nullptr;
+      cudaError_t e = scratch_alloc((void **)&wt, sizeof(float) * update_gemm_scratch_floats(k, n), st);
+      if (e == cudaSuccess && !a_ok) e = scratch_alloc((void **)&ap, sizeof(float) * (size_t)m * kp, st);
+      if (e == cudaSuccess && !o_ok) e = scratch_alloc((void **)&op, sizeof(float) * (size_t)m * np, st);
+      int rc = 0;
+      if (e != cudaSuccess) { set_error("gemm_tf32: scratch: %s", cudaGetErrorString(e)); rc = (int)e; }
+      if (rc == 0 && !a_ok) launch_pad_rows(d_a, lda, m, k, ap, kp, st);
+      if (rc == 0 && update_gemm_tma_supported(a_ok ? d_a : ap, a_ok ? lda : kp, d_b, ldb, o_ok ? d_out : op, o_ok ? ldo : np, m, k, n)) {
+        rc = launch_update_gemm_tma(a_ok ? d_a : ap, a_ok ? lda : kp, d_b, ldb, m, k, n, o_ok ? d_out : op, o_ok ? ldo : np, wt,
+                                    umma_error_flag(), st);
+        if (rc == 0 && !o_ok) launch_unpad_rows(op, np, m, n, d_out, ldo, st);
+      } else if (rc == 0) {
+        rc = launch_gemm_tf32(d_a, lda, d_b, ldb, m, k, n, d_out, ldo, st);
+      }
+      if (wt) scratch_free(wt, st);
+      if (ap) scratch_free(ap, st);
+      if (op) scratch_free(op, st);
+      return rc;
+    }
   }
   if (tuning().umma_gemm == 1 && lda >= k && ldb >= n && ldo >= n && umma_gemm_supported(d_a, lda, d_b, ldb, k, n))
     return launch_umma_gemm(d_a, lda, d_b, ldb, m, k, n, d_out, ldo, umma_error_flag(), (cudaStream_t)stream);
@@ -387,7 +415,7 @@ int hcspmm_loa_reorder(const int32_t *d_rowptr, const int32_t *d_colidx, const i
 void hcspmm_graph_destroy(hcspmm_graph_t *g) {
   if (!g) return;
   cudaFree(g->rowptr); cudaFree(g->colidx); cudaFree(g->bp); cudaFree(g->etc);
-  cudaFree(g->etr); cudaFree(g->ht); cudaFree(g->x); cudaFree(g->y);
+  cudaFree(g->etr); cudaFree(g->ht); cudaFree(g->x); cudaFree(g->y); cudaFree(g->splits); cudaFree(g->ws);
   if (g->stream) cudaStreamDestroy(g->stream);
   delete g;
 }
@@ -431,7 +459,20 @@ int hcspmm_graph_create(const int32_t *h_rowptr, const int32_t *h_colidx, int32_
   rc = launch_preprocess(g->colidx, g->rowptr, n_rows, nnz, g->n_windows, classifier, g->bp,
                          g->etc, g->etr, g->ht, ws, ws_bytes, g->stream);
   if (rc) goto fail;
-  G_TRY(cudaStreamSynchronize(g->stream));
+  {
+    const size_t cnt = hcspmm_merge_path_count(n_rows, nnz, HCSPMM_SPLITS_CHUNK);
+    G_TRY(cudaMalloc(&g->splits, sizeof(int32_t) * cnt));
+    rc = launch_merge_path_splits(g->rowptr, n_rows, nnz, HCSPMM_SPLITS_CHUNK, g->splits, g->stream);
+    if (rc) goto fail;
+    g->n_splits = (int32_t)cnt - 1;
+    int32_t *h_ht = new int32_t[w];
+    cudaError_t e_ = cudaMemcpyAsync(h_ht, g->ht, sizeof(int32_t) * (size_t)g->n_windows, cudaMemcpyDeviceToHost, g->stream);
+    if (e_ == cudaSuccess) e_ = cudaStreamSynchronize(g->stream);
+    g->n_tc = 0;
+    for (int32_t i = 0; i < g->n_windows; ++i) g->n_tc += h_ht[i] == 1;
+    delete[] h_ht;
+    if (e_ != cudaSuccess) { set_error("graph_create: %s", cudaGetErrorString(e_)); rc = (int)e_; goto fail; }
+  }
   cudaFree(ws);
   *out = g;
   return 0;
@@ -449,16 +490,22 @@ int hcspmm_graph_spmm_host(hcspmm_graph_t *g, const float *h_x, int32_t dim, int
     return HCSPMM_E_INVALID;
   }
   if (dim != g->buf_dim) {
-    cudaFree(g->x); cudaFree(g->y);
-    g->x = g->y = nullptr; g->buf_dim = 0;
+    cudaFree(g->x); cudaFree(g->y); cudaFree(g->ws);
+    g->x = g->y = nullptr; g->ws = nullptr; g->buf_dim = 0;
+    g->ws_bytes = balanced_workspace_bytes(g->n_rows, g->nnz, dim);
+    CUDA_TRY(cudaMalloc(&g->ws, g->ws_bytes));
     CUDA_TRY(cudaMalloc(&g->x, sizeof(float) * (size_t)g->x_rows * dim));
     CUDA_TRY(cudaMalloc(&g->y, sizeof(float) * (size_t)(g->n_rows > 0 ? g->n_rows : 1) * dim));
     g->buf_dim = dim;
   }
   CUDA_TRY(cudaMemcpyAsync(g->x, h_x, sizeof(float) * (size_t)g->x_rows * dim,
                            cudaMemcpyHostToDevice, g->stream));
+  hcspmm_aux_t aux;
+  memset(&aux, 0, sizeof(aux));
+  aux.d_splits = g->splits; aux.splits_chunk = HCSPMM_SPLITS_CHUNK; aux.n_splits = g->n_splits;
+  aux.n_tc_windows = g->n_tc; aux.d_workspace = g->ws; aux.workspace_bytes = g->ws_bytes;
   int rc = launch_spmm(g->x, dim, g->x_rows, g->rowptr, g->colidx, g->bp, g->etc, g->etr, g->ht,
-                       g->n_rows, g->nnz, dim, precision, 0, g->y, dim, nullptr, g->stream);
+                       g->n_rows, g->nnz, dim, precision, 0, g->y, dim, &aux, g->stream);
   if (rc) return rc;
   CUDA_TRY(cudaMemcpyAsync(h_y, g->y, sizeof(float) * (size_t)g->n_rows * dim,
                            cudaMemcpyDeviceToHost, g->stream));

@@ -36,6 +36,7 @@ struct Tuning {
   int barrier_timeout_ms; // hcspmm_peer_barrier: how long a rank waits for a peer before flagging *d_err
   int dense_tma;   // 1: dense super-windows on the TMA gather4 kernel (dense_tma.cu), 0: cp.async kernels (dense.cu)
   int fuse_update; // 1: Aggregation + Update as one kernel when the dense plan covers the graph
+  int dense_min_rowlen; // dense plan: minimum mean stored entries per row of a 128-row super-window
 };
 Tuning &tuning();
 

@@ -78,7 +78,7 @@ size_t dense_plan_workspace_bytes(int32_t n_rows, int64_t nnz) {
 // one CTA: decide per super-window, then scan
 __global__ void __launch_bounds__(1024) dense_select_kernel(const int *__restrict__ rowptr, const int *__restrict__ ht,
                                                             const int *__restrict__ bp128, int n_rows, int n_windows,
-                                                            int n_super, int min_reuse_x2, int *sw_slot, int *sw_ids,
+                                                            int n_super, int min_reuse_x2, int min_rowlen, int *sw_slot, int *sw_ids,
                                                             int *sw_off, int *ht2, int *counts) {
   __shared__ int wbuf[32];
   __shared__ int s_carry_n, s_carry_c;
@@ -98,7 +98,12 @@ __global__ void __launch_bounds__(1024) dense_select_kernel(const int *__restric
         all_tc = all_tc && (empty || ht[w] != 0);
       }
       ucols = (bp128[sw] * BLK_W + DN_KC - 1) / DN_KC * DN_KC;
-      dense = all_tc && ucols > 0 && (2LL * e >= (long long)min_reuse_x2 * ucols);
+      // B200 re-fit of the selector at super-window granularity (benchmarks/selector_fit.py): the tcgen05 path wins
+      // when the rows are long enough on average (>= 8 entries: 97 % of the measured cells) -- the CUDA-core path
+      // is latency-bound on short rows, the dense contraction is indifferent to them -- and the columns are shared
+      // (reuse >= min_reuse: executed flops grow with the distinct columns, useful ones with the entries)
+      dense = all_tc && ucols > 0 && (2LL * e >= (long long)min_reuse_x2 * ucols) &&
+              (min_reuse_x2 == 0 || e >= (long long)min_rowlen * (r1 - r0));
     }
     // two block scans: dense index, column offset
     int vals[2] = {dense, dense ? ucols : 0}, exc[2], tot[2];
@@ -175,7 +180,8 @@ int dense_plan_count(const int32_t *colidx, const int32_t *rowptr, const int32_t
   PlanScratch s = carve(ws, n_rows, nnz);
   int rc = launch_preprocess_super(colidx, rowptr, n_rows, n_super, s.bp128, s.etc128, s.ht_tmp, s.pre_ws, stream);
   if (rc) return rc;
-  dense_select_kernel<<<1, 1024, 0, stream>>>(rowptr, ht, s.bp128, n_rows, n_windows, n_super, min_reuse_x2, s.sw_slot,
+  dense_select_kernel<<<1, 1024, 0, stream>>>(rowptr, ht, s.bp128, n_rows, n_windows, n_super, min_reuse_x2,
+                                              tuning().dense_min_rowlen, s.sw_slot,
                                               s.sw_ids, s.sw_off, s.ht2, s.counts);
   cudaError_t err = cudaGetLastError();
   if (err == cudaSuccess) err = cudaMemcpyAsync(h_counts, s.counts, 8, cudaMemcpyDeviceToHost, stream);

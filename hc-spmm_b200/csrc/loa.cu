@@ -7,7 +7,8 @@
 // skeleton is kept and everything INSIDE a step is made data-parallel on one persistent CTA of
 // 1024 threads (state in global memory / L2, a few block barriers per step, no host round trips):
 //
-//   scan     for every new block column c and every row r of c's CSC list that is still unvisited:
+//   scan     for every new block column c and every row r of c's CSC list that is still unvisited (work is dealt
+//            by flat position over all lists, so hub columns are shared by the whole CTA):
 //            cns[r] += 1 (atomicAdd) and r is discovered.  The reference discovers candidates in
 //            scan order and breaks profit ties by "first discovered" (strict '>' at :731,779), so
 //            each touch carries its position in the reference's nested-loop order and the vertex
@@ -138,17 +139,22 @@ __global__ void __launch_bounds__(LOA_THREADS, 1) loa_kernel(const LoaParams p) 
         carry += total;
       }
       __syncthreads();
-      for (int i = wid; i < scan_len; i += LOA_THREADS / 32) {   // one warp per column
-        const int c = scan_list[i];
-        const int j0 = p.rowptr_in[c], j1 = p.rowptr_in[c + 1];
-        const unsigned long long kb = key_base + (unsigned long long)p.pref[i];
-        for (int j = j0 + lane; j < j1; j += 32) {
-          const int r = p.colidx_in[j];
-          if (!__ldcg(p.visit + r)) {
-            atomicAdd(&p.cns[r], 1);
-            const unsigned long long old = atomicMin(&p.disc[r], kb + (unsigned long long)(j - j0));
-            if (old == DISC_NONE) p.pro[atomicAdd(&s_npro, 1)] = r;
-          }
+      // every touch (column i of the scan list, position j in its CSC list) is one unit of work, dealt to the
+      // threads by its FLAT position t in the reference's nested-loop order -- which is also its discovery key --
+      // so a hub column with 10^5 entries is spread over the whole CTA instead of being walked by one warp
+      // (one warp per column: 564 s on the products shape).  The column of t is found in the prefix sums.
+      for (long long t = tid; t < carry; t += LOA_THREADS) {
+        int lo = 0, hi = scan_len - 1;
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (p.pref[mid] <= t) lo = mid; else hi = mid - 1;
+        }
+        const int c = scan_list[lo];
+        const int r = p.colidx_in[p.rowptr_in[c] + (int)(t - p.pref[lo])];
+        if (!__ldcg(p.visit + r)) {
+          atomicAdd(&p.cns[r], 1);
+          const unsigned long long old = atomicMin(&p.disc[r], key_base + (unsigned long long)t);
+          if (old == DISC_NONE) p.pro[atomicAdd(&s_npro, 1)] = r;
         }
       }
       key_base += (unsigned long long)carry;

@@ -107,6 +107,61 @@ __global__ void __launch_bounds__(256) halo_pull_kernel(const float *const *__re
   }
 }
 
+// The same exchange as a PUSH: the OWNER writes the rows each peer's shard references straight into that peer's
+// operand buffer (NVLink stores are posted -- no request/response round trip as with loads).  send_row[j] for
+// j in [send_seg[s], send_seg[s+1]) are this rank's row indices peer s wants, ascending; they land in peer s's operand
+// at rows dst_base[s] + (j - send_seg[s]) (dst_base[s] already points at this rank's segment there).  Batches are dealt
+// round-robin over the peers starting at `first`, as in the pull.  The caller's next hcspmm_peer_barrier publishes
+// the rows (st.release.sys after a system fence) before any peer's SpMM reads them.
+__global__ void __launch_bounds__(256) halo_push_kernel(const float *__restrict__ src, long long lds,
+                                                        const int *__restrict__ send_row, const int *__restrict__ send_seg,
+                                                        float *const *__restrict__ dst_base, long long ldd, int world,
+                                                        unsigned long long peer_mask, int first, int c0, int width) {
+  __shared__ int s_seg[65];
+  __shared__ float *s_base[64];
+  __shared__ int s_list[64];
+  __shared__ int s_nb, s_ninc;
+  for (int i = threadIdx.x; i <= world; i += blockDim.x) s_seg[i] = send_seg[i];
+  for (int i = threadIdx.x; i < world; i += blockDim.x) s_base[i] = dst_base[i];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int nb = 0, ninc = 0;
+    for (int i = 0; i < world; ++i) {
+      const int o = (first + i) % world;
+      if (!((peer_mask >> o) & 1ull)) continue;
+      s_list[ninc++] = o;
+      nb = max(nb, (s_seg[o + 1] - s_seg[o] + PULL_ROWS - 1) / PULL_ROWS);
+    }
+    s_nb = nb;
+    s_ninc = ninc;
+  }
+  __syncthreads();
+  const int ninc = s_ninc;
+  if (ninc == 0) return;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  const int nvec = width >> 2;
+  const long long total = (long long)s_nb * ninc;
+  for (long long t = warp; t < total; t += n_warps) {
+    const int o = s_list[(int)(t % ninc)];
+    const int j0 = s_seg[o] + (int)(t / ninc) * PULL_ROWS, j1 = s_seg[o + 1];
+    if (j0 >= j1) continue;
+    const float *from[PULL_ROWS];
+#pragma unroll
+    for (int j = 0; j < PULL_ROWS; ++j) from[j] = src + (long long)__ldg(send_row + min(j0 + j, j1 - 1)) * lds + c0;
+    float *to = s_base[o] + (long long)(j0 - s_seg[o]) * ldd + c0;
+    for (int v = lane; v < nvec; v += 32) {
+      float4 x[PULL_ROWS];
+#pragma unroll
+      for (int j = 0; j < PULL_ROWS; ++j) x[j] = ldg_f4(from[j] + v * 4);
+#pragma unroll
+      for (int j = 0; j < PULL_ROWS; ++j)
+        if (j0 + j < j1) *reinterpret_cast<float4 *>(to + (long long)j * ldd + v * 4) = x[j];
+    }
+  }
+}
+
 }  // namespace hcspmm
 
 using namespace hcspmm;
@@ -188,6 +243,30 @@ int hcspmm_halo_pull(const float *const *d_peer_x, int64_t lds, const int32_t *d
                                                                      first_owner % world, col0, width, d_dst, ldd);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("halo_pull: %s", cudaGetErrorString(e)); return (int)e; }
+  return 0;
+}
+
+int hcspmm_halo_push(const float *d_src, int64_t lds, const int32_t *d_send_row, const int32_t *d_send_seg,
+                     float *const *d_dst_base, int64_t ldd, int32_t world, uint64_t peer_mask, int32_t first_peer,
+                     int32_t rows, int32_t col0, int32_t width, void *stream) {
+  if (rows <= 0 || width == 0 || peer_mask == 0) return 0;
+  if (!d_src || !d_send_row || !d_send_seg || !d_dst_base || world < 1 || world > 64 || width < 0 || col0 < 0 ||
+      first_peer < 0) {
+    set_error("halo_push: bad argument");
+    return HCSPMM_E_INVALID;
+  }
+  if ((width & 3) || (col0 & 3) || (lds & 3) || (ldd & 3) || (reinterpret_cast<uintptr_t>(d_src) & 15)) {
+    set_error("halo_push: width, col0 and leading dims must be multiples of 4 floats, src 16-byte aligned");
+    return HCSPMM_E_ALIGN;
+  }
+  const long long warps = ((long long)rows + PULL_ROWS - 1) / PULL_ROWS + world;
+  long long grid = (warps + 7) / 8;
+  const long long cap = tuning().pull_ctas > 0 ? tuning().pull_ctas : 148 * 8;
+  if (grid > cap) grid = cap;
+  halo_push_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(d_src, lds, d_send_row, d_send_seg, d_dst_base, ldd,
+                                                                     world, peer_mask, first_peer % world, col0, width);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("halo_push: %s", cudaGetErrorString(e)); return (int)e; }
   return 0;
 }
 

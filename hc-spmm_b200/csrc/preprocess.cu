@@ -44,6 +44,15 @@ __device__ __forceinline__ int classify(int size, unsigned n_edges, int num, int
   }
   float sf = (float)size;
   float df = __fdiv_rn((float)n_edges, (float)(int)((unsigned)num << 7));
+  if (mode == HCSPMM_CLASSIFIER_B200_WINDOW) {
+    // The reference's own recipe (technical report IV-C) re-run on B200 (benchmarks/selector_fit.py,
+    // profiles/r2_selector_fit.json): 16-row synthetic windows, 1..130 distinct columns, sparsity 1/16..15/16, CUDA-core
+    // path against the per-window mma.sync path at dim 128, logistic regression on the reference's two features.
+    // Same form as :261 -- score > 0 -> CUDA cores -- with the B200 coefficients; no U <= 32 guard (this
+    // implementation has no MAX_BLK), but the per-window path keeps <= 1024 condensed columns resident.
+    const double zb = (double)sf * -0.02312523 + (double)df * -9.74306426 + 4.93743285;
+    return (!(zb > 0.0) && num * BLK_W <= 1024) ? 1 : 0;
+  }
   double t = __dmul_rn((double)df, -6.578043);
   double u = __fma_rn((double)sf, 0.19854024, t);
   double z = __dadd_rn(u, -3.14922857);
@@ -249,7 +258,7 @@ int launch_preprocess(const int32_t *colidx, const int32_t *rowptr, int32_t n_ro
               n_rows);
     return HCSPMM_E_INVALID;
   }
-  if (mode < 0 || mode > HCSPMM_CLASSIFIER_ALL_TC) {
+  if (mode < 0 || mode > HCSPMM_CLASSIFIER_B200_WINDOW) {
     set_error("preprocess: unknown classifier mode %d", mode);
     return HCSPMM_E_INVALID;
   }

@@ -956,6 +956,15 @@ __global__ void unpad_rows_kernel(const float *__restrict__ src, int dpad, int d
   dst[r * ldd + c] = src[r * dpad + c];
 }
 
+void launch_pad_rows(const float *src, int64_t lds, int32_t rows, int32_t dim, float *dst, int32_t dpad, cudaStream_t stream) {
+  const long long total = (long long)rows * dpad;
+  if (total > 0) pad_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(src, lds, dim, dst, dpad, total);
+}
+void launch_unpad_rows(const float *src, int32_t dpad, int32_t rows, int32_t dim, float *dst, int64_t ldd, cudaStream_t stream) {
+  const long long total = (long long)rows * dim;
+  if (total > 0) unpad_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(src, dpad, dim, dst, ldd, total);
+}
+
 // X (FP32, leading dim ldx) -> dense BF16 copy [rows, dim], round to nearest even
 __global__ void f32_to_bf16_rows_kernel(const float *__restrict__ x, long long ldx, int dim2, uint32_t *__restrict__ xb,
                                         long long ldb2, long long total2) {

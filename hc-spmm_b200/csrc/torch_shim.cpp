@@ -354,11 +354,11 @@ torch::Tensor gemm_tf32(torch::Tensor a, torch::Tensor b) {
 }
 
 std::string set_classifier(const std::string &mode) {
-  static const char *names[] = {"shipped", "intended", "b200", "all_cuda", "all_tc"};
+  static const char *names[] = {"shipped", "intended", "b200", "all_cuda", "all_tc", "b200_window"};
   std::string old = names[g_classifier];
-  for (int i = 0; i < 5; ++i)
+  for (int i = 0; i < 6; ++i)
     if (mode == names[i]) { g_classifier = i; return old; }
-  TORCH_CHECK(false, "unknown classifier '", mode, "' (shipped|intended|b200|all_cuda|all_tc)");
+  TORCH_CHECK(false, "unknown classifier '", mode, "' (shipped|intended|b200|all_cuda|all_tc|b200_window)");
 }
 
 std::string set_precision(const std::string &mode) {

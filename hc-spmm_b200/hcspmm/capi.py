@@ -14,7 +14,7 @@ import torch
 from .build import LIB_PATH
 
 BLK_H, BLK_W = 16, 8
-CLASSIFIERS = {"shipped": 0, "intended": 1, "b200": 2, "all_cuda": 3, "all_tc": 4}
+CLASSIFIERS = {"shipped": 0, "intended": 1, "b200": 2, "all_cuda": 3, "all_tc": 4, "b200_window": 5}
 PRECISIONS = {"tf32": 0, "tf32x2": 1, "fp32": 2, "bf16": 3, "bf16_stored": 4}
 
 EXPORTS = [
@@ -26,7 +26,7 @@ EXPORTS = [
     "hcspmm_peer_alloc", "hcspmm_peer_open", "hcspmm_peer_close", "hcspmm_peer_free", "hcspmm_peer_barrier",
     "hcspmm_halo_pull", "hcspmm_debug_l2_gather",
     "hcspmm_merge_path_count", "hcspmm_merge_path_splits", "hcspmm_spmm_workspace_bytes", "hcspmm_spmm_aux",
-    "hcspmm_f32_to_bf16", "hcspmm_spmm_gemm_aux",
+    "hcspmm_f32_to_bf16", "hcspmm_spmm_gemm_aux", "hcspmm_halo_push",
 ]
 
 _lib = None
@@ -94,6 +94,7 @@ def lib() -> ctypes.CDLL:
         L.hcspmm_spmm_aux.argtypes = [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _int, _int,
                                       _vp, _i64, ctypes.POINTER(Aux), _vp]
         L.hcspmm_f32_to_bf16.argtypes = [_vp, _i64, _i32, _i32, _vp, _i64, _vp]
+        L.hcspmm_halo_push.argtypes = [_vp, _i64, _vp, _vp, _vp, _i64, _i32, ctypes.c_uint64, _i32, _i32, _i32, _i32, _vp]
         L.hcspmm_spmm_gemm_aux.argtypes = [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _int, _vp, _i64,
                                            _i32, _vp, _i64, _vp, _i64, ctypes.POINTER(Aux), _vp]
         _lib = L

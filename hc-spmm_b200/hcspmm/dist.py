@@ -26,6 +26,9 @@ Schedules:
                 flag barrier of ours (hcspmm_peer_barrier).  No collective, no packing pass on the
                 owner, nothing sent that is not needed.  `n_slabs` > 1 pulls feature slab k+1 on a
                 high-priority stream while the SpMM of slab k runs.
+  * "push":     the same halo rows over the same peer-mapped buffers, but WRITTEN by their owner (hcspmm_halo_push)
+                before the barrier instead of read by the consumer after it: NVLink stores are posted, loads wait
+                for a response.
   * "auto":     CUDA: "peer".  Otherwise "halo" when it moves <= 0.6 of the all-gather's rows
                 (decided once, collectively), else "gather".
 gather / slabs: shards are padded to the largest shard so the collective is a plain equal-size
@@ -68,7 +71,7 @@ def _default_spmm():
 class ShardedGraph:
     def __init__(self, rowptr: torch.Tensor, colidx: torch.Tensor, group=None, schedule: str = "gather",
                  n_slabs: int = 1, spmm=None, preprocess=None, cuts=None, n_passes: int = 1,
-                 operand: str = "fp32"):
+                 operand: str = "fp32", single: bool = False):
         """rowptr / colidx: the FULL graph's CSR on this rank's device (identical on every rank).
         cuts: reuse another ShardedGraph's row cuts (the transposed graph for backward must be
         partitioned like the forward one).
@@ -82,8 +85,10 @@ class ShardedGraph:
         assert operand in ("fp32", "bf16")
         self.operand = operand
         self.group = group
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        # single = True: the whole graph on this process even inside an initialised process group (the
+        # single-GPU reference a multi-GPU run compares its losses with)
+        self.world = dist.get_world_size(group) if (dist.is_initialized() and not single) else 1
+        self.rank = dist.get_rank(group) if (dist.is_initialized() and not single) else 0
         self.n = rowptr.numel() - 1
         self.cuts = list(cuts) if cuts is not None else partition.window_cuts(rowptr, self.world)
         self.r0, self.r1 = self.cuts[self.rank], self.cuts[self.rank + 1]
@@ -98,6 +103,9 @@ class ShardedGraph:
         self.nnz_local = ci_l.numel()
         self.halo = None
         self.peer = None
+        self.push = schedule == "push"
+        if self.push:
+            schedule = "peer"
         if self.world > 1 and schedule in ("auto", "peer") and dev.type == "cuda":
             # NVLink peer memory (CUDA IPC between the ranks' processes); "auto" falls back to the NCCL
             # schedules, on every rank together, where the platform refuses it
@@ -109,7 +117,7 @@ class ShardedGraph:
                 if schedule == "peer":
                     raise
         if self.world > 1 and schedule in ("halo", "auto", "peer"):
-            self._setup_halo(ci64, bounds, dev, lists_only=schedule == "peer")
+            self._setup_halo(ci64, bounds, dev, lists_only=schedule == "peer" and not self.push)
             if schedule == "auto" and self.halo["ratio"] > 0.6:
                 self.halo = None
             self.schedule = schedule if schedule == "peer" else (
@@ -123,8 +131,12 @@ class ShardedGraph:
             owner = torch.bucketize(ci64, bounds[1:-1], right=True)
             self.colidx = (ci64 - bounds[owner] + owner * self.max_rows).to(torch.int32).contiguous()
         del ci64
+        self._fused, self._gemm = None, torch.mm
         if spmm is None:
             spmm, preprocess = _default_spmm()
+            import HCSPMM
+            self._fused = lambda x, rp_, ci_, pre_, w: HCSPMM.forward_fixed32_fused(x, rp_, ci_, *pre_, w)
+            self._gemm = lambda a, b: HCSPMM.gemm_tf32(a.contiguous(), b.contiguous())
         self._spmm = spmm
         self.pre = preprocess(self.colidx, self.rowptr) if preprocess is not None else ()
         self.passes = None
@@ -133,6 +145,8 @@ class ShardedGraph:
             self._setup_passes(preprocess)
         self._bufs = {}
         self._comm_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+        if self.push and self.peer is not None:
+            self.schedule = "push"
 
     def _setup_halo(self, ci64, bounds, dev, lists_only=False):
         """Which rows of X this shard needs from every owner, and which of its own rows every peer needs."""
@@ -158,6 +172,13 @@ class ShardedGraph:
         send_idx = torch.empty(sum(sc), dtype=torch.int64, device=dev)
         dist.all_to_all_single(send_idx, want, output_split_sizes=sc, input_split_sizes=rc, group=self.group)
         self.halo = dict(ids=ids, rows=int(ids.numel()), recv=rc, send=sc, send_idx=send_idx, ratio=ratio)
+        if self.push:       # owner-side lists of the push schedule + the consumer-side layout of the pull model
+            seg = torch.zeros(self.world + 1, dtype=torch.int32, device=dev)
+            seg[1:] = torch.cumsum(recv_counts, 0).to(torch.int32)
+            send_seg = torch.zeros(self.world + 1, dtype=torch.int32, device=dev)
+            send_seg[1:] = torch.cumsum(send_counts, 0).to(torch.int32)
+            self.halo.update(seg=seg, src_row=want.to(torch.int32), send_seg=send_seg,
+                             send_row=send_idx.to(torch.int32).contiguous())
 
     # ------------------------------------------------------------------------------------------
     def shard_rows(self, x_full: torch.Tensor) -> torch.Tensor:
@@ -184,6 +205,30 @@ class ShardedGraph:
         if self.schedule == "slabs" and self.n_slabs > 1 and dim >= 8 * self.n_slabs and self._comm_stream is not None:
             return self._aggregate_slabs(x_local)
         return self._spmm(self.exchange(x_local), self.rowptr, self.colidx, self.pre)
+
+    def aggregate_fused(self, x_local: torch.Tensor, weights: torch.Tensor):
+        """(out, Z) = ((A_r X) W, A_r X): the exchange, then the reference's fused Aggregation + Update entry point
+        (HCSPMM.forward_fixed32_fused: one tcgen05 kernel when the shard's dense plan covers it, else aggregation +
+        TMA Update GEMM) on the exchanged operand.  Injected operators (CPU tests) and BF16 operands take the two
+        steps separately."""
+        if self._fused is None:
+            z = self.aggregate(x_local)
+            return self._gemm(z, weights), z
+        if self.world == 1:
+            operand = x_local.contiguous()
+        else:
+            if self.peer is not None:
+                self.peer.check()
+            operand = self.exchange(x_local)
+            if operand.dtype != torch.float32 or not operand.is_contiguous():
+                z = self.aggregate(x_local)
+                return self._gemm(z, weights), z
+        out, z = self._fused(operand, self.rowptr, self.colidx, self.pre, weights)
+        return out, z
+
+    def update(self, h: torch.Tensor, weights: torch.Tensor) -> torch.Tensor:
+        """The row-local Update product H W on the library's TF32 GEMM (TMA + tcgen05)."""
+        return self._gemm(h, weights)
 
     @property
     def x_rows(self) -> int:
@@ -272,9 +317,15 @@ class ShardedGraph:
             own0 = int(h["seg"][self.rank])
             firsts = [None] * self.world                         # every rank's own-segment offset in ITS operand
             dist.all_gather_object(firsts, own0, group=self.group)
+            segs = [None] * self.world                           # push: where MY rows start in every peer's operand
+            dist.all_gather_object(segs, h["seg"].tolist(), group=self.group)
             for _ in range(2):                                   # alternate: see csrc/peer.cu header
                 ptr, ptrs = pm.shared(h["rows"] * dpad * esz)
-                table = torch.tensor([p + f * dpad * esz for p, f in zip(ptrs, firsts)], dtype=torch.int64, device=dev)
+                if self.push:
+                    table = torch.tensor([p + segs[s][self.rank] * dpad * esz for s, p in enumerate(ptrs)],
+                                         dtype=torch.int64, device=dev)
+                else:
+                    table = torch.tensor([p + f * dpad * esz for p, f in zip(ptrs, firsts)], dtype=torch.int64, device=dev)
                 t = pm.tensor(ptr, (h["rows"], dpad), torch.int16).view(torch.bfloat16) if b16 else \
                     pm.tensor(ptr, (h["rows"], dpad))
                 slots.append((t, table))
@@ -288,10 +339,17 @@ class ShardedGraph:
             HCSPMM.f32_to_bf16_into(x_local, own)                # one rounding per row, on its owner
         else:
             own[:, :dim].copy_(x_local)                          # pad columns stay zero
+        if self.push:                                            # owner writes its rows into the peers' operands
+            from . import peer as _peer
+            src = own.view(torch.float32) if b16 else own
+            mask = ((1 << self.world) - 1) & ~(1 << self.rank)
+            _peer.halo_push(src, h["send_row"], h["send_seg"], self._peer_tab, src.stride(0), self.world, mask, self.rank + 1)
         self.peer.barrier()
         return cat, dpad
 
     def _pull_halo(self, cat, dpad, col0=0, width=None, mask=None):
+        if self.push:                                            # the owners already wrote every row (before the barrier)
+            return
         h = self.halo                                            # own rows are already in place: own bit clear
         mask = (((1 << self.world) - 1) & ~(1 << self.rank)) if mask is None else mask
         if cat.dtype == torch.bfloat16:                          # the pull moves bytes: count a row in float units
@@ -305,8 +363,8 @@ class ShardedGraph:
     def _aggregate_peer(self, x_local: torch.Tensor) -> torch.Tensor:
         dim, dev = x_local.shape[1], x_local.device
         cat, dpad = self._peer_stage(x_local.float())
-        n_slabs = self.n_slabs if (dpad >= 32 * self.n_slabs and cat.dtype == torch.float32) else 1
-        if self.passes is not None:
+        n_slabs = self.n_slabs if (dpad >= 32 * self.n_slabs and cat.dtype == torch.float32 and not self.push) else 1
+        if self.passes is not None and not self.push:
             p0, p1 = self.passes
             y = torch.empty(self.n_local, dpad, device=dev)
             cur, comm = torch.cuda.current_stream(dev), self._hi_stream
@@ -425,14 +483,52 @@ class ShardedAggregate(torch.autograd.Function):
         return ctx.graph_t.aggregate(d_y.contiguous()), None, None
 
 
+class ShardedGCNLayer(torch.autograd.Function):
+    """X' = A (X W) on a row-partitioned graph -- the routing of the reference's GCN Functions
+    (GNN_model.py:61-162; hcspmm/gnn.py "pre"): forward = Update GEMM, then the exchanged aggregation; backward =
+    the FUSED entry point (dX, d(XW)) = ((A^T dY) W^T, A^T dY) on the exchanged dY, then dW = X^T d(XW)."""
+
+    @staticmethod
+    def forward(ctx, x_local, weights, graph: ShardedGraph, graph_t):
+        ctx.graph_t = graph_t if graph_t is not None else graph
+        ctx.save_for_backward(x_local, weights)
+        return graph.aggregate(graph.update(x_local, weights))
+
+    @staticmethod
+    def backward(ctx, d_y):
+        x_local, weights = ctx.saved_tensors
+        d_x, d_xw = ctx.graph_t.aggregate_fused(d_y.contiguous(), weights.t())
+        return d_x, torch.mm(x_local.t(), d_xw), None, None
+
+
+class ShardedGINLayer(torch.autograd.Function):
+    """X' = (A X) W (GNN_model.py:166-232; hcspmm/gnn.py "post"): forward = the fused entry point on the exchanged
+    X; backward = dAgg = dY W^T (Update GEMM), dW = Agg^T dY, dX = A^T dAgg (exchanged aggregation)."""
+
+    @staticmethod
+    def forward(ctx, x_local, weights, graph: ShardedGraph, graph_t):
+        ctx.graph, ctx.graph_t = graph, graph_t if graph_t is not None else graph
+        out, agg = graph.aggregate_fused(x_local, weights)
+        ctx.save_for_backward(agg, weights)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_y):
+        agg, weights = ctx.saved_tensors
+        d_y = d_y.contiguous()
+        d_agg = ctx.graph.update(d_y, weights.t())
+        return ctx.graph_t.aggregate(d_agg), torch.mm(agg.t(), d_y), None, None
+
+
 class DistGCN(torch.nn.Module):
-    """2+-layer GCN of HC-SpMM_main.py:67-87 on a row-partitioned graph: every rank holds its rows of
-    X and of the labels and a replica of the weights; Update GEMMs are row-local, Aggregations go
-    through ShardedAggregate, weight gradients are summed with one all-reduce per step."""
+    """2+-layer GCN / GIN of HC-SpMM_main.py:67-87 on a row-partitioned graph: every rank holds its rows of X and of
+    the labels and a replica of the weights; Update GEMMs are row-local (the library's TMA + tcgen05 GEMM), every
+    Aggregation goes through the exchange and the HCSPMM entry points -- the fused ones where the reference uses them
+    (ShardedGCNLayer / ShardedGINLayer) -- and weight gradients are summed with one all-reduce per step."""
 
     def __init__(self, graph: ShardedGraph, in_dim, hidden, classes, num_layers=2, seed=0, graph_t=None,
                  order: str = "auto"):
-        """order: "update_first" = A (H W) (GCN), "aggregate_first" = (A H) W (GIN), "auto" = the cheaper."""
+        """order: "update_first" = A (H W) (GCN), "aggregate_first" = (A H) W (GIN), "auto" = the cheaper per layer."""
         super().__init__()
         self.order = order
         g = torch.Generator().manual_seed(seed)            # identical replicas on every rank
@@ -445,13 +541,11 @@ class DistGCN(torch.nn.Module):
     def forward(self, x_local):
         h = x_local
         for i, w in enumerate(self.weights):
-            # A (H W) = (A H) W: exchange and aggregate at the narrower of the two widths -- the
-            # all-gather moves N * width * 4 bytes per rank and the SpMM gathers nnz * width * 4
+            # A (H W) = (A H) W: exchange and aggregate at the narrower of the two widths -- the exchange moves
+            # rows * width * 4 bytes per rank and the SpMM gathers nnz * width * 4
             update_first = {"update_first": True, "aggregate_first": False}.get(self.order, w.shape[1] <= w.shape[0])
-            if update_first:
-                h = ShardedAggregate.apply(torch.mm(h, w), self.graph, self.graph_t)
-            else:
-                h = torch.mm(ShardedAggregate.apply(h, self.graph, self.graph_t), w)
+            layer = ShardedGCNLayer if update_first else ShardedGINLayer
+            h = layer.apply(h, w, self.graph, self.graph_t)
             if i + 1 < len(self.weights):
                 h = torch.relu(h)
         return torch.nn.functional.log_softmax(h, dim=1)

@@ -117,3 +117,16 @@ def halo_pull(peer_table: torch.Tensor, lds: int, src_row: torch.Tensor, seg: to
                                                 dst.stride(0), torch.cuda.current_stream(dst.device).cuda_stream),
                     "hcspmm_halo_pull")
     return dst
+
+
+def halo_push(src: torch.Tensor, send_row: torch.Tensor, send_seg: torch.Tensor, dst_table: torch.Tensor, ldd: int,
+              world: int, peer_mask: int, first_peer: int = 0, col0: int = 0, width: int | None = None):
+    """hcspmm_halo_push on the current stream: peer s's operand rows dst_table[s] + j * ldd <- src[send_row[send_seg[s] + j]]
+    for every peer in peer_mask, round-robin from first_peer.  src is FP32 (or a float32 view of bfloat16 rows)."""
+    width = src.shape[1] - col0 if width is None else width
+    rows = int(send_row.numel())
+    with torch.cuda.device(src.device):
+        capi._check(capi.lib().hcspmm_halo_push(src.data_ptr(), src.stride(0), send_row.data_ptr(), send_seg.data_ptr(),
+                                                dst_table.data_ptr(), ldd, world, peer_mask, first_peer, rows, col0, width,
+                                                torch.cuda.current_stream(src.device).cuda_stream),
+                    "hcspmm_halo_push")

@@ -50,6 +50,10 @@ extern "C" {
 #define HCSPMM_CLASSIFIER_B200      2
 #define HCSPMM_CLASSIFIER_ALL_CUDA  3
 #define HCSPMM_CLASSIFIER_ALL_TC    4
+/* 5: the reference's logistic form (:261) with coefficients RE-FITTED ON B200 by the paper's recipe (16-row synthetic
+ *    windows, CUDA-core path vs per-window mma.sync path, dim 128): label 1 iff
+ *    -0.02312523 (U-1) - 9.74306426 density + 4.93743285 <= 0.  benchmarks/selector_fit.py, profiles/r2_selector_fit.json */
+#define HCSPMM_CLASSIFIER_B200_WINDOW 5
 
 /* Arithmetic of windows labelled "tensor core" (hybrid_type != 0).  CUDA-core
  * windows are always an exact FP32 sum, as in the reference (:982-990).
@@ -84,6 +88,9 @@ const char *hcspmm_last_error(void);
  *   "umma"       1: tcgen05 / TMEM dense super-window kernel (hcspmm_spmm_plan); 0: per-window paths
  *   "umma_gemm"  Update GEMM kernel: 2 = TMA + tcgen05 persistent warp-specialised kernel, 1 = register-staged
  *                tcgen05 kernel, 0 = mma.sync kernel (also the fallback for unaligned operands)
+ *   "dense_min_rowlen" a super-window joins the dense plan only if it holds >= this many stored entries per row on
+ *                average (default 8: the boundary the B200 re-fit found, profiles/r2_selector_fit.json); the
+ *                min_reuse_x2 argument of hcspmm_dense_plan_count applies as well (0 = force: no threshold at all)
  *   "dense_tma"  which kernel multiplies dense super-windows.  csrc/dense_tma.cu is the five-role kernel (TMA for
  *                the plan's index chunks and W^T, dedicated epilogue warps, optional FUSED Update); csrc/dense.cu holds
  *                the earlier producer/issuer kernels.  1 (default): dense.cu for plain aggregation (measured fastest,
@@ -296,6 +303,15 @@ int hcspmm_peer_barrier(int32_t *const *d_flag_ptrs, int32_t rank, int32_t world
 int hcspmm_halo_pull(const float *const *d_peer_x, int64_t lds, const int32_t *d_src_row, const int32_t *d_seg,
                      int32_t world, uint64_t owner_mask, int32_t first_owner, int32_t rows, int32_t col0, int32_t width,
                      float *d_dst, int64_t ldd, void *stream);
+
+/* The same exchange as a PUSH by the owner: rows d_send_row[j], j in [d_send_seg[s], d_send_seg[s+1]), of d_src are
+ * written to peer s's operand at d_dst_base[s] + (j - d_send_seg[s]) * ldd (d_dst_base[s] = peer s's mapped operand
+ * buffer advanced to this rank's segment), for every peer whose bit is set in peer_mask.  rows = d_send_seg[world].
+ * NVLink stores are posted, loads wait for a response: measured 2 GPUs, 512-byte rows, pull 470 GB/s per rank.
+ * The caller's following hcspmm_peer_barrier makes the rows visible to the peers' SpMM.                          */
+int hcspmm_halo_push(const float *d_src, int64_t lds, const int32_t *d_send_row, const int32_t *d_send_seg,
+                     float *const *d_dst_base, int64_t ldd, int32_t world, uint64_t peer_mask, int32_t first_peer,
+                     int32_t rows, int32_t col0, int32_t width, void *stream);
 
 /* d_out[r, 0..dim) (bfloat16, row pitch ld_out elements) = round-to-nearest-even of d_x[r, 0..dim). */
 int hcspmm_f32_to_bf16(const float *d_x, int64_t ldx, int32_t rows, int32_t dim, void *d_out, int64_t ld_out,

@@ -44,7 +44,8 @@ def _worker(rank, world, port, q):
         d_rp, d_ci = torch.from_numpy(rp).to(dev), torch.from_numpy(ci).to(dev)
         results = []
         cases = [("peer", 1, 1, "fp32"), ("gather", 1, 1, "fp32"), ("halo", 1, 1, "fp32"), ("peer", 2, 1, "fp32"),
-                 ("peer", 1, 2, "fp32"), ("peer", 1, 1, "bf16"), ("auto", 1, 1, "fp32")]
+                 ("peer", 1, 2, "fp32"), ("peer", 1, 1, "bf16"), ("auto", 1, 1, "fp32"), ("push", 1, 1, "fp32"),
+                 ("push", 1, 1, "bf16")]
         for schedule, slabs, passes, operand in cases:
             g = hd.ShardedGraph(d_rp, d_ci, schedule=schedule, n_slabs=slabs, n_passes=passes, operand=operand)
             for dim in (128, 100, 64):

@@ -375,7 +375,8 @@ def test_spmm_bf16_stored_operand(capi, name):
 
 # ---- TMA + tcgen05 persistent Update GEMM (csrc/update_gemm.cu) ---------------------------------
 @pytest.mark.parametrize("m,k,n", [(128, 32, 32), (128, 64, 256), (1000, 128, 128), (513, 100, 48), (4096, 256, 256),
-                                   (300, 36, 16), (2000, 128, 320), (77, 8, 4), (40000, 128, 128), (19000, 100, 128)])
+                                   (300, 36, 16), (2000, 128, 320), (77, 8, 4), (40000, 128, 128), (19000, 100, 128),
+                                   (40000, 47, 128), (40000, 128, 47), (30000, 47, 47)])   # odd widths: padded copies
 @pytest.mark.parametrize("rounders", [1, 0])
 def test_gemm_tma(capi, m, k, n, rounders):
     """rounders = 1: cvt.rna in shared memory (the reference's rounding, oracle-tight); 0: the tensor map's
@@ -582,6 +583,36 @@ def test_b200_selector_labels_candidates_and_wide_dense(capi):
             assert capi.lib().hcspmm_debug_umma_error() == 0
     finally:
         capi.set_tuning("umma", old)
+
+
+def test_b200_refit_rules(capi):
+    """The re-fitted selector (benchmarks/selector_fit.py): (a) `b200_window` labels a 16-row window tensor-core iff the
+    reference's logistic form with the B200 coefficients says so; (b) a super-window joins the dense plan only when its
+    rows hold >= 8 entries on average (knob dense_min_rowlen)."""
+    for name in ("sbm_1024", "rmat_hub_4096", "dense_2048", "band2_320"):
+        rp, ci = GRAPHS[name]
+        n = rp.size - 1
+        bp, etc, etr, ht = (t.cpu().numpy() for t in capi.preprocess(dev(ci), dev(rp), "b200_window"))
+        want = np.zeros_like(ht)
+        for w in range((n + 15) // 16):
+            e0, e1 = rp[16 * w], rp[min(16 * w + 16, n)]
+            if e1 == e0:
+                continue
+            u = int(etc[e0:e1].max()) + 1
+            dens = np.float32(e1 - e0) / np.float32(bp[w] * 128)
+            z = float(u - 1) * -0.02312523 + float(dens) * -9.74306426 + 4.93743285
+            want[w] = int(not (z > 0.0) and bp[w] * 8 <= 1024)
+        assert np.array_equal(ht, want), name
+    rp, ci = GRAPHS["band2_320"]                       # 4 entries per row, every column shared by 5 rows
+    d_rp, d_ci = dev(rp), dev(ci)
+    bp, etc, etr, ht = capi.preprocess(d_ci, d_rp, "all_tc")
+    assert capi.DensePlan(d_rp, d_ci, etr, ht, min_reuse=2.0).n_dense == 0           # rows too short for tcgen05 to pay
+    old = capi.set_tuning("dense_min_rowlen", 1)
+    try:
+        assert capi.DensePlan(d_rp, d_ci, etr, ht, min_reuse=2.0).n_dense == 3
+    finally:
+        capi.set_tuning("dense_min_rowlen", old)
+    assert capi.DensePlan(d_rp, d_ci, etr, ht, min_reuse=0.0).n_dense == 3           # 0 = force
 
 
 # ---- BF16-stored X --------------------------------------------------------------------------------

@@ -58,3 +58,29 @@ def test_halo_pull_rejects_misaligned():
     d = torch.zeros(8, 6, device="cuda")
     rc = L.hcspmm_halo_pull(d.data_ptr(), 6, d.data_ptr(), d.data_ptr(), 1, 1, 0, 8, 0, 6, d.data_ptr(), 6, None)
     assert rc == -2
+
+
+@pytest.mark.parametrize("dim,col0,width", [(128, 0, 128), (64, 16, 32), (256, 0, 256)])
+def test_halo_push_matches_indexing(dim, col0, width):
+    """The owner-side push: rows send_row[j] of the local shard land in each consumer's operand segment, in list
+    order; three local buffers stand in for three peers, the caller's own bit is left clear."""
+    from hcspmm import peer
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(dim + col0)
+    src = torch.randn(500, dim, device=dev, generator=g)
+    counts = [123, 0, 77]                                        # what peers 0 / 1 (self) / 2 want
+    lists = [torch.sort(torch.randperm(500, device=dev, generator=g)[:c]).values for c in counts]
+    send_row = torch.cat(lists).to(torch.int32)
+    send_seg = torch.tensor([0, 123, 123, 200], dtype=torch.int32, device=dev)
+    peers = [torch.full((300, dim), -1.0, device=dev) for _ in range(3)]
+    offs = [40, 0, 11]                                           # where this rank's segment starts in each operand
+    table = torch.tensor([p.data_ptr() + o * dim * 4 for p, o in zip(peers, offs)], dtype=torch.int64, device=dev)
+    peer.halo_push(src, send_row, send_seg, table, dim, 3, 0b101, first_peer=2, col0=col0, width=width)
+    torch.cuda.synchronize()
+    for s in (0, 2):
+        got = peers[s][offs[s]: offs[s] + counts[s], col0:col0 + width]
+        assert torch.equal(got, src[lists[s].long(), col0:col0 + width])
+        rest = peers[s].clone()
+        rest[offs[s]: offs[s] + counts[s], col0:col0 + width] = -1.0
+        assert bool((rest == -1.0).all())                        # nothing else was written
+    assert bool((peers[1] == -1.0).all())
