@@ -39,6 +39,7 @@ def main():
     ap.add_argument("--model", default="gcn", choices=["gcn", "gin"],
                     help="gcn: X' = A (X W) (GNN_model.py:61-162); gin: X' = (A X) W (GNN_model.py:166-232)")
     ap.add_argument("--dense", action="store_true", help="tcgen05 dense super-window plans")
+    ap.add_argument("--profile", action="store_true", help="print the CUDA-time breakdown of one epoch (torch.profiler)")
     ap.add_argument("--operand", default="fp32", choices=["fp32", "bf16"], help="N > 1: exchange operand storage")
     ap.add_argument("--fp32-matmul", action="store_true",
                     help="Update GEMMs (torch.mm) in full FP32; default TF32 like the reference's stack "
@@ -113,6 +114,16 @@ def main():
             losses.append(float(l))
     times.sort()
     g.check()
+    if args.profile and rank == 0:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            opt.zero_grad()
+            loss = model.loss(x, y)
+            loss.backward()
+            model.sync_grads()
+            opt.step()
+            torch.cuda.synchronize()
+        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=90), file=sys.stderr)
 
     # where an epoch goes: exchange and local SpMM of every aggregation width, timed on their own (max over ranks)
     def tm(fn, k=5):

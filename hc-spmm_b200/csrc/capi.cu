@@ -17,7 +17,7 @@ void set_error(const char *fmt, ...) {
 }
 
 Tuning &tuning() {
-  static Tuning t = {1024, 0, 1, 1, 0, 1, 1, 2, 1, 1, 1, 0, 0, 64, 1, 0, 2048, 10000, 1, 1, 8};
+  static Tuning t = {1024, 0, 1, 1, 0, 1, 1, 2, 1, 1, 1, 0, 0, 64, 1, 0, 2048, 10000, 1, 1, 8, 72};
   return t;
 }
 
@@ -147,6 +147,7 @@ int hcspmm_set_tuning(const char *key, int value) {
   else if (key && !strcmp(key, "dense_tma")) slot = &tuning().dense_tma;
   else if (key && !strcmp(key, "fuse_update")) slot = &tuning().fuse_update;
   else if (key && !strcmp(key, "dense_min_rowlen")) slot = &tuning().dense_min_rowlen;
+  else if (key && !strcmp(key, "l2_hot_mb")) slot = &tuning().l2_hot_mb;
   if (!slot) return -1;
   int old = *slot;
   *slot = value;

@@ -37,6 +37,7 @@ struct Tuning {
   int dense_tma;   // 1: dense super-windows on the TMA gather4 kernel (dense_tma.cu), 0: cp.async kernels (dense.cu)
   int fuse_update; // 1: Aggregation + Update as one kernel when the dense plan covers the graph
   int dense_min_rowlen; // dense plan: minimum mean stored entries per row of a 128-row super-window
+  int l2_hot_mb;   // balanced kernel with tagged column ids: megabytes of X rows kept L2-resident (evict_last); 0 = off
 };
 Tuning &tuning();
 

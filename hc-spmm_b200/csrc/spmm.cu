@@ -71,6 +71,8 @@ struct BalParams {
   int low_degree;    // mean row length < 64: launch the three-CTAs-per-SM build
   int warp_split;    // > 0: items with a mean row length >= warp_split give every warp an equal run of entries;
                      // other items (and 0) use the warp-per-row / CTA-per-long-row phases
+  int hint_cls_min;  // >= 0: s.colidx is TAGGED (hcspmm_tag_columns); rows of class >= this are loaded evict_last,
+                     // the others evict_first.  -1: plain column ids, every row evict_last
 };
 constexpr int MAX_WPC = 8;
 
@@ -84,6 +86,10 @@ template <> struct Vec<4, false> {
   float4 a;
   __device__ __forceinline__ void zero() { a = make_float4(0.f, 0.f, 0.f, 0.f); }
   __device__ __forceinline__ void load(const float *p) { a = ldg_f4(p); }
+  __device__ __forceinline__ void load_hint(const float *p, uint64_t pol) {
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(p), "l"(pol));
+  }
   __device__ __forceinline__ void add(const Vec &o) { add4(a, o.a); }
   __device__ __forceinline__ void xor_reduce(int off) {
     a.x += __shfl_xor_sync(0xffffffffu, a.x, off);
@@ -101,6 +107,12 @@ template <> struct Vec<8, false> {
     asm volatile("ld.global.nc.L2::evict_last.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
                  : "l"(p));
+  }
+  // the same 256-bit load with a per-load L2 eviction policy (createpolicy): hot rows evict_last, cold rows evict_first
+  __device__ __forceinline__ void load_hint(const float *p, uint64_t pol) {
+    asm volatile("ld.global.nc.L2::cache_hint.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p), "l"(pol));
   }
   __device__ __forceinline__ void add(const Vec &o) { add4(a, o.a); add4(b, o.b); }
   __device__ __forceinline__ void xor_reduce(int off) {
@@ -129,14 +141,20 @@ template <> struct Vec<8, false> {
 template <> struct Vec<8, true> {
   float4 a, b;
   __device__ __forceinline__ void zero() { a = b = make_float4(0.f, 0.f, 0.f, 0.f); }
-  __device__ __forceinline__ void load(const float *p) {
-    const float4 raw = ldg_f4(p);
+  __device__ __forceinline__ void widen(const float4 raw) {
     const uint32_t w0 = __float_as_uint(raw.x), w1 = __float_as_uint(raw.y), w2 = __float_as_uint(raw.z),
                    w3 = __float_as_uint(raw.w);
     a = make_float4(__uint_as_float(w0 << 16), __uint_as_float(w0 & 0xffff0000u), __uint_as_float(w1 << 16),
                     __uint_as_float(w1 & 0xffff0000u));
     b = make_float4(__uint_as_float(w2 << 16), __uint_as_float(w2 & 0xffff0000u), __uint_as_float(w3 << 16),
                     __uint_as_float(w3 & 0xffff0000u));
+  }
+  __device__ __forceinline__ void load(const float *p) { widen(ldg_f4(p)); }
+  __device__ __forceinline__ void load_hint(const float *p, uint64_t pol) {
+    float4 raw;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(raw.x), "=f"(raw.y), "=f"(raw.z), "=f"(raw.w) : "l"(p), "l"(pol));
+    widen(raw);
   }
   __device__ __forceinline__ void add(const Vec &o) { add4(a, o.a); add4(b, o.b); }
   __device__ __forceinline__ void xor_reduce(int off) {
@@ -159,6 +177,27 @@ template <> struct Vec<8, true> {
   }
 };
 
+// Per-load L2 residency control of the balanced kernel.  The gather of a graph whose X does not fit L2 is served by
+// whatever L2 happens to keep; with every row loaded evict_last (round 1) nothing discriminates, and the products
+// shape hits 51 % although 5 % of its rows take 75 % of the references.  Here column ids arrive TAGGED with the
+// hotness class of their column (3 bits above bit 28, hcspmm_tag_columns: class by rank in descending reference
+// count) and each row is loaded with the policy of its class: rows among the hottest `budget / row bytes` are
+// evict_last, all others evict_first -- same sums, same order, only the cache hints differ.
+struct GatherHint {
+  unsigned mask;      // column id = tagged & mask
+  unsigned cls_min;   // hot iff (tagged >> 29) >= cls_min
+  uint64_t pol_hot, pol_cold;
+};
+__device__ __forceinline__ GatherHint no_hint() { return GatherHint{0xffffffffu, 0u, 0ull, 0ull}; }
+__device__ __forceinline__ GatherHint make_hint(int cls_min) {
+  GatherHint h;
+  h.mask = 0x1fffffffu;
+  h.cls_min = (unsigned)cls_min;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(h.pol_hot));
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(h.pol_cold));
+  return h;
+}
+
 #ifndef HCSPMM_INFLIGHT_BYTES
 #define HCSPMM_INFLIGHT_BYTES 128  // gathered bytes kept in flight per lane (ring depth x vector bytes)
 #endif
@@ -168,12 +207,13 @@ template <> struct Vec<8, true> {
 // chunk0, chunk0 + chunk_stride, ...   A group of LPE lanes reads one X row, lane g of the group
 // owning vectors g, g + LPE, ... (NV of them, VW floats each).
 // ---------------------------------------------------------------------------------------
-template <int LPE, int NV, int VW, bool B16>
+template <int LPE, int NV, int VW, bool B16, bool HINT = false>
 __device__ __forceinline__ void gather_accumulate(Vec<VW, B16> (&acc)[NV], const float *__restrict__ xlane,
                                                   long long ldx, int x_rows,
                                                   const int *__restrict__ colidx, int eb, int ee,
                                                   int chunk0, int chunk_stride, int lane, int q,
-                                                  const bool (&active)[NV], bool all_active) {
+                                                  const bool (&active)[NV], bool all_active,
+                                                  const GatherHint h = no_hint()) {
   constexpr int G = 32 / LPE;         // edges handled concurrently by one warp
   constexpr int STEPS = 32 / G;       // gather steps per full 32-edge chunk
   constexpr int XDIV = B16 ? 2 : 1;      // X offsets in float units: a BF16 row is half as long
@@ -190,7 +230,7 @@ __device__ __forceinline__ void gather_accumulate(Vec<VW, B16> (&acc)[NV], const
     const int nb = base + chunk_stride * 32;
     c_next = (nb + lane < ee) ? __ldg(colidx + nb + lane) : -1;  // next chunk's ids, early
     (void)all_active;
-    const bool fast = n == 32 && __all_sync(0xffffffffu, (unsigned)c < (unsigned)x_rows);
+    const bool fast = n == 32 && __all_sync(0xffffffffu, ((unsigned)c & (HINT ? h.mask : 0xffffffffu)) < (unsigned)x_rows);
     if (fast) {
       // full chunk, every id valid: unpredicated ring of U loads in flight -- slot s % U is consumed
       // and immediately refilled with step s + U.  Lanes beyond the slab width (voff < 0) re-read
@@ -198,20 +238,34 @@ __device__ __forceinline__ void gather_accumulate(Vec<VW, B16> (&acc)[NV], const
       Vec<VW, B16> v[U][NV];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int cu = __shfl_sync(0xffffffffu, c, u * G + q);
-        const float *src = xlane + (long long)cu * ldx;
+        const unsigned ct = (unsigned)__shfl_sync(0xffffffffu, c, u * G + q);
+        if constexpr (HINT) {
+          const float *src = xlane + (long long)(ct & h.mask) * ldx;
+          const uint64_t pol = (ct >> 29) >= h.cls_min ? h.pol_hot : h.pol_cold;
 #pragma unroll
-        for (int i = 0; i < NV; ++i) v[u][i].load(src + voff[i]);
+          for (int i = 0; i < NV; ++i) v[u][i].load_hint(src + voff[i], pol);
+        } else {
+          const float *src = xlane + (long long)(int)ct * ldx;
+#pragma unroll
+          for (int i = 0; i < NV; ++i) v[u][i].load(src + voff[i]);
+        }
       }
 #pragma unroll
       for (int s = 0; s < STEPS; ++s) {
 #pragma unroll
         for (int i = 0; i < NV; ++i) acc[i].add(v[s % U][i]);
         if (s + U < STEPS) {
-          const int cu = __shfl_sync(0xffffffffu, c, (s + U) * G + q);
-          const float *src = xlane + (long long)cu * ldx;
+          const unsigned ct = (unsigned)__shfl_sync(0xffffffffu, c, (s + U) * G + q);
+          if constexpr (HINT) {
+            const float *src = xlane + (long long)(ct & h.mask) * ldx;
+            const uint64_t pol = (ct >> 29) >= h.cls_min ? h.pol_hot : h.pol_cold;
 #pragma unroll
-          for (int i = 0; i < NV; ++i) v[s % U][i].load(src + voff[i]);
+            for (int i = 0; i < NV; ++i) v[s % U][i].load_hint(src + voff[i], pol);
+          } else {
+            const float *src = xlane + (long long)(int)ct * ldx;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) v[s % U][i].load(src + voff[i]);
+          }
         }
       }
     } else {
@@ -221,13 +275,16 @@ __device__ __forceinline__ void gather_accumulate(Vec<VW, B16> (&acc)[NV], const
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int j = (t + u) * G + q;
-          const int cu = __shfl_sync(0xffffffffu, c, j & 31);
-          const bool ok = (j < n) && ((unsigned)cu < (unsigned)x_rows);
+          const unsigned ct = (unsigned)__shfl_sync(0xffffffffu, c, j & 31);
+          const unsigned cu = HINT ? (ct & h.mask) : ct;
+          const bool ok = (j < n) && (cu < (unsigned)x_rows);
           const float *src = xlane + (long long)cu * ldx;
 #pragma unroll
           for (int i = 0; i < NV; ++i) {
-            if (ok && active[i]) v[u][i].load(src + i * LPE * VW / XDIV);
-            else v[u][i].zero();
+            if (ok && active[i]) {
+              if constexpr (HINT) v[u][i].load_hint(src + i * LPE * VW / XDIV, (ct >> 29) >= h.cls_min ? h.pol_hot : h.pol_cold);
+              else v[u][i].load(src + i * LPE * VW / XDIV);
+            } else v[u][i].zero();
           }
         }
 #pragma unroll
@@ -244,11 +301,12 @@ __device__ __forceinline__ void gather_accumulate(Vec<VW, B16> (&acc)[NV], const
 // once and nothing is reduced across lanes.  The group fetches LPE column ids with one load and
 // broadcasts them inside the group (sub-warp shuffle masks: groups may run different trip counts).
 // ---------------------------------------------------------------------------------------
-template <int LPE, int NV, int VW, bool B16>
+template <int LPE, int NV, int VW, bool B16, bool HINT = false>
 __device__ __forceinline__ void gather_group_row(Vec<VW, B16> (&acc)[NV], const float *__restrict__ xlane,
                                                  long long ldx, int x_rows,
                                                  const int *__restrict__ colidx, int eb, int ee, int lane,
-                                                 int q, int g, const bool (&active)[NV]) {
+                                                 int q, int g, const bool (&active)[NV],
+                                                 const GatherHint h = no_hint()) {
   constexpr int XDIV = B16 ? 2 : 1;
   constexpr int UB0 = HCSPMM_INFLIGHT_BYTES * XDIV / (NV * VW * 4);
   constexpr int UB = UB0 < 1 ? 1 : (UB0 > LPE ? LPE : UB0);
@@ -262,13 +320,16 @@ __device__ __forceinline__ void gather_group_row(Vec<VW, B16> (&acc)[NV], const 
       Vec<VW, B16> v[UB][NV];
 #pragma unroll
       for (int u = 0; u < UB; ++u) {
-        const int cu = __shfl_sync(gmask, my, q * LPE + ((j0 + u) & (LPE - 1)));
-        const bool ok = (j0 + u < cnt) && ((unsigned)cu < (unsigned)x_rows);
+        const unsigned ct = (unsigned)__shfl_sync(gmask, my, q * LPE + ((j0 + u) & (LPE - 1)));
+        const unsigned cu = HINT ? (ct & h.mask) : ct;
+        const bool ok = (j0 + u < cnt) && (cu < (unsigned)x_rows);
         const float *src = xlane + (long long)cu * ldx;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
-          if (ok && active[i]) v[u][i].load(src + i * LPE * VW / XDIV);
-          else v[u][i].zero();
+          if (ok && active[i]) {
+            if constexpr (HINT) v[u][i].load_hint(src + i * LPE * VW / XDIV, (ct >> 29) >= h.cls_min ? h.pol_hot : h.pol_cold);
+            else v[u][i].load(src + i * LPE * VW / XDIV);
+          } else v[u][i].zero();
         }
       }
 #pragma unroll
@@ -617,7 +678,7 @@ __global__ void merge_path_splits_kernel(const int *__restrict__ rowptr, int n_r
   splits[i] = merge_path_rows(rowptr, n_rows, nnz, diag);
 }
 
-template <int LPE, int NV, int VW, int MINB, bool B16 = false>
+template <int LPE, int NV, int VW, int MINB, bool B16 = false, bool HINT = false>
 __global__ void __launch_bounds__(CTA_THREADS, MINB) spmm_balanced_kernel(const BalParams bp) {
   const SpmmParams &p = bp.s;
   extern __shared__ __align__(16) float smem[];   // [2 * CTA_WARPS * slab] row pieces | uint16 row offsets [chunk + 2]
@@ -687,6 +748,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) spmm_balanced_kernel(const 
   for (int i = 0; i < NV; ++i) active[i] = (g + i * LPE) < nvec;
   const bool all_active = nvec == LPE * NV;
   const float *xlane = p.x + (feat0 + g * VW) / (B16 ? 2 : 1);
+  const GatherHint hint = HINT ? make_hint(bp.hint_cls_min) : no_hint();
   const int e_cta = y1 - y0;
   const int short_row = (G > 1 && p.short_row > 0 && e_cta < rows_here * p.short_row &&
                          2 * rows_here >= CTA_WARPS * G)
@@ -730,8 +792,8 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) spmm_balanced_kernel(const 
         Vec<VW, B16> acc[NV];
 #pragma unroll
         for (int i = 0; i < NV; ++i) acc[i].zero();
-        gather_accumulate<LPE, NV, VW, B16>(acc, xlane, p.ldx, p.x_rows, p.colidx, eb, ee, 0, 1, lane, q, active,
-                                            all_active);
+        gather_accumulate<LPE, NV, VW, B16, HINT>(acc, xlane, p.ldx, p.x_rows, p.colidx, eb, ee, 0, 1, lane, q, active,
+                                            all_active, hint);
         group_reduce<LPE, NV, VW, B16>(acc);
         int accf = 0;
         float *dst;
@@ -789,7 +851,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) spmm_balanced_kernel(const 
       Vec<VW, B16> acc[NV];
 #pragma unroll
       for (int i = 0; i < NV; ++i) acc[i].zero();
-      gather_group_row<LPE, NV, VW, B16>(acc, xlane, p.ldx, p.x_rows, p.colidx, eb, ee, lane, q, g, active);
+      gather_group_row<LPE, NV, VW, B16, HINT>(acc, xlane, p.ldx, p.x_rows, p.colidx, eb, ee, lane, q, g, active, hint);
       int accf;
       float *yrow = out_row(r, accf) + g * VW;
 #pragma unroll
@@ -834,8 +896,8 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) spmm_balanced_kernel(const 
     Vec<VW, B16> acc[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) acc[i].zero();
-    gather_accumulate<LPE, NV, VW, B16>(acc, xlane, p.ldx, p.x_rows, p.colidx, eb, ee, 0, 1, lane, q, active,
-                                        all_active);
+    gather_accumulate<LPE, NV, VW, B16, HINT>(acc, xlane, p.ldx, p.x_rows, p.colidx, eb, ee, 0, 1, lane, q, active,
+                                        all_active, hint);
     group_reduce<LPE, NV, VW, B16>(acc);
     if (q == 0) {
       int accf;
@@ -862,8 +924,8 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) spmm_balanced_kernel(const 
     Vec<VW, B16> acc[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) acc[i].zero();
-    gather_accumulate<LPE, NV, VW, B16>(acc, xlane, p.ldx, p.x_rows, p.colidx, eb, ee, wid, CTA_WARPS, lane, q,
-                                        active, all_active);
+    gather_accumulate<LPE, NV, VW, B16, HINT>(acc, xlane, p.ldx, p.x_rows, p.colidx, eb, ee, wid, CTA_WARPS, lane, q,
+                                        active, all_active, hint);
     group_reduce<LPE, NV, VW, B16>(acc);
     if (q == 0) {
 #pragma unroll
@@ -1014,9 +1076,9 @@ static cudaError_t launch_hybrid(const SpmmParams &p, dim3 grid, size_t smem, cu
   return launch_hybrid_b<LPE, NV, VW, HCSPMM_MIN_CTAS>(p, grid, smem, stream);
 }
 
-template <int LPE, int NV, int VW, bool B16, int MINB>
+template <int LPE, int NV, int VW, bool B16, int MINB, bool HINT = false>
 static cudaError_t launch_balanced_b(const BalParams &bp, dim3 grid, size_t smem, cudaStream_t stream) {
-  auto kern = spmm_balanced_kernel<LPE, NV, VW, MINB, B16>;
+  auto kern = spmm_balanced_kernel<LPE, NV, VW, MINB, B16, HINT>;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
   BalParams q = bp;
@@ -1028,6 +1090,14 @@ template <int LPE, int NV, int VW, bool B16>
 static cudaError_t launch_balanced_t(const BalParams &bp, dim3 grid, size_t smem, cudaStream_t stream) {
   // low-degree graphs (rows of a few dozen entries) are latency-bound: three CTAs per SM hide more of it than
   // the deeper gather ring of the two-CTA build does (FP32, one vector per lane: dim <= 256 / 128)
+  if constexpr (!B16 && VW == 8) {
+    // tagged column ids + L2 residency hints (run_balanced decides; only these variants read tagged ids)
+    if (bp.hint_cls_min >= 0) {
+      if constexpr (NV == 1)
+        if (bp.low_degree && tuning().occupancy3) return launch_balanced_b<LPE, NV, VW, B16, 3, true>(bp, grid, smem, stream);
+      return launch_balanced_b<LPE, NV, VW, B16, HCSPMM_MIN_CTAS, true>(bp, grid, smem, stream);
+    }
+  }
   if constexpr (!B16 && NV == 1) {
     if (bp.low_degree && tuning().occupancy3 >= 2) return launch_balanced_b<LPE, NV, VW, B16, 4>(bp, grid, smem, stream);
     if (bp.low_degree && tuning().occupancy3) return launch_balanced_b<LPE, NV, VW, B16, 3>(bp, grid, smem, stream);
@@ -1049,6 +1119,7 @@ struct BalAux {
   int splits_chunk = 0, n_splits = 0;
   void *ws = nullptr;
   size_t ws_bytes = 0;
+  const int *colidx_tagged = nullptr;   // hcspmm_tag_columns: column ids with their hotness class in bits 29..31
 };
 
 static int default_chunk(int slab, bool b16) {
@@ -1103,6 +1174,18 @@ static cudaError_t run_balanced(const SpmmParams &p, long long nnz, bool v8, boo
   }
   bp.warp_split = tuning().warp_split;   // mean row length from which an item is cut by warp runs
   bp.low_degree = nnz < 64LL * p.n_rows;
+  // L2 residency hints: only when X does not fit the budget anyway (otherwise every row is evict_last, as before)
+  bp.hint_cls_min = -1;
+  if (aux.colidx_tagged != nullptr && tuning().l2_hot_mb > 0 && v8 && !b16) {
+    const long long row_bytes = (long long)p.dim * (b16 ? 2 : 4);
+    const long long budget_rows = ((long long)tuning().l2_hot_mb << 20) / (row_bytes > 0 ? row_bytes : 1);
+    if (budget_rows < (long long)p.x_rows) {
+      int c = 1;
+      while (c <= 7 && ((16384LL << (7 - c)) > budget_rows)) ++c;
+      bp.hint_cls_min = c;               // 8: nothing fits -> every row evict_first
+      bp.s.colidx = aux.colidx_tagged;
+    }
+  }
   const int slab = p.slab;
   dim3 grid((unsigned)n_items, (p.dim + slab - 1) / slab, 1);
   const size_t smem = (size_t)2 * CTA_WARPS * slab * sizeof(float) + (size_t)(chunk + 4) / 2 * sizeof(int);
@@ -1171,6 +1254,7 @@ int launch_spmm(const float *x, int64_t ldx, int32_t x_rows, const int32_t *rowp
   if (aux_in) {
     aux.splits = aux_in->d_splits; aux.splits_chunk = aux_in->splits_chunk; aux.n_splits = aux_in->n_splits;
     aux.ws = aux_in->d_workspace; aux.ws_bytes = aux_in->workspace_bytes;
+    aux.colidx_tagged = aux_in->d_colidx_tagged;
     n_tc_windows = aux_in->n_tc_windows;
   }
   if (n_rows < 0 || dim < 0 || nnz < 0 || x_rows < 0) {

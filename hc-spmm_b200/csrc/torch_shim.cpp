@@ -21,6 +21,8 @@
 
 #include <string.h>
 
+#include <algorithm>
+
 #include <vector>
 
 #include "../../include/hcspmm.h"
@@ -36,11 +38,12 @@ namespace {
 // graphs preprocessed afterwards, so two graphs (or two threads) never see each other's settings.
 constexpr int32_t kPlanMagic = 0x48435044;
 enum { H_MAGIC = 0, H_NDENSE, H_TOTALCOLS, H_NROWS, H_VERSION, H_PRECISION, H_DENSE, H_NTC, H_SPLITS_CHUNK, H_NSPLITS,
-       H_SPLITS_OFF, H_CLASSIFIER, H_PLAN_FULL, kHdrWords = 16 };
+       H_SPLITS_OFF, H_CLASSIFIER, H_PLAN_FULL, H_TAG_OFF, H_NCOLS, kHdrWords = 16 };
 bool g_dense = false;                        // defaults for the next preprocess()
 int g_classifier = HCSPMM_CLASSIFIER_SHIPPED;
 int g_precision = HCSPMM_PRECISION_TF32;
 bool g_bug_compat = false;
+bool g_tag_columns = true;                   // preprocess() also emits hotness-tagged column ids (L2 residency hints)
 
 void check_rc(int rc, const char *what) {
   TORCH_CHECK(rc == 0, "HCSPMM.", what, " failed (code ", rc, "): ", hcspmm_last_error());
@@ -152,13 +155,30 @@ std::vector<torch::Tensor> preprocess(torch::Tensor edgeList, torch::Tensor node
   }
   // merge-path split points of the work-balanced kernel (static per graph)
   const int64_t plan_words = plan.defined() ? plan.numel() : 0;
-  const int64_t n_split_words = (int64_t)hcspmm_merge_path_count((int32_t)num_nodes, edge_num, HCSPMM_SPLITS_CHUNK);
-  auto col_nzr = torch::empty({plan_words + n_split_words}, opts);
+  const int64_t n_split_words = ((int64_t)hcspmm_merge_path_count((int32_t)num_nodes, edge_num, HCSPMM_SPLITS_CHUNK) + 3) / 4 * 4;
+  // hotness-tagged column ids for the balanced kernel's L2 residency hints: worth their nnz words only when a
+  // gathered matrix of this many rows can exceed L2 at all (>= 128-byte rows against a 64 MB budget)
+  int64_t n_cols = 0, tag_words = 0;
+  if (g_tag_columns && edge_num >= 8 * num_nodes && edge_num > 0) {
+    n_cols = std::max<int64_t>(num_nodes, edgeList.max().item<int64_t>() + 1);
+    if (n_cols * 128 > (64LL << 20) && n_cols < (1LL << 29)) tag_words = edge_num;
+  }
+  auto col_nzr = torch::empty({plan_words + n_split_words + tag_words}, opts);
+  if (tag_words > 0) {
+    const size_t tws = hcspmm_tag_columns_workspace_bytes((int32_t)n_cols, edge_num);
+    auto tw = torch::empty({(int64_t)tws}, opts.dtype(torch::kUInt8));
+    check_rc(hcspmm_tag_columns(edgeList.data_ptr<int32_t>(), edge_num, (int32_t)n_cols,
+                                col_nzr.data_ptr<int32_t>() + plan_words + n_split_words, tw.data_ptr(), tws, stream),
+             "tag_columns");
+    h[H_TAG_OFF] = (int32_t)(plan_words + n_split_words); h[H_NCOLS] = (int32_t)n_cols;
+  }
   if (plan_words > 0) col_nzr.narrow(0, 0, plan_words).copy_(plan);
   check_rc(hcspmm_merge_path_splits(nodePointer.data_ptr<int32_t>(), (int32_t)num_nodes, edge_num, HCSPMM_SPLITS_CHUNK,
                                     col_nzr.data_ptr<int32_t>() + plan_words, stream),
            "merge_path_splits");
-  h[H_SPLITS_CHUNK] = HCSPMM_SPLITS_CHUNK; h[H_NSPLITS] = (int32_t)(n_split_words - 1); h[H_SPLITS_OFF] = (int32_t)plan_words;
+  h[H_SPLITS_CHUNK] = HCSPMM_SPLITS_CHUNK;
+  h[H_NSPLITS] = (int32_t)hcspmm_merge_path_count((int32_t)num_nodes, edge_num, HCSPMM_SPLITS_CHUNK) - 1;
+  h[H_SPLITS_OFF] = (int32_t)plan_words;
   return {bp, etc, etr, ht, row_nzr, col_nzr};
 }
 
@@ -189,6 +209,7 @@ AuxView make_aux(const torch::Tensor &input, const Graph &g, const torch::Tensor
   if (h[H_NSPLITS] > 0 && col_nzr.numel() >= (int64_t)h[H_SPLITS_OFF] + h[H_NSPLITS] + 1) {
     v.aux.d_splits = blob + h[H_SPLITS_OFF]; v.aux.splits_chunk = h[H_SPLITS_CHUNK]; v.aux.n_splits = h[H_NSPLITS];
   }
+  if (h[H_TAG_OFF] > 0 && col_nzr.numel() >= (int64_t)h[H_TAG_OFF] + g.nnz) v.aux.d_colidx_tagged = blob + h[H_TAG_OFF];
   if (h[H_DENSE] && h[H_NDENSE] > 0) {
     v.aux.d_plan = blob; v.aux.n_dense = h[H_NDENSE]; v.aux.total_cols = h[H_TOTALCOLS]; v.aux.plan_full = h[H_PLAN_FULL];
   }
@@ -375,6 +396,12 @@ bool set_dense(bool on) {
   return old;
 }
 
+bool set_tag_columns(bool on) {
+  bool old = g_tag_columns;
+  g_tag_columns = on;
+  return old;
+}
+
 bool set_bug_compat(bool on) {
   bool old = g_bug_compat;
   g_bug_compat = on;
@@ -429,6 +456,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("set_classifier", &set_classifier, "shipped | intended | b200 | all_cuda | all_tc; returns the previous mode");
   m.def("set_precision", &set_precision, "tf32 | tf32x2 | fp32 | bf16; returns the previous mode");
   m.def("set_dense", &set_dense, "tcgen05 kernels: dense super-window plans in preprocess()/forward*(), Update GEMM");
+  m.def("set_tag_columns", &set_tag_columns, "preprocess() emits hotness-tagged column ids for the L2 residency hints (default on)");
   m.def("set_bug_compat", &set_bug_compat, "read strided `weights` as raw memory like the reference");
   m.def("set_tuning", &set_tuning, "kernel tuning knob (long_row, slab); returns the previous value");
 }

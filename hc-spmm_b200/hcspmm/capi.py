@@ -27,6 +27,7 @@ EXPORTS = [
     "hcspmm_halo_pull", "hcspmm_debug_l2_gather",
     "hcspmm_merge_path_count", "hcspmm_merge_path_splits", "hcspmm_spmm_workspace_bytes", "hcspmm_spmm_aux",
     "hcspmm_f32_to_bf16", "hcspmm_spmm_gemm_aux", "hcspmm_halo_push",
+    "hcspmm_tag_columns_workspace_bytes", "hcspmm_tag_columns",
 ]
 
 _lib = None
@@ -42,7 +43,8 @@ class Aux(ctypes.Structure):
     """hcspmm_aux_t (include/hcspmm.h): per-graph products handed to every aggregation."""
     _fields_ = [("d_splits", ctypes.c_void_p), ("splits_chunk", ctypes.c_int32), ("n_splits", ctypes.c_int32),
                 ("n_tc_windows", ctypes.c_int32), ("d_plan", ctypes.c_void_p), ("n_dense", ctypes.c_int32),
-                ("plan_full", ctypes.c_int32), ("total_cols", ctypes.c_int64), ("d_workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t)]
+                ("plan_full", ctypes.c_int32), ("total_cols", ctypes.c_int64), ("d_workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
+                ("d_colidx_tagged", ctypes.c_void_p)]
 
 
 def lib() -> ctypes.CDLL:
@@ -94,6 +96,9 @@ def lib() -> ctypes.CDLL:
         L.hcspmm_spmm_aux.argtypes = [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _int, _int,
                                       _vp, _i64, ctypes.POINTER(Aux), _vp]
         L.hcspmm_f32_to_bf16.argtypes = [_vp, _i64, _i32, _i32, _vp, _i64, _vp]
+        L.hcspmm_tag_columns_workspace_bytes.restype = _sz
+        L.hcspmm_tag_columns_workspace_bytes.argtypes = [_i32, _i64]
+        L.hcspmm_tag_columns.argtypes = [_vp, _i64, _i32, _vp, _vp, _sz, _vp]
         L.hcspmm_halo_push.argtypes = [_vp, _i64, _vp, _vp, _vp, _i64, _i32, ctypes.c_uint64, _i32, _i32, _i32, _i32, _vp]
         L.hcspmm_spmm_gemm_aux.argtypes = [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _int, _vp, _i64,
                                            _i32, _vp, _i64, _vp, _i64, ctypes.POINTER(Aux), _vp]
@@ -162,13 +167,27 @@ def spmm(x: torch.Tensor, rowptr, colidx, bp=None, etc=None, etr=None, ht=None, 
 SPLITS_CHUNK = 4096      # HCSPMM_SPLITS_CHUNK
 
 
+def tag_column_ids(colidx: torch.Tensor, n_cols: int) -> torch.Tensor:
+    """hcspmm_tag_columns: the column ids with the hotness class of their column (rank by reference count) in bits 29..31."""
+    nnz = colidx.numel()
+    out = torch.empty(nnz, dtype=torch.int32, device=colidx.device)
+    with torch.cuda.device(colidx.device):
+        nbytes = lib().hcspmm_tag_columns_workspace_bytes(n_cols, nnz)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=colidx.device)
+        _check(lib().hcspmm_tag_columns(_ptr(colidx), nnz, n_cols, _ptr(out), _ptr(ws), nbytes, _stream(colidx)),
+               "hcspmm_tag_columns")
+    return out
+
+
 class GraphAux:
     """The per-graph products of hcspmm_aux_t for a device CSR: merge-path split points (computed once), the count of
     windows labelled 1 and a reusable workspace -- what HCSPMM.preprocess() packs into its two opaque tensors."""
 
-    def __init__(self, rowptr: torch.Tensor, colidx: torch.Tensor, ht: torch.Tensor | None = None, plan=None):
+    def __init__(self, rowptr: torch.Tensor, colidx: torch.Tensor, ht: torch.Tensor | None = None, plan=None,
+                 tag_columns: bool = False, n_cols: int | None = None):
         n, nnz = rowptr.numel() - 1, colidx.numel()
         self.n, self.nnz = n, nnz
+        self.tagged = tag_column_ids(colidx, n_cols if n_cols is not None else n) if (tag_columns and nnz > 0) else None
         with torch.cuda.device(rowptr.device):
             cnt = lib().hcspmm_merge_path_count(n, nnz, SPLITS_CHUNK)
             self.splits = torch.empty(cnt, dtype=torch.int32, device=rowptr.device)
@@ -194,6 +213,8 @@ class GraphAux:
             a.d_plan, a.n_dense, a.total_cols = self.plan.plan.data_ptr(), self.plan.n_dense, self.plan.total_cols
             a.plan_full = self.plan_full
         a.d_workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        if self.tagged is not None:
+            a.d_colidx_tagged = self.tagged.data_ptr()
         return a
 
 

@@ -91,6 +91,8 @@ const char *hcspmm_last_error(void);
  *   "dense_min_rowlen" a super-window joins the dense plan only if it holds >= this many stored entries per row on
  *                average (default 8: the boundary the B200 re-fit found, profiles/r2_selector_fit.json); the
  *                min_reuse_x2 argument of hcspmm_dense_plan_count applies as well (0 = force: no threshold at all)
+ *   "l2_hot_mb"  megabytes of gathered X rows the balanced kernel keeps L2-resident when the caller passes tagged
+ *                column ids (default 72 of the 126 MB L2; 0 = hints off)
  *   "dense_tma"  which kernel multiplies dense super-windows.  csrc/dense_tma.cu is the five-role kernel (TMA for
  *                the plan's index chunks and W^T, dedicated epilogue warps, optional FUSED Update); csrc/dense.cu holds
  *                the earlier producer/issuer kernels.  1 (default): dense.cu for plain aggregation (measured fastest,
@@ -207,6 +209,10 @@ int hcspmm_spmm_plan(const float *d_x, int64_t ldx, int32_t x_rows, const int32_
  *   d_plan / n_dense / total_cols        dense super-window plan (hcspmm_dense_plan_fill) or NULL; plan_full = 1 when
  *                                        the plan covers every row that has stored entries (then the fused entry
  *                                        point below runs Aggregation + Update as ONE kernel)
+ *   d_colidx_tagged                      the CSR's column ids with the hotness class of their column in bits 29..31
+ *                                        (hcspmm_tag_columns): when X does not fit the L2 budget (knob "l2_hot_mb"),
+ *                                        the balanced kernel loads the hottest rows evict_last and the others
+ *                                        evict_first instead of leaving residency to chance; NULL = every row evict_last
  *   d_workspace / workspace_bytes        >= hcspmm_spmm_workspace_bytes() bytes, 16-byte aligned, for the row
  *                                        pieces of the balanced kernel; NULL = the library's private pool
  * hcspmm_spmm_aux(..., NULL, ...) is hcspmm_spmm.                                                              */
@@ -221,7 +227,11 @@ typedef struct {
   int64_t total_cols;
   void *d_workspace;
   size_t workspace_bytes;
+  const int32_t *d_colidx_tagged;   /* hcspmm_tag_columns output, or NULL */
 } hcspmm_aux_t;
+size_t hcspmm_tag_columns_workspace_bytes(int32_t n_cols, int64_t nnz);
+int hcspmm_tag_columns(const int32_t *d_colidx, int64_t nnz, int32_t n_cols, int32_t *d_tagged, void *d_workspace,
+                       size_t workspace_bytes, void *stream);
 size_t hcspmm_merge_path_count(int32_t n_rows, int64_t nnz, int32_t chunk);      /* entries of d_splits: n_splits + 1 */
 int hcspmm_merge_path_splits(const int32_t *d_rowptr, int32_t n_rows, int64_t nnz, int32_t chunk, int32_t *d_splits,
                              void *stream);
