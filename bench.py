@@ -478,7 +478,8 @@ def run_workload(ctx, shape_name, dim, steps, warmup, classifier, dense, precisi
         del y_cpu
     ok = all(v <= tol for k_, v in parity.items() if k_ in ("rel_fro", "cpu_rel_fro"))
     parity["ok"] = bool(ok)
-    assert ok, f"parity check failed: {parity}"
+    if not ok:      # the line still goes out, with parity.ok = false: a wrong result must be visible, not a missing line
+        print(f"[bench] PARITY CHECK FAILED on {shape_name} dim {dim}: {parity}", file=sys.stderr, flush=True)
 
     # ---- launches of OUR kernels per step (library rules; per-graph products from preprocess) -------------------
     bal_knob = HCSPMM.set_tuning("balance", 1)

@@ -75,6 +75,7 @@ def main():
             g1 = hd.ShardedGraph(rp, ci, single=True)
             m1 = hd.DistGCN(g1, args.feat, args.hidden, args.classes, num_layers=args.layers, seed=0, order=order).to(dev)
             o1 = torch.optim.Adam(m1.parameters(), lr=0.01)
+            x_all = m1.pad_features(x_all)
             ref_losses = []
             for ep in range(args.warmup + args.epochs):
                 o1.zero_grad()
@@ -88,6 +89,7 @@ def main():
     torch.cuda.empty_cache()
 
     model = hd.DistGCN(g, args.feat, args.hidden, args.classes, num_layers=args.layers, seed=0, order=order).to(dev)
+    x = model.pad_features(x)           # feature layout at the padded width (100 -> 104): once, outside the epochs
     opt = torch.optim.Adam(model.parameters(), lr=0.01)
     times, losses, all_losses = [], [], []
     for ep in range(args.warmup + args.epochs):

@@ -17,7 +17,7 @@ void set_error(const char *fmt, ...) {
 }
 
 Tuning &tuning() {
-  static Tuning t = {1024, 0, 1, 1, 0, 1, 1, 2, 1, 1, 1, 0, 0, 64, 1, 0, 2048, 10000, 1, 1, 8, 72};
+  static Tuning t = {1024, 0, 1, 1, 0, 1, 1, 2, 1, 1, 1, 0, 0, 64, 1, 0, 2048, 10000, 1, 1, 8, 72, 2048};
   return t;
 }
 
@@ -148,6 +148,7 @@ int hcspmm_set_tuning(const char *key, int value) {
   else if (key && !strcmp(key, "fuse_update")) slot = &tuning().fuse_update;
   else if (key && !strcmp(key, "dense_min_rowlen")) slot = &tuning().dense_min_rowlen;
   else if (key && !strcmp(key, "l2_hot_mb")) slot = &tuning().l2_hot_mb;
+  else if (key && !strcmp(key, "l2_hot_min_row")) slot = &tuning().l2_hot_min_row;
   if (!slot) return -1;
   int old = *slot;
   *slot = value;
@@ -312,7 +313,15 @@ int hcspmm_spmm_aux(const float *d_x, int64_t ldx, int32_t x_rows, const int32_t
     }
   }
   if (xr) scratch_free(xr, (cudaStream_t)stream);
-  if (rc == 0) {
+  if (rc == 0 && aux->plan_full) {
+    // every row with stored entries was computed above: nothing is left for the per-window / balanced kernels
+    // (their launches cost 0.14 ms per aggregation on the proteins shape just to skip every window); rows of
+    // super-windows without entries are zero
+    if ((long long)n_dense * 128 < n_rows && !accumulate) {
+      cudaError_t e = cudaMemset2DAsync(d_y, sizeof(float) * ldy, 0, sizeof(float) * dim, n_rows, (cudaStream_t)stream);
+      if (e != cudaSuccess) { set_error("spmm_plan: memset: %s", cudaGetErrorString(e)); return (int)e; }
+    }
+  } else if (rc == 0) {
     hcspmm_aux_t rest = *aux;
     rest.n_tc_windows = -1;   // the plan's labels differ from the caller's count
     rc = launch_spmm(d_x, ldx, x_rows, d_rowptr, d_colidx, d_block_partition, d_edge_to_column, d_edge_to_row,

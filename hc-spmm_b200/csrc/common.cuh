@@ -38,6 +38,7 @@ struct Tuning {
   int fuse_update; // 1: Aggregation + Update as one kernel when the dense plan covers the graph
   int dense_min_rowlen; // dense plan: minimum mean stored entries per row of a 128-row super-window
   int l2_hot_mb;   // balanced kernel with tagged column ids: megabytes of X rows kept L2-resident (evict_last); 0 = off
+  int l2_hot_min_row; // ... applied only to gathers of at least this many bytes per row
 };
 Tuning &tuning();
 

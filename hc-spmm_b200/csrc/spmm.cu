@@ -1176,7 +1176,11 @@ static cudaError_t run_balanced(const SpmmParams &p, long long nnz, bool v8, boo
   bp.low_degree = nnz < 64LL * p.n_rows;
   // L2 residency hints: only when X does not fit the budget anyway (otherwise every row is evict_last, as before)
   bp.hint_cls_min = -1;
-  if (aux.colidx_tagged != nullptr && tuning().l2_hot_mb > 0 && v8 && !b16) {
+  // Measured (scripts/r2/hint_probe.py): the hints pay only for rows of >= 2 KB (Reddit shape dim 512: 15.5 -> 14.4 ms);
+  // at 512-byte / 1 KB rows they LOSE 5-15 % (products dim 128: 3.26 -> 3.74 ms, Reddit dim 256: 6.37 -> 6.73 ms) -- LRU
+  // already keeps the hub rows that matter -- so they apply from knob "l2_hot_min_row" bytes per row upwards.
+  if (aux.colidx_tagged != nullptr && tuning().l2_hot_mb > 0 && v8 && !b16 &&
+      (long long)p.dim * 4 >= tuning().l2_hot_min_row) {
     const long long row_bytes = (long long)p.dim * (b16 ? 2 : 4);
     const long long budget_rows = ((long long)tuning().l2_hot_mb << 20) / (row_bytes > 0 ? row_bytes : 1);
     if (budget_rows < (long long)p.x_rows) {

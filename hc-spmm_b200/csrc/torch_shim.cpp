@@ -43,7 +43,8 @@ bool g_dense = false;                        // defaults for the next preprocess
 int g_classifier = HCSPMM_CLASSIFIER_SHIPPED;
 int g_precision = HCSPMM_PRECISION_TF32;
 bool g_bug_compat = false;
-bool g_tag_columns = true;                   // preprocess() also emits hotness-tagged column ids (L2 residency hints)
+bool g_tag_columns = false;                  // preprocess() also emits hotness-tagged column ids (L2 residency hints:
+                                             // they pay from 2 KB rows = dim 512 upwards, so they are opt-in)
 
 void check_rc(int rc, const char *what) {
   TORCH_CHECK(rc == 0, "HCSPMM.", what, " failed (code ", rc, "): ", hcspmm_last_error());
@@ -456,7 +457,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("set_classifier", &set_classifier, "shipped | intended | b200 | all_cuda | all_tc; returns the previous mode");
   m.def("set_precision", &set_precision, "tf32 | tf32x2 | fp32 | bf16; returns the previous mode");
   m.def("set_dense", &set_dense, "tcgen05 kernels: dense super-window plans in preprocess()/forward*(), Update GEMM");
-  m.def("set_tag_columns", &set_tag_columns, "preprocess() emits hotness-tagged column ids for the L2 residency hints (default on)");
+  m.def("set_tag_columns", &set_tag_columns, "preprocess() also emits hotness-tagged column ids for the L2 residency hints of wide gathers (default off)");
   m.def("set_bug_compat", &set_bug_compat, "read strided `weights` as raw memory like the reference");
   m.def("set_tuning", &set_tuning, "kernel tuning knob (long_row, slab); returns the previous value");
 }

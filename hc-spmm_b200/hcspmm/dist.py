@@ -527,19 +527,38 @@ class DistGCN(torch.nn.Module):
     (ShardedGCNLayer / ShardedGINLayer) -- and weight gradients are summed with one all-reduce per step."""
 
     def __init__(self, graph: ShardedGraph, in_dim, hidden, classes, num_layers=2, seed=0, graph_t=None,
-                 order: str = "auto"):
-        """order: "update_first" = A (H W) (GCN), "aggregate_first" = (A H) W (GIN), "auto" = the cheaper per layer."""
+                 order: str = "auto", pad_to: int = 8):
+        """order: "update_first" = A (H W) (GCN), "aggregate_first" = (A H) W (GIN), "auto" = the cheaper per layer.
+        pad_to: feature / class widths are laid out as multiples of this (zero columns): 100 input features travel
+        and aggregate as 104, 47 classes as 48, so every aggregation takes the 256-bit gather path and every Update
+        GEMM the TMA path without per-call pad / unpad passes.  The padding weights start at zero, receive zero
+        gradients (the padded logits are sliced away before the loss) and so stay zero: the model is unchanged."""
         super().__init__()
         self.order = order
         g = torch.Generator().manual_seed(seed)            # identical replicas on every rank
         dims = [in_dim] + [hidden] * (num_layers - 1) + [classes]
-        self.weights = torch.nn.ParameterList(
-            [torch.nn.Parameter(torch.randn(dims[i], dims[i + 1], generator=g) / dims[i] ** 0.5)
-             for i in range(num_layers)])
+        pad = lambda d: (d + pad_to - 1) // pad_to * pad_to if pad_to > 1 else d
+        self.in_dim, self.classes = in_dim, classes
+        ws = []
+        for i in range(num_layers):
+            w = torch.randn(dims[i], dims[i + 1], generator=g) / dims[i] ** 0.5
+            wp = torch.zeros(pad(dims[i]), pad(dims[i + 1]))
+            wp[:dims[i], :dims[i + 1]] = w
+            ws.append(torch.nn.Parameter(wp))
+        self.weights = torch.nn.ParameterList(ws)
         self.graph, self.graph_t = graph, graph_t
 
+    def pad_features(self, x_local: torch.Tensor) -> torch.Tensor:
+        """Lay the input features out at the padded width once (a data-layout step, outside the epoch)."""
+        wp = self.weights[0].shape[0]
+        if x_local.shape[1] == wp:
+            return x_local
+        out = torch.zeros(x_local.shape[0], wp, device=x_local.device, dtype=x_local.dtype)
+        out[:, :x_local.shape[1]] = x_local
+        return out
+
     def forward(self, x_local):
-        h = x_local
+        h = self.pad_features(x_local)
         for i, w in enumerate(self.weights):
             # A (H W) = (A H) W: exchange and aggregate at the narrower of the two widths -- the exchange moves
             # rows * width * 4 bytes per rank and the SpMM gathers nnz * width * 4
@@ -548,11 +567,13 @@ class DistGCN(torch.nn.Module):
             h = layer.apply(h, w, self.graph, self.graph_t)
             if i + 1 < len(self.weights):
                 h = torch.relu(h)
-        return torch.nn.functional.log_softmax(h, dim=1)
+        return torch.nn.functional.log_softmax(h[:, :self.classes], dim=1)
 
     def loss(self, x_local, y_local):
-        """nll_loss averaged over ALL vertices (sum over local rows / N)."""
-        return torch.nn.functional.nll_loss(self.forward(x_local), y_local, reduction="sum") / self.graph.n
+        """nll_loss averaged over ALL vertices (sum over local rows / N) -- as a gather + sum: torch's nll_loss with
+        reduction="sum" reduces 2.4 M rows in one block (2.6 ms forward + 1.4 ms backward at the products shape)."""
+        logp = self.forward(x_local)
+        return -logp.gather(1, y_local.view(-1, 1)).sum() / self.graph.n
 
     def sync_grads(self):
         if self.graph.world > 1:

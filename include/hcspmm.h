@@ -93,6 +93,8 @@ const char *hcspmm_last_error(void);
  *                min_reuse_x2 argument of hcspmm_dense_plan_count applies as well (0 = force: no threshold at all)
  *   "l2_hot_mb"  megabytes of gathered X rows the balanced kernel keeps L2-resident when the caller passes tagged
  *                column ids (default 72 of the 126 MB L2; 0 = hints off)
+ *   "l2_hot_min_row" the hints apply to gathers of at least this many bytes per row (default 2048: measured to lose
+ *                below -- LRU already keeps the hub rows -- and to gain 7 % at the Reddit shape, dim 512)
  *   "dense_tma"  which kernel multiplies dense super-windows.  csrc/dense_tma.cu is the five-role kernel (TMA for
  *                the plan's index chunks and W^T, dedicated epilogue warps, optional FUSED Update); csrc/dense.cu holds
  *                the earlier producer/issuer kernels.  1 (default): dense.cu for plain aggregation (measured fastest,

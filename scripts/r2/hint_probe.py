@@ -7,6 +7,7 @@ import torch
 from hcspmm import capi, graphs
 
 dev = torch.device("cuda", 0)
+capi.set_tuning("l2_hot_min_row", 0)      # measure the hints at every width
 
 
 def t(fn, n=10):

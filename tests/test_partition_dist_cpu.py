@@ -106,16 +106,18 @@ def _worker(rank, world, port, name, out_dir, schedule="gather"):
         dist.all_reduce(lt)
         a = torch.sparse_csr_tensor(_t(rp.astype(np.int64)), _t(ci.astype(np.int64)), torch.ones(ci.size), size=(n, n))
         ws = [w.detach().clone().requires_grad_(True) for w in model.weights]
-        h = x
+        h = model.pad_features(x)                 # widths are laid out as multiples of 8 (zero columns / zero weights)
+        assert h.shape[1] == 16 and ws[0].shape == (16, 8) and ws[1].shape == (8, 8)
         for i, w in enumerate(ws):
             h = torch.sparse.mm(a, h @ w)
             if i + 1 < len(ws):
                 h = torch.relu(h)
-        ref = torch.nn.functional.nll_loss(torch.log_softmax(h, 1), labels)
+        ref = torch.nn.functional.nll_loss(torch.log_softmax(h[:, :model.classes], 1), labels)
         ref.backward()
         assert abs(float(lt) - float(ref.detach())) <= 1e-4 * max(1.0, abs(float(ref.detach())))
         for w, p in zip(ws, model.weights):
             assert rel_fro(p.grad.numpy(), w.grad.numpy()) <= 1e-4
+        assert not model.weights[0].grad[12:].any() and not model.weights[1].grad[:, 4:].any()   # padding stays untrained
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
