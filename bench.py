@@ -62,6 +62,12 @@ def parse():
     ap.add_argument("--exchange-passes", type=int, default=1, choices=[1, 2],
                     help="peer exchange: 2 = shard cut by source into two accumulating SpMM passes, second half of the pull overlapped")
     ap.add_argument("--overlap-ctas", type=int, default=64)
+    ap.add_argument("--stage-copy", action="store_true",
+                    help="N > 1: keep the rank's X shard in ordinary memory and copy it into the exchange operand every step "
+                         "(default: X lives in the operand's own-rows segment)")
+    ap.add_argument("--direct-refs", type=int, default=None,
+                    help="peer exchange: remote rows of X referenced at most this many times by a shard are read in place by "
+                         "the SpMM instead of being pulled (0 = off; default: auto, 2 on low-reuse halos)")
     ap.add_argument("--exchange-slabs", type=int, default=1,
                     help="N > 1: all-gather X in this many feature slabs, slab k+1 in flight while the SpMM of slab k runs "
                          "(1 = one all-gather, then one SpMM)")
@@ -354,7 +360,7 @@ def run_workload(ctx, shape_name, dim, steps, warmup, classifier, dense, precisi
     HCSPMM.set_precision(precision)
     operand = "bf16" if (precision == "bf16" and world > 1) else "fp32"
     sg = hd.ShardedGraph(rp, ci, schedule=args.exchange, n_slabs=max(1, args.exchange_slabs), n_passes=args.exchange_passes,
-                         operand=operand)
+                         operand=operand, direct_refs=args.direct_refs)
     sg.overlap_ctas = args.overlap_ctas
     r0, r1 = sg.r0, sg.r1
     rp_l, ci_run = sg.rowptr, sg.colidx
@@ -377,6 +383,14 @@ def run_workload(ctx, shape_name, dim, steps, warmup, classifier, dense, precisi
     g.manual_seed(1234)
     x_full = torch.randn(n, dim, device=dev, generator=g)       # same on every rank (same seed)
     x_loc = x_full[r0:r1].contiguous()
+    x_in_operand = False
+    if world > 1 and not args.stage_copy:
+        # the rank's shard of X lives where the exchange reads it: in its rows of the peer-visible operand buffer (what a
+        # GCN layer's Update GEMM writes there directly, hcspmm.dist.ShardedGCNLayer) -- no per-step staging copy
+        xo = sg.own_rows(dim)
+        if xo is not None:
+            xo.copy_(x_loc)
+            x_loc, x_in_operand = xo, True
     n_slabs = sg.n_slabs if (world > 1 and sg.schedule in ("slabs", "halo", "peer")) else 1
 
     def step():
@@ -436,11 +450,20 @@ def run_workload(ctx, shape_name, dim, steps, warmup, classifier, dense, precisi
         operand_t = sg.exchange(x_loc)
         esz = 2 if operand_t.dtype == torch.bfloat16 else 4
         phases = {"exchange_only_ms": tm(lambda: sg.exchange(x_loc)),
-                  "kernel_only_ms": tm(lambda: sg._spmm(operand_t, rp_l, ci_run, pre)),
+                  "kernel_only_ms": tm(lambda: sg.local_spmm(operand_t)),
                   "exchange_bytes_per_rank": int(sg.exchange_rows() * dim * esz),
                   "exchange_rows_vs_allgather": sg.exchange_rows() / max(1, (world - 1) * sg.max_rows)}
         if phases["exchange_only_ms"] > 0:
             phases["exchange_gbs_per_rank"] = phases["exchange_bytes_per_rank"] / phases["exchange_only_ms"] / 1e6
+        if sg.direct is not None:
+            # segment mode: rows referenced <= T times are read in place by the SpMM (inside kernel_only_ms); only the
+            # pulled rows travel in exchange_only_ms
+            d_ = sg.direct
+            phases["in_place"] = {"max_refs": d_["T"], "rows_in_place": d_["rows"], "references_in_place": d_["refs"],
+                                  "rows_pulled": d_["pulled_rows"], "halo_rows": d_["halo_rows"]}
+            pulled_bytes = d_["pulled_rows"] * dim * esz
+            if phases["exchange_only_ms"] > 0:
+                phases["exchange_gbs_per_rank"] = pulled_bytes / phases["exchange_only_ms"] / 1e6
     sg.check()          # a peer barrier that timed out would have left stale rows in the operand
 
     # ---- parity, outside the timed region, on the result of a real step ------------------------------------------
@@ -626,6 +649,9 @@ def run_workload(ctx, shape_name, dim, steps, warmup, classifier, dense, precisi
                        "windows": (n_l + 15) // 16, "partition": f"row windows, nnz-balanced, {world} shard(s)",
                        "exchange": exchange_desc[sg.schedule] if world > 1 else "none",
                        "phases": phases,
+                       "x_placement": None if world == 1 else (
+                           "each rank's row shard of X lives in its rows of the peer-visible exchange operand (no staging copy; "
+                           "--stage-copy adds the copy)" if x_in_operand else "ordinary device memory, copied into the exchange operand every step"),
                        "l2": "inputs larger than L2 (X %.0f MB + CSR %.0f MB vs 126 MB), no flush" %
                              (n * dim * 4 / 1e6, nnz * 4 / 1e6),
                        "preprocess_ms": prep_ms, "graph_gen_s": t_gen,

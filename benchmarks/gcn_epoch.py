@@ -41,6 +41,9 @@ def main():
     ap.add_argument("--dense", action="store_true", help="tcgen05 dense super-window plans")
     ap.add_argument("--profile", action="store_true", help="print the CUDA-time breakdown of one epoch (torch.profiler)")
     ap.add_argument("--operand", default="fp32", choices=["fp32", "bf16"], help="N > 1: exchange operand storage")
+    ap.add_argument("--direct-refs", type=int, default=None,
+                    help="N > 1, peer exchange: remote rows referenced at most this many times are read in place by the SpMM "
+                         "(0 = off, default auto)")
     ap.add_argument("--fp32-matmul", action="store_true",
                     help="Update GEMMs (torch.mm) in full FP32; default TF32 like the reference's stack "
                          "(PyTorch 1.8: allow_tf32 on by default; its fused kernels use wmma TF32, :1809-1837)")
@@ -58,7 +61,8 @@ def main():
     HCSPMM.set_dense(bool(args.dense))
     HCSPMM.set_classifier(args.classifier)
     rp, ci, info = graphs.named(args.shape, device=dev, scale=args.scale)
-    g = hd.ShardedGraph(rp, ci, schedule=args.schedule, n_slabs=args.slabs, operand=args.operand)
+    g = hd.ShardedGraph(rp, ci, schedule=args.schedule, n_slabs=args.slabs, operand=args.operand,
+                        direct_refs=args.direct_refs)
     # the SAME problem at every N: global features / labels from one seed, then this rank's rows
     # (A is binary and unnormalised like the reference's; features are scaled so the logits start O(1))
     gen = torch.Generator(device=dev).manual_seed(100)
@@ -147,9 +151,12 @@ def main():
     with torch.no_grad():
         for w in sorted({min(wt.shape) for wt in model.weights} if args.model == "gcn" else {wt.shape[0] for wt in model.weights}):
             xx = torch.randn(g.n_local, w, device=dev)
-            op = g.exchange(xx).contiguous().clone()
-            phases[f"width{w}"] = {"exchange_ms": tm(lambda: g.exchange(xx)) if world > 1 else 0.0,
-                                   "spmm_ms": tm(lambda: g._spmm(op, g.rowptr, g.colidx, g.pre)),
+            ex_ms = tm(lambda: g.exchange(xx)) if world > 1 else 0.0
+            op = g.exchange(xx)                  # the operand of the latest exchange (segment mode reads the peers' too)
+            if world > 1:
+                dist.barrier()
+            phases[f"width{w}"] = {"exchange_ms": ex_ms,
+                                   "spmm_ms": tm(lambda: g.local_spmm(op)),
                                    "aggregate_ms": tm(lambda: g.aggregate(xx))}
     if rank == 0:
         print(json.dumps({"metric": "gcn_epoch_ms", "value": times[len(times) // 2], "unit": "ms", "n_gpus": world,
@@ -159,6 +166,7 @@ def main():
                                      "classes": args.classes, "schedule": g.schedule, "slabs": g.n_slabs,
                                      "exchange_rows_vs_allgather": (g.exchange_rows() / max(1, (world - 1) * g.max_rows)) if world > 1 else None,
                                      "classifier": args.classifier, "operand": args.operand,
+                                     "in_place": None if g.direct is None else {k_: g.direct[k_] for k_ in ("T", "rows", "refs", "pulled_rows", "halo_rows")},
                                      "update_gemm": "HCSPMM.gemm_tf32 (cvt.rna TF32, FP32 accumulate); weight gradients torch.mm " +
                                                     ("fp32" if args.fp32_matmul else "tf32")},
                           "phases": phases, "loss_first": losses[0], "loss_last": losses[-1],

@@ -281,6 +281,10 @@ int hcspmm_spmm_aux(const float *d_x, int64_t ldx, int32_t x_rows, const int32_t
   const int64_t total_cols = aux ? aux->total_cols : 0;
   // the tcgen05 kernel holds a [128 x <=256] accumulator in TMEM: wider operands go in column blocks of 256
   const int32_t dblock = dim > 256 ? 256 : dim;
+  if (aux && aux->d_colidx_segments && d_plan && n_dense > 0) {
+    set_error("spmm: segment-tagged column ids cannot be combined with a dense super-window plan");
+    return HCSPMM_E_INVALID;
+  }
   const bool dense = d_plan && n_dense > 0 && tuning().umma && precision == HCSPMM_PRECISION_TF32 && d_x && d_y &&
                      (ldx & 3) == 0 && (dim % 16) == 0 && dense_supported(d_x, d_y, ldy, dblock);
   if (!dense)

@@ -73,6 +73,9 @@ struct BalParams {
                      // other items (and 0) use the warp-per-row / CTA-per-long-row phases
   int hint_cls_min;  // >= 0: s.colidx is TAGGED (hcspmm_tag_columns); rows of class >= this are loaded evict_last,
                      // the others evict_first.  -1: plain column ids, every row evict_last
+  int seg_mode;           // 1: s.colidx carries segment tags, seg_x[] is valid
+  const float *seg_x[8];  // segment mode (hcspmm_aux_t.d_colidx_segments): base of the X segment a column id's bits
+                          // 29..31 name; seg_x[0] = s.x
 };
 constexpr int MAX_WPC = 8;
 
@@ -187,15 +190,35 @@ struct GatherHint {
   unsigned mask;      // column id = tagged & mask
   unsigned cls_min;   // hot iff (tagged >> 29) >= cls_min
   uint64_t pol_hot, pol_cold;
+  const float *const *seg;   // MODE 2: bases of the X segments (shared memory), indexed by tagged >> 29
+  int lane_off;              // MODE 2: this lane's float offset inside a row (feature slab + lane vector)
 };
-__device__ __forceinline__ GatherHint no_hint() { return GatherHint{0xffffffffu, 0u, 0ull, 0ull}; }
+__device__ __forceinline__ GatherHint no_hint() { return GatherHint{0xffffffffu, 0u, 0ull, 0ull, nullptr, 0}; }
 __device__ __forceinline__ GatherHint make_hint(int cls_min) {
   GatherHint h;
   h.mask = 0x1fffffffu;
   h.cls_min = (unsigned)cls_min;
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(h.pol_hot));
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(h.pol_cold));
+  h.seg = nullptr;
+  h.lane_off = 0;
   return h;
+}
+// MODE 2 -- X in SEGMENTS: bits 29..31 of a column id select the buffer its row lives in.  Segment 0 is the rank's own
+// exchange operand; segments 1..7 are the operands of its PEERS, mapped over NVLink (CUDA IPC): rows of X that the
+// shard references only once or twice are not copied into the local operand first (halo pull) but read in place by
+// the gather itself -- the transfer of those rows overlaps the sums, and they are neither written to nor re-read
+// from local memory.  Same loads, same sum order: only the address of a row depends on its segment.
+__device__ __forceinline__ GatherHint make_segments(const float *const *seg, int lane_off) {
+  return GatherHint{0x1fffffffu, 0u, 0ull, 0ull, seg, lane_off};
+}
+// the X row of a (possibly tagged) column id, at this lane's offset
+template <int MODE>
+__device__ __forceinline__ const float *row_ptr(const float *__restrict__ xlane, long long ldx, unsigned ct,
+                                                const GatherHint &h) {
+  if constexpr (MODE == 2) return h.seg[ct >> 29] + h.lane_off + (long long)(ct & h.mask) * ldx;
+  else if constexpr (MODE == 1) return xlane + (long long)(ct & h.mask) * ldx;
+  else return xlane + (long long)(int)ct * ldx;
 }
 
 #ifndef HCSPMM_INFLIGHT_BYTES
@@ -207,7 +230,7 @@ __device__ __forceinline__ GatherHint make_hint(int cls_min) {
 // chunk0, chunk0 + chunk_stride, ...   A group of LPE lanes reads one X row, lane g of the group
 // owning vectors g, g + LPE, ... (NV of them, VW floats each).
 // ---------------------------------------------------------------------------------------
-template <int LPE, int NV, int VW, bool B16, bool HINT = false>
+template <int LPE, int NV, int VW, bool B16, int MODE = 0>
 __device__ __forceinline__ void gather_accumulate(Vec<VW, B16> (&acc)[NV], const float *__restrict__ xlane,
                                                   long long ldx, int x_rows,
                                                   const int *__restrict__ colidx, int eb, int ee,
@@ -230,7 +253,7 @@ __device__ __forceinline__ void gather_accumulate(Vec<VW, B16> (&acc)[NV], const
     const int nb = base + chunk_stride * 32;
     c_next = (nb + lane < ee) ? __ldg(colidx + nb + lane) : -1;  // next chunk's ids, early
     (void)all_active;
-    const bool fast = n == 32 && __all_sync(0xffffffffu, ((unsigned)c & (HINT ? h.mask : 0xffffffffu)) < (unsigned)x_rows);
+    const bool fast = n == 32 && __all_sync(0xffffffffu, ((unsigned)c & (MODE ? h.mask : 0xffffffffu)) < (unsigned)x_rows);
     if (fast) {
       // full chunk, every id valid: unpredicated ring of U loads in flight -- slot s % U is consumed
       // and immediately refilled with step s + U.  Lanes beyond the slab width (voff < 0) re-read
@@ -239,13 +262,12 @@ __device__ __forceinline__ void gather_accumulate(Vec<VW, B16> (&acc)[NV], const
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const unsigned ct = (unsigned)__shfl_sync(0xffffffffu, c, u * G + q);
-        if constexpr (HINT) {
-          const float *src = xlane + (long long)(ct & h.mask) * ldx;
+        const float *src = row_ptr<MODE>(xlane, ldx, ct, h);
+        if constexpr (MODE == 1) {
           const uint64_t pol = (ct >> 29) >= h.cls_min ? h.pol_hot : h.pol_cold;
 #pragma unroll
           for (int i = 0; i < NV; ++i) v[u][i].load_hint(src + voff[i], pol);
         } else {
-          const float *src = xlane + (long long)(int)ct * ldx;
 #pragma unroll
           for (int i = 0; i < NV; ++i) v[u][i].load(src + voff[i]);
         }
@@ -256,13 +278,12 @@ __device__ __forceinline__ void gather_accumulate(Vec<VW, B16> (&acc)[NV], const
         for (int i = 0; i < NV; ++i) acc[i].add(v[s % U][i]);
         if (s + U < STEPS) {
           const unsigned ct = (unsigned)__shfl_sync(0xffffffffu, c, (s + U) * G + q);
-          if constexpr (HINT) {
-            const float *src = xlane + (long long)(ct & h.mask) * ldx;
+          const float *src = row_ptr<MODE>(xlane, ldx, ct, h);
+          if constexpr (MODE == 1) {
             const uint64_t pol = (ct >> 29) >= h.cls_min ? h.pol_hot : h.pol_cold;
 #pragma unroll
             for (int i = 0; i < NV; ++i) v[s % U][i].load_hint(src + voff[i], pol);
           } else {
-            const float *src = xlane + (long long)(int)ct * ldx;
 #pragma unroll
             for (int i = 0; i < NV; ++i) v[s % U][i].load(src + voff[i]);
           }
@@ -276,13 +297,13 @@ __device__ __forceinline__ void gather_accumulate(Vec<VW, B16> (&acc)[NV], const
         for (int u = 0; u < U; ++u) {
           const int j = (t + u) * G + q;
           const unsigned ct = (unsigned)__shfl_sync(0xffffffffu, c, j & 31);
-          const unsigned cu = HINT ? (ct & h.mask) : ct;
+          const unsigned cu = MODE ? (ct & h.mask) : ct;
           const bool ok = (j < n) && (cu < (unsigned)x_rows);
-          const float *src = xlane + (long long)cu * ldx;
+          const float *src = row_ptr<MODE>(xlane, ldx, ok ? ct : 0u, h);
 #pragma unroll
           for (int i = 0; i < NV; ++i) {
             if (ok && active[i]) {
-              if constexpr (HINT) v[u][i].load_hint(src + i * LPE * VW / XDIV, (ct >> 29) >= h.cls_min ? h.pol_hot : h.pol_cold);
+              if constexpr (MODE == 1) v[u][i].load_hint(src + i * LPE * VW / XDIV, (ct >> 29) >= h.cls_min ? h.pol_hot : h.pol_cold);
               else v[u][i].load(src + i * LPE * VW / XDIV);
             } else v[u][i].zero();
           }
@@ -301,7 +322,7 @@ __device__ __forceinline__ void gather_accumulate(Vec<VW, B16> (&acc)[NV], const
 // once and nothing is reduced across lanes.  The group fetches LPE column ids with one load and
 // broadcasts them inside the group (sub-warp shuffle masks: groups may run different trip counts).
 // ---------------------------------------------------------------------------------------
-template <int LPE, int NV, int VW, bool B16, bool HINT = false>
+template <int LPE, int NV, int VW, bool B16, int MODE = 0>
 __device__ __forceinline__ void gather_group_row(Vec<VW, B16> (&acc)[NV], const float *__restrict__ xlane,
                                                  long long ldx, int x_rows,
                                                  const int *__restrict__ colidx, int eb, int ee, int lane,
@@ -321,13 +342,13 @@ __device__ __forceinline__ void gather_group_row(Vec<VW, B16> (&acc)[NV], const 
 #pragma unroll
       for (int u = 0; u < UB; ++u) {
         const unsigned ct = (unsigned)__shfl_sync(gmask, my, q * LPE + ((j0 + u) & (LPE - 1)));
-        const unsigned cu = HINT ? (ct & h.mask) : ct;
+        const unsigned cu = MODE ? (ct & h.mask) : ct;
         const bool ok = (j0 + u < cnt) && (cu < (unsigned)x_rows);
-        const float *src = xlane + (long long)cu * ldx;
+        const float *src = row_ptr<MODE>(xlane, ldx, ok ? ct : 0u, h);
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
           if (ok && active[i]) {
-            if constexpr (HINT) v[u][i].load_hint(src + i * LPE * VW / XDIV, (ct >> 29) >= h.cls_min ? h.pol_hot : h.pol_cold);
+            if constexpr (MODE == 1) v[u][i].load_hint(src + i * LPE * VW / XDIV, (ct >> 29) >= h.cls_min ? h.pol_hot : h.pol_cold);
             else v[u][i].load(src + i * LPE * VW / XDIV);
           } else v[u][i].zero();
         }
@@ -678,12 +699,13 @@ __global__ void merge_path_splits_kernel(const int *__restrict__ rowptr, int n_r
   splits[i] = merge_path_rows(rowptr, n_rows, nnz, diag);
 }
 
-template <int LPE, int NV, int VW, int MINB, bool B16 = false, bool HINT = false>
+template <int LPE, int NV, int VW, int MINB, bool B16 = false, int MODE = 0>
 __global__ void __launch_bounds__(CTA_THREADS, MINB) spmm_balanced_kernel(const BalParams bp) {
   const SpmmParams &p = bp.s;
   extern __shared__ __align__(16) float smem[];   // [2 * CTA_WARPS * slab] row pieces | uint16 row offsets [chunk + 2]
   __shared__ int s_next;
   __shared__ int s_prow[CTA_WARPS][2];
+  __shared__ const float *s_seg[8];
   constexpr int G = 32 / LPE;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int k = blockIdx.x;
@@ -699,6 +721,9 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) spmm_balanced_kernel(const 
   const int x1 = __ldg(bp.splits + min((k + 1) * bp.split_stride, bp.split_max));
   const int y0 = (int)(d0 - x0), y1 = (int)(d1 - x1);
   if (tid == 0) s_next = 0;
+  if constexpr (MODE == 2) {
+    if (tid < 8) s_seg[tid] = bp.seg_x[tid];   // published by the __syncthreads() below, before any gather
+  }
   // entries [y0, y1); rows x0 .. x1-1 end here, row x1 takes part through its entries below y1
   const bool last_in = x1 < p.n_rows && __ldg(p.rowptr + x1) < y1;
   const int rows_here = x1 - x0 + (last_in ? 1 : 0);
@@ -748,7 +773,8 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) spmm_balanced_kernel(const 
   for (int i = 0; i < NV; ++i) active[i] = (g + i * LPE) < nvec;
   const bool all_active = nvec == LPE * NV;
   const float *xlane = p.x + (feat0 + g * VW) / (B16 ? 2 : 1);
-  const GatherHint hint = HINT ? make_hint(bp.hint_cls_min) : no_hint();
+  const GatherHint hint = MODE == 2 ? make_segments(s_seg, (feat0 + g * VW) / (B16 ? 2 : 1))
+                                    : (MODE == 1 ? make_hint(bp.hint_cls_min) : no_hint());
   const int e_cta = y1 - y0;
   const int short_row = (G > 1 && p.short_row > 0 && e_cta < rows_here * p.short_row &&
                          2 * rows_here >= CTA_WARPS * G)
@@ -792,7 +818,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) spmm_balanced_kernel(const 
         Vec<VW, B16> acc[NV];
 #pragma unroll
         for (int i = 0; i < NV; ++i) acc[i].zero();
-        gather_accumulate<LPE, NV, VW, B16, HINT>(acc, xlane, p.ldx, p.x_rows, p.colidx, eb, ee, 0, 1, lane, q, active,
+        gather_accumulate<LPE, NV, VW, B16, MODE>(acc, xlane, p.ldx, p.x_rows, p.colidx, eb, ee, 0, 1, lane, q, active,
                                             all_active, hint);
         group_reduce<LPE, NV, VW, B16>(acc);
         int accf = 0;
@@ -851,7 +877,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) spmm_balanced_kernel(const 
       Vec<VW, B16> acc[NV];
 #pragma unroll
       for (int i = 0; i < NV; ++i) acc[i].zero();
-      gather_group_row<LPE, NV, VW, B16, HINT>(acc, xlane, p.ldx, p.x_rows, p.colidx, eb, ee, lane, q, g, active, hint);
+      gather_group_row<LPE, NV, VW, B16, MODE>(acc, xlane, p.ldx, p.x_rows, p.colidx, eb, ee, lane, q, g, active, hint);
       int accf;
       float *yrow = out_row(r, accf) + g * VW;
 #pragma unroll
@@ -896,7 +922,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) spmm_balanced_kernel(const 
     Vec<VW, B16> acc[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) acc[i].zero();
-    gather_accumulate<LPE, NV, VW, B16, HINT>(acc, xlane, p.ldx, p.x_rows, p.colidx, eb, ee, 0, 1, lane, q, active,
+    gather_accumulate<LPE, NV, VW, B16, MODE>(acc, xlane, p.ldx, p.x_rows, p.colidx, eb, ee, 0, 1, lane, q, active,
                                         all_active, hint);
     group_reduce<LPE, NV, VW, B16>(acc);
     if (q == 0) {
@@ -924,7 +950,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) spmm_balanced_kernel(const 
     Vec<VW, B16> acc[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) acc[i].zero();
-    gather_accumulate<LPE, NV, VW, B16, HINT>(acc, xlane, p.ldx, p.x_rows, p.colidx, eb, ee, wid, CTA_WARPS, lane, q,
+    gather_accumulate<LPE, NV, VW, B16, MODE>(acc, xlane, p.ldx, p.x_rows, p.colidx, eb, ee, wid, CTA_WARPS, lane, q,
                                         active, all_active, hint);
     group_reduce<LPE, NV, VW, B16>(acc);
     if (q == 0) {
@@ -1076,9 +1102,9 @@ static cudaError_t launch_hybrid(const SpmmParams &p, dim3 grid, size_t smem, cu
   return launch_hybrid_b<LPE, NV, VW, HCSPMM_MIN_CTAS>(p, grid, smem, stream);
 }
 
-template <int LPE, int NV, int VW, bool B16, int MINB, bool HINT = false>
+template <int LPE, int NV, int VW, bool B16, int MINB, int MODE = 0>
 static cudaError_t launch_balanced_b(const BalParams &bp, dim3 grid, size_t smem, cudaStream_t stream) {
-  auto kern = spmm_balanced_kernel<LPE, NV, VW, MINB, B16, HINT>;
+  auto kern = spmm_balanced_kernel<LPE, NV, VW, MINB, B16, MODE>;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
   BalParams q = bp;
@@ -1090,6 +1116,15 @@ template <int LPE, int NV, int VW, bool B16>
 static cudaError_t launch_balanced_t(const BalParams &bp, dim3 grid, size_t smem, cudaStream_t stream) {
   // low-degree graphs (rows of a few dozen entries) are latency-bound: three CTAs per SM hide more of it than
   // the deeper gather ring of the two-CTA build does (FP32, one vector per lane: dim <= 256 / 128)
+  if (bp.seg_mode) {   // X in segments (peer-mapped operands read in place): 256-bit FP32 / BF16 rows up to 1 KB
+    if constexpr (VW == 8 && NV == 1) {
+      if constexpr (!B16)
+        if (bp.low_degree && tuning().occupancy3) return launch_balanced_b<LPE, NV, VW, B16, 3, 2>(bp, grid, smem, stream);
+      return launch_balanced_b<LPE, NV, VW, B16, HCSPMM_MIN_CTAS, 2>(bp, grid, smem, stream);
+    } else {
+      return cudaErrorInvalidValue;
+    }
+  }
   if constexpr (!B16 && VW == 8) {
     // tagged column ids + L2 residency hints (run_balanced decides; only these variants read tagged ids)
     if (bp.hint_cls_min >= 0) {
@@ -1120,6 +1155,8 @@ struct BalAux {
   void *ws = nullptr;
   size_t ws_bytes = 0;
   const int *colidx_tagged = nullptr;   // hcspmm_tag_columns: column ids with their hotness class in bits 29..31
+  const int *colidx_seg = nullptr;      // column ids with the SEGMENT of their X row in bits 29..31 (segment mode)
+  const float *seg_x[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 static int default_chunk(int slab, bool b16) {
@@ -1190,6 +1227,15 @@ static cudaError_t run_balanced(const SpmmParams &p, long long nnz, bool v8, boo
       bp.s.colidx = aux.colidx_tagged;
     }
   }
+  bp.seg_mode = 0;
+  for (int i = 0; i < 8; ++i) bp.seg_x[i] = nullptr;
+  if (aux.colidx_seg != nullptr) {
+    bp.seg_mode = 1;
+    bp.hint_cls_min = -1;
+    bp.s.colidx = aux.colidx_seg;
+    bp.seg_x[0] = p.x;
+    for (int i = 1; i < 8; ++i) bp.seg_x[i] = aux.seg_x[i] != nullptr ? aux.seg_x[i] : p.x;
+  }
   const int slab = p.slab;
   dim3 grid((unsigned)n_items, (p.dim + slab - 1) / slab, 1);
   const size_t smem = (size_t)2 * CTA_WARPS * slab * sizeof(float) + (size_t)(chunk + 4) / 2 * sizeof(int);
@@ -1259,8 +1305,11 @@ int launch_spmm(const float *x, int64_t ldx, int32_t x_rows, const int32_t *rowp
     aux.splits = aux_in->d_splits; aux.splits_chunk = aux_in->splits_chunk; aux.n_splits = aux_in->n_splits;
     aux.ws = aux_in->d_workspace; aux.ws_bytes = aux_in->workspace_bytes;
     aux.colidx_tagged = aux_in->d_colidx_tagged;
+    aux.colidx_seg = aux_in->d_colidx_segments;
+    for (int i = 0; i < 8; ++i) aux.seg_x[i] = reinterpret_cast<const float *>(aux_in->segment_x[i]);
     n_tc_windows = aux_in->n_tc_windows;
   }
+  const bool seg_mode = aux.colidx_seg != nullptr;
   if (n_rows < 0 || dim < 0 || nnz < 0 || x_rows < 0) {
     set_error("spmm: negative size");
     return HCSPMM_E_INVALID;
@@ -1293,7 +1342,15 @@ int launch_spmm(const float *x, int64_t ldx, int32_t x_rows, const int32_t *rowp
     }
     precision = HCSPMM_PRECISION_BF16;
   }
-  const bool labels = ht != nullptr && precision != HCSPMM_PRECISION_FP32 && precision != HCSPMM_PRECISION_BF16;
+  bool labels = ht != nullptr && precision != HCSPMM_PRECISION_FP32 && precision != HCSPMM_PRECISION_BF16;
+  if (seg_mode) {
+    // rows of X read in place from several buffers: only the balanced CUDA-core kernel resolves segment tags
+    if (labels && n_tc_windows != 0) {
+      set_error("spmm: segment-tagged column ids need a graph without tensor-core windows (n_tc_windows = 0)");
+      return HCSPMM_E_INVALID;
+    }
+    labels = false;
+  }
   if (labels && (!bp || (nnz > 0 && (!etc || !etr)))) {
     set_error("spmm: hybrid_type given without blockPartition/edgeToColumn/edgeToRow");
     return HCSPMM_E_INVALID;
@@ -1339,7 +1396,12 @@ int launch_spmm(const float *x, int64_t ldx, int32_t x_rows, const int32_t *rowp
     p.n_windows = n_windows;
     dim3 grid((n_windows + wpc - 1) / wpc, (dim + slab - 1) / slab, 1);
     const size_t smem = hybrid_smem_bytes(slab, false);
-    if (use_balanced(n_rows, nnz)) err = run_balanced(p, nnz, true, true, aux, stream);
+    if (seg_mode && (slab < dim || dim > 256)) {
+      if (xb) scratch_free(xb, stream);
+      set_error("spmm: segment mode serves rows of at most 256 features (column blocks beyond)");
+      return HCSPMM_E_INVALID;
+    }
+    if (use_balanced(n_rows, nnz) || seg_mode) err = run_balanced(p, nnz, true, true, aux, stream);
     else if (slab <= 32) err = launch_hybrid_bf16<4, 1>(p, grid, smem, stream);
     else if (slab <= 64) err = launch_hybrid_bf16<8, 1>(p, grid, smem, stream);
     else if (slab <= 128) err = launch_hybrid_bf16<16, 1>(p, grid, smem, stream);
@@ -1348,6 +1410,11 @@ int launch_spmm(const float *x, int64_t ldx, int32_t x_rows, const int32_t *rowp
     if (xb) scratch_free(xb, stream);
     if (err != cudaSuccess) { set_error("spmm bf16 launch: %s", cudaGetErrorString(err)); return (int)err; }
     return 0;
+  }
+  if (seg_mode && !(vec && tuning().vec8 != 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 31) == 0 &&
+                    (ldx & 7) == 0 && (ldy & 7) == 0 && (dim & 7) == 0 && dim <= 256)) {
+    set_error("spmm: segment mode needs 32-byte aligned rows of at most 256 features (FP32)");
+    return HCSPMM_E_ALIGN;
   }
   if (!vec && (long long)n_rows * dim >= (1 << 20) && tuning().pad_odd) {
     // Large operand with an odd width / unaligned rows (e.g. dim = 47 classes): run the vector
@@ -1404,7 +1471,7 @@ int launch_spmm(const float *x, int64_t ldx, int32_t x_rows, const int32_t *rowp
     const bool v8 = tuning().vec8 != 0 &&
                     ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 31) == 0 &&
                     (ldx & 7) == 0 && (ldy & 7) == 0 && (dim & 7) == 0 && (slab & 7) == 0;
-    if (use_balanced(n_rows, nnz)) {
+    if (use_balanced(n_rows, nnz) || seg_mode) {
       // tensor-core windows (if any are labelled) on the per-window kernel, everything else balanced
       err = cudaSuccess;
       if (labels && n_tc_windows != 0) {   // no window labelled 1 (e.g. the shipped selector): nothing to launch

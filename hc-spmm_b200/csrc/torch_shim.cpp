@@ -290,6 +290,46 @@ torch::Tensor spmm_bf16(torch::Tensor input, torch::Tensor nodePointer, torch::T
   return out;
 }
 
+// out (+)= A * X with X in SEGMENTS (hcspmm_aux_t.d_colidx_segments): `input` is segment 0 (FP32 or bfloat16 rows),
+// segment_ptrs[s], s = 1..7, are device addresses of further buffers with the same row pitch -- the peers' exchange
+// operands, mapped over NVLink -- and colidx_segments carries the segment of every entry in bits 29..31.  x_rows
+// bounds the row index inside any segment.  CUDA-core balanced kernel; row_nzr / col_nzr are the products of
+// preprocess() on the shard (split points, workspace).
+torch::Tensor spmm_segments(torch::Tensor input, torch::Tensor nodePointer, torch::Tensor colidx_segments,
+                            std::vector<int64_t> segment_ptrs, int64_t x_rows, torch::Tensor out, bool accumulate,
+                            c10::optional<torch::Tensor> row_nzr, c10::optional<torch::Tensor> col_nzr) {
+  const bool b16 = input.scalar_type() == torch::kBFloat16;
+  TORCH_CHECK(input.is_cuda() && (b16 || input.scalar_type() == torch::kFloat32) && input.dim() == 2 && input.stride(1) == 1,
+              "input must be a 2-D float32 / bfloat16 CUDA tensor with unit column stride");
+  TORCH_CHECK(out.is_cuda() && out.scalar_type() == torch::kFloat32 && out.dim() == 2 && out.stride(1) == 1 &&
+              out.device() == input.device(), "out must be a 2-D float32 CUDA tensor on the input's device");
+  check_i32(nodePointer, "nodePointer", input);
+  check_i32(colidx_segments, "colidx_segments", input);
+  TORCH_CHECK(segment_ptrs.size() <= 8, "at most 8 segments");
+  Graph g;
+  g.rowptr = nodePointer.data_ptr<int32_t>();
+  g.colidx = colidx_segments.data_ptr<int32_t>();
+  g.bp = g.etc = g.etr = g.ht = nullptr;
+  g.n_rows = (int32_t)(nodePointer.size(0) - 1);
+  g.nnz = colidx_segments.size(0);
+  TORCH_CHECK(out.size(0) == g.n_rows && out.size(1) == input.size(1), "out must be [num_nodes, dim]");
+  TORCH_CHECK(x_rows >= input.size(0) && x_rows < (1LL << 29), "x_rows must bound every segment's rows (< 2^29)");
+  c10::cuda::CUDAGuard guard(input.device());
+  const int64_t dim = input.size(1);
+  AuxView v = make_aux(input, g, row_nzr.has_value() ? *row_nzr : torch::Tensor(),
+                       col_nzr.has_value() ? *col_nzr : torch::Tensor(), dim);
+  if (!v.ok) v.aux.n_tc_windows = 0;
+  v.aux.d_colidx_tagged = nullptr;
+  v.aux.d_colidx_segments = g.colidx;
+  for (size_t i = 0; i < segment_ptrs.size(); ++i) v.aux.segment_x[i] = reinterpret_cast<const void *>(segment_ptrs[i]);
+  check_rc(hcspmm_spmm_aux(reinterpret_cast<const float *>(input.data_ptr()), input.stride(0), (int32_t)x_rows, g.rowptr,
+                           g.colidx, nullptr, nullptr, nullptr, nullptr, g.n_rows, g.nnz, (int32_t)dim,
+                           b16 ? HCSPMM_PRECISION_BF16_STORED : HCSPMM_PRECISION_FP32, accumulate ? 1 : 0,
+                           out.data_ptr<float>(), out.stride(0), &v.aux, at::cuda::getCurrentCUDAStream().stream()),
+           "spmm_segments");
+  return out;
+}
+
 // out[r, :] (bfloat16 view, any row pitch) = round-to-nearest-even of input[r, :]
 torch::Tensor f32_to_bf16_into(torch::Tensor input, torch::Tensor out) {
   TORCH_CHECK(input.is_cuda() && input.scalar_type() == torch::kFloat32 && input.dim() == 2 && input.stride(1) == 1,
@@ -362,14 +402,25 @@ std::vector<torch::Tensor> spmm_forward_final_fused(torch::Tensor input, torch::
   return fused_impl(input, g, row_nzr, col_nzr, weights, output, "forward_final_fused");
 }
 
-torch::Tensor gemm_tf32(torch::Tensor a, torch::Tensor b) {
-  check_f32_2d(a, "a");
+// a @ b (TF32 product, FP32 accumulate).  `out` (optional): a [m, n] float32 view with unit column stride -- e.g. the
+// own-rows segment of a multi-GPU exchange operand, so the Update GEMM's result needs no staging copy.
+torch::Tensor gemm_tf32(torch::Tensor a, torch::Tensor b, c10::optional<torch::Tensor> out_opt) {
+  TORCH_CHECK(a.is_cuda() && a.scalar_type() == torch::kFloat32 && a.dim() == 2 && (a.stride(1) == 1 || a.size(1) == 1),
+              "a must be a 2-D float32 CUDA tensor with unit column stride");
   check_f32_2d(b, "b");
   TORCH_CHECK(a.device() == b.device() && a.size(1) == b.size(0), "gemm_tf32: shape/device mismatch");
   c10::cuda::CUDAGuard guard(a.device());
-  auto out = torch::empty({a.size(0), b.size(1)}, a.options());
-  check_rc(hcspmm_gemm_tf32(a.data_ptr<float>(), a.size(1), b.data_ptr<float>(), b.size(1), (int32_t)a.size(0),
-                            (int32_t)a.size(1), (int32_t)b.size(1), out.data_ptr<float>(), b.size(1),
+  torch::Tensor out;
+  if (out_opt.has_value()) {
+    out = *out_opt;
+    TORCH_CHECK(out.is_cuda() && out.device() == a.device() && out.scalar_type() == torch::kFloat32 && out.dim() == 2 &&
+                out.size(0) == a.size(0) && out.size(1) == b.size(1) && (out.stride(1) == 1 || out.size(1) == 1),
+                "gemm_tf32: out must be a [m, n] float32 view with unit column stride on a's device");
+  } else {
+    out = torch::empty({a.size(0), b.size(1)}, a.options());
+  }
+  check_rc(hcspmm_gemm_tf32(a.data_ptr<float>(), a.stride(0), b.data_ptr<float>(), b.size(1), (int32_t)a.size(0),
+                            (int32_t)a.size(1), (int32_t)b.size(1), out.data_ptr<float>(), out.stride(0),
                             at::cuda::getCurrentCUDAStream().stream()),
            "gemm_tf32");
   return out;
@@ -452,8 +503,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         pybind11::arg("input"), pybind11::arg("nodePointer"), pybind11::arg("edgeList"), pybind11::arg("blockPartition"),
         pybind11::arg("edgeToColumn"), pybind11::arg("edgeToRow"), pybind11::arg("hybrid_type"), pybind11::arg("out"),
         pybind11::arg("accumulate"), pybind11::arg("row_nzr") = pybind11::none(), pybind11::arg("col_nzr") = pybind11::none());
+  m.def("spmm_segments", &spmm_segments, "out (+)= A @ X with X in segments (peer-mapped operands read in place)",
+        pybind11::arg("input"), pybind11::arg("nodePointer"), pybind11::arg("colidx_segments"), pybind11::arg("segment_ptrs"), pybind11::arg("x_rows"),
+        pybind11::arg("out"), pybind11::arg("accumulate") = false, pybind11::arg("row_nzr") = pybind11::none(), pybind11::arg("col_nzr") = pybind11::none());
   m.def("f32_to_bf16_into", &f32_to_bf16_into, "out (bfloat16 view) = RNE(input)");
-  m.def("gemm_tf32", &gemm_tf32, "a @ b with TF32 tensor-core product");
+  m.def("gemm_tf32", &gemm_tf32, "a @ b with TF32 tensor-core product (optionally into a row-strided `out`)",
+        pybind11::arg("a"), pybind11::arg("b"), pybind11::arg("out") = pybind11::none());
   m.def("set_classifier", &set_classifier, "shipped | intended | b200 | all_cuda | all_tc; returns the previous mode");
   m.def("set_precision", &set_precision, "tf32 | tf32x2 | fp32 | bf16; returns the previous mode");
   m.def("set_dense", &set_dense, "tcgen05 kernels: dense super-window plans in preprocess()/forward*(), Update GEMM");

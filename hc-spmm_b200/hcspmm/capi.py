@@ -44,7 +44,8 @@ class Aux(ctypes.Structure):
     _fields_ = [("d_splits", ctypes.c_void_p), ("splits_chunk", ctypes.c_int32), ("n_splits", ctypes.c_int32),
                 ("n_tc_windows", ctypes.c_int32), ("d_plan", ctypes.c_void_p), ("n_dense", ctypes.c_int32),
                 ("plan_full", ctypes.c_int32), ("total_cols", ctypes.c_int64), ("d_workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
-                ("d_colidx_tagged", ctypes.c_void_p)]
+                ("d_colidx_tagged", ctypes.c_void_p), ("d_colidx_segments", ctypes.c_void_p),
+                ("segment_x", ctypes.c_void_p * 8)]
 
 
 def lib() -> ctypes.CDLL:

@@ -71,7 +71,7 @@ def _default_spmm():
 class ShardedGraph:
     def __init__(self, rowptr: torch.Tensor, colidx: torch.Tensor, group=None, schedule: str = "gather",
                  n_slabs: int = 1, spmm=None, preprocess=None, cuts=None, n_passes: int = 1,
-                 operand: str = "fp32", single: bool = False):
+                 operand: str = "fp32", single: bool = False, direct_refs: int | None = None):
         """rowptr / colidx: the FULL graph's CSR on this rank's device (identical on every rank).
         cuts: reuse another ShardedGraph's row cuts (the transposed graph for backward must be
         partitioned like the forward one).
@@ -81,7 +81,13 @@ class ShardedGraph:
         operand = "bf16" ("peer" schedule, widths that are multiples of 8): the exchange operand is stored as
         bfloat16 -- every rank rounds its own rows once (RNE), the halo travels at half the bytes and the local
         SpMM gathers bfloat16 rows with FP32 accumulation: the BF16 precision mode of the single-GPU path
-        (north star: 1e-2 against FP32), end to end.  "fp32" (default) is exact."""
+        (north star: 1e-2 against FP32), end to end.  "fp32" (default) is exact.
+        direct_refs = T ("peer" schedule): remote rows of X that this shard references at most T times are NOT pulled
+        into the local operand; the SpMM's gather reads them in place from their owner's peer-mapped operand
+        (segment-tagged column ids, HCSPMM.spmm_segments) -- on a power-law graph 40 % of a 1/8 shard's halo rows
+        are referenced exactly once (4.5 % of its remote references), so the pull shrinks by that much, those rows
+        are neither written to nor re-read from local memory, and their transfer overlaps the sums.  None = auto
+        (2 when at least a quarter of the halo rows qualify and the shard is all CUDA-core), 0 = off."""
         assert operand in ("fp32", "bf16")
         self.operand = operand
         self.group = group
@@ -130,8 +136,8 @@ class ShardedGraph:
         else:
             owner = torch.bucketize(ci64, bounds[1:-1], right=True)
             self.colidx = (ci64 - bounds[owner] + owner * self.max_rows).to(torch.int32).contiguous()
-        del ci64
         self._fused, self._gemm = None, torch.mm
+        native = spmm is None
         if spmm is None:
             spmm, preprocess = _default_spmm()
             import HCSPMM
@@ -139,6 +145,11 @@ class ShardedGraph:
             self._gemm = lambda a, b: HCSPMM.gemm_tf32(a.contiguous(), b.contiguous())
         self._spmm = spmm
         self.pre = preprocess(self.colidx, self.rowptr) if preprocess is not None else ()
+        self.direct = None
+        if (native and self.peer is not None and not self.push and self.halo is not None and direct_refs != 0
+                and self.world <= 8 and n_passes == 1 and self.n_slabs == 1):
+            self._setup_direct(ci64, bounds, direct_refs)
+        del ci64
         self.passes = None
         self.overlap_ctas = 64
         if self.peer is not None and n_passes == 2 and self.world > 2:
@@ -150,8 +161,9 @@ class ShardedGraph:
 
     def _setup_halo(self, ci64, bounds, dev, lists_only=False):
         """Which rows of X this shard needs from every owner, and which of its own rows every peer needs."""
-        uniq = torch.unique(ci64)                                             # ascending global ids
+        uniq, refs = torch.unique(ci64, return_counts=True)                   # ascending global ids
         own = torch.bucketize(uniq, bounds[1:-1], right=True)
+        self._uniq_refs = (uniq, refs, own) if lists_only else None           # _setup_direct
         mine = torch.arange(self.r0, self.r1, device=dev, dtype=torch.int64)  # own rows: all of them
         ids = torch.cat([uniq[own < self.rank], mine, uniq[own > self.rank]])
         own = torch.bucketize(ids, bounds[1:-1], right=True)
@@ -179,6 +191,41 @@ class ShardedGraph:
             send_seg[1:] = torch.cumsum(send_counts, 0).to(torch.int32)
             self.halo.update(seg=seg, src_row=want.to(torch.int32), send_seg=send_seg,
                              send_row=send_idx.to(torch.int32).contiguous())
+
+    def _setup_direct(self, ci64, bounds, direct_refs):
+        """Segment mode (see __init__, direct_refs): split the halo into rows that are pulled (referenced more than T
+        times) and rows the SpMM reads in place from their owner's operand.  Rebuilds the pull lists for the pulled
+        rows only and writes `colidx_seg`: entries of pulled / own rows address the local operand (segment 0), entries
+        of in-place rows carry segment (owner - rank) mod P in bits 29..31 and the row inside the OWNER's operand."""
+        uniq, refs, own = self._uniq_refs
+        self._uniq_refs = None
+        hdr = self.pre[4] if len(self.pre) >= 6 and self.pre[4].device.type == "cpu" else None
+        all_cuda = hdr is not None and int(hdr[1]) == 0 and int(hdr[7]) == 0        # no dense plan, no label-1 windows
+        T = 2 if direct_refs is None else int(direct_refs)
+        remote = own != self.rank
+        cold = remote & (refs <= T)
+        n_remote = int(remote.sum())
+        want_it = all_cuda and n_remote > 0 and (direct_refs is not None or 4 * int(cold.sum()) >= n_remote)
+        flag = torch.tensor([1 if want_it else 0], device=uniq.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)             # every owner's layout changes: together
+        if int(flag) == 0:
+            return
+        dev = uniq.device
+        ids, _ = partition.pulled_layout(ci64, bounds, self.rank, T)
+        own_ids = torch.bucketize(ids, bounds[1:-1], right=True)
+        recv_counts = torch.bincount(own_ids, minlength=self.world)
+        seg = torch.zeros(self.world + 1, dtype=torch.int32, device=dev)
+        seg[1:] = torch.cumsum(recv_counts, 0).to(torch.int32)
+        firsts = [None] * self.world            # where every rank's own rows start in ITS operand
+        rows_all = [None] * self.world          # and how many rows that operand has
+        dist.all_gather_object(firsts, int(seg[self.rank]), group=self.group)
+        dist.all_gather_object(rows_all, int(ids.numel()), group=self.group)
+        self.colidx_seg = partition.tag_segments(ci64, ids, bounds, self.rank, self.world, firsts)
+        pulled_before = self.halo["rows"] - self.n_local
+        self.halo = dict(ids=ids, rows=int(ids.numel()), recv=recv_counts.tolist(), ratio=self.halo["ratio"],
+                         src_row=(ids - bounds[own_ids]).to(torch.int32).contiguous(), seg=seg)
+        self.direct = dict(T=T, rows=int(cold.sum()), refs=int(refs[cold].sum()), pulled_rows=self.halo["rows"] - self.n_local,
+                           halo_rows=pulled_before, x_rows=max(rows_all), firsts=firsts)
 
     # ------------------------------------------------------------------------------------------
     def shard_rows(self, x_full: torch.Tensor) -> torch.Tensor:
@@ -211,7 +258,7 @@ class ShardedGraph:
         (HCSPMM.forward_fixed32_fused: one tcgen05 kernel when the shard's dense plan covers it, else aggregation +
         TMA Update GEMM) on the exchanged operand.  Injected operators (CPU tests) and BF16 operands take the two
         steps separately."""
-        if self._fused is None:
+        if self._fused is None or self.direct is not None:     # segment mode: the operand alone does not hold every row
             z = self.aggregate(x_local)
             return self._gemm(z, weights), z
         if self.world == 1:
@@ -226,9 +273,13 @@ class ShardedGraph:
         out, z = self._fused(operand, self.rowptr, self.colidx, self.pre, weights)
         return out, z
 
-    def update(self, h: torch.Tensor, weights: torch.Tensor) -> torch.Tensor:
-        """The row-local Update product H W on the library's TF32 GEMM (TMA + tcgen05)."""
-        return self._gemm(h, weights)
+    def update(self, h: torch.Tensor, weights: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """The row-local Update product H W on the library's TF32 GEMM (TMA + tcgen05); `out`: e.g. own_rows(width),
+        so that the product lands in the exchange operand of the aggregation that follows."""
+        if out is None or self._fused is None:
+            return self._gemm(h, weights)
+        import HCSPMM
+        return HCSPMM.gemm_tf32(h.contiguous(), weights.contiguous(), out)
 
     @property
     def x_rows(self) -> int:
@@ -266,6 +317,8 @@ class ShardedGraph:
         """Rows of X this rank receives from its peers per aggregation."""
         if self.world == 1:
             return 0
+        if self.direct is not None:       # pulled rows + one row per in-place reference: what crosses NVLink
+            return self.direct["pulled_rows"] + self.direct["refs"]
         return self.halo["rows"] - self.n_local if self.halo is not None else (self.world - 1) * self.max_rows
 
     def check(self):
@@ -302,17 +355,15 @@ class ShardedGraph:
             rp, ci = rp.to(torch.int32), self.colidx[m].contiguous()
             self.passes.append(dict(rowptr=rp, colidx=ci, pre=preprocess(ci, rp), mask=sum(1 << o for o in owners)))
 
-    def _peer_stage(self, x_local: torch.Tensor):
-        """Write the shard into the own-rows segment of this width's next operand buffer (peer-visible) and pass
-        the barrier: afterwards every rank's shard of this aggregation can be pulled.  -> (operand, padded width).
-        With operand = "bf16" (and a width that is a multiple of 8) the buffer holds bfloat16 rows."""
-        dim, dev = x_local.shape[1], x_local.device
+    def _peer_bufs(self, dim: int):
+        """The two peer-visible operand buffers of this aggregation width (created collectively on first use)."""
         b16 = self.operand == "bf16" and dim % 8 == 0
         dpad = dim if b16 else (dim + 7) // 8 * 8                 # 32-byte FP32 rows: the 256-bit gather path
         esz = 2 if b16 else 4
         key = ("peer", dpad, b16)
         h = self.halo
         if key not in self._bufs:
+            dev = self.peer.device
             pm, slots = self.peer, []
             own0 = int(h["seg"][self.rank])
             firsts = [None] * self.world                         # every rank's own-segment offset in ITS operand
@@ -328,13 +379,47 @@ class ShardedGraph:
                     table = torch.tensor([p + f * dpad * esz for p, f in zip(ptrs, firsts)], dtype=torch.int64, device=dev)
                 t = pm.tensor(ptr, (h["rows"], dpad), torch.int16).view(torch.bfloat16) if b16 else \
                     pm.tensor(ptr, (h["rows"], dpad))
-                slots.append((t, table))
+                # segment s = the operand of rank (rank + s) mod P, from its first row (segment mode)
+                segs_x = [0] + [ptrs[(self.rank + t_) % self.world] for t_ in range(1, self.world)]
+                slots.append((t, table, segs_x))
             self._bufs[key] = dict(slots=slots, turn=0, own0=own0)
-        b = self._bufs[key]
-        cat, self._peer_tab = b["slots"][b["turn"]]
+        return self._bufs[key], dpad, b16
+
+    def own_rows(self, dim: int):
+        """Where this rank's rows of the NEXT exchange operand of width `dim` live: a [n_local, dim] FP32 view of
+        peer-visible memory.  A producer that writes X there (the Update GEMM of a GCN layer: `update(h, w, out=...)`,
+        or a caller that keeps a static X there) hands `aggregate` that view and no staging copy is made.  Stream
+        ordered: write it on the stream the previous aggregation ran on.  None when the exchange does not go through
+        peer memory (one rank, NCCL schedules) or the operand is stored as bfloat16."""
+        if self.peer is None or self.world == 1:
+            return None
+        b, dpad, b16 = self._peer_bufs(dim)
+        if b16:
+            return None
+        cat = b["slots"][b["turn"]][0]
+        return cat[b["own0"]: b["own0"] + self.n_local, :dim]
+
+    def _peer_stage(self, x_local: torch.Tensor):
+        """Write the shard into the own-rows segment of this width's next operand buffer (peer-visible) and pass
+        the barrier: afterwards every rank's shard of this aggregation can be pulled.  -> (operand, padded width).
+        With operand = "bf16" (and a width that is a multiple of 8) the buffer holds bfloat16 rows.  An x_local that
+        already IS the own-rows segment of one of the two buffers (own_rows) is used where it lies."""
+        dim = x_local.shape[1]
+        b, dpad, b16 = self._peer_bufs(dim)
+        h = self.halo
+        in_place = None
+        if not b16 and x_local.dtype == torch.float32 and x_local.stride(0) == dpad:
+            for k_, slot in enumerate(b["slots"]):
+                if x_local.data_ptr() == slot[0].data_ptr() + b["own0"] * dpad * 4:
+                    in_place = k_
+        if in_place is not None:
+            b["turn"] = in_place
+        cat, self._peer_tab, self._peer_segs = b["slots"][b["turn"]]
         b["turn"] ^= 1
         own = cat[b["own0"]: b["own0"] + self.n_local]
-        if b16:
+        if in_place is not None:
+            pass                                                 # the producer wrote the rows where they are read
+        elif b16:
             import HCSPMM
             HCSPMM.f32_to_bf16_into(x_local, own)                # one rounding per row, on its owner
         else:
@@ -360,9 +445,30 @@ class ShardedGraph:
             return
         self._pull(self._peer_tab, dpad, h["src_row"], h["seg"], self.world, cat, col0, width, mask, self.rank + 1)
 
+    def _spmm_segments(self, cat: torch.Tensor) -> torch.Tensor:
+        """Segment mode: Y_r from the local operand `cat` (own + pulled rows) and the peers' operands of the same
+        exchange, read in place (the operand returned by the latest _peer_stage of this width)."""
+        import HCSPMM
+        dpad = cat.shape[1]
+        y = torch.empty(self.n_local, dpad, device=cat.device)
+        wmax = 256                                                   # the kernel's widest row: column blocks beyond
+        esz = cat.element_size()
+        for c0 in range(0, dpad, wmax):
+            c1 = min(dpad, c0 + wmax)
+            segs = [0] + [p_ + c0 * esz for p_ in self._peer_segs[1:]]
+            HCSPMM.spmm_segments(cat[:, c0:c1], self.rowptr, self.colidx_seg, segs, self.direct["x_rows"], y[:, c0:c1],
+                                 False, self.pre[4], self.pre[5])
+        return y
+
+    def local_spmm(self, operand: torch.Tensor) -> torch.Tensor:
+        """The compute step alone, on the operand the latest `exchange` returned (phase timing)."""
+        if self.direct is not None:
+            return self._spmm_segments(operand)
+        return self._spmm(operand, self.rowptr, self.colidx, self.pre)
+
     def _aggregate_peer(self, x_local: torch.Tensor) -> torch.Tensor:
         dim, dev = x_local.shape[1], x_local.device
-        cat, dpad = self._peer_stage(x_local.float())
+        cat, dpad = self._peer_stage(x_local if x_local.dtype == torch.float32 else x_local.float())
         n_slabs = self.n_slabs if (dpad >= 32 * self.n_slabs and cat.dtype == torch.float32 and not self.push) else 1
         if self.passes is not None and not self.push:
             p0, p1 = self.passes
@@ -382,6 +488,12 @@ class ShardedGraph:
             self._spmm(cat, p0["rowptr"], p0["colidx"], p0["pre"], out=y)
             cur.wait_event(ev1)
             self._spmm(cat, p1["rowptr"], p1["colidx"], p1["pre"], out=y, accumulate=True)
+            return y if dpad == dim else y[:, :dim]
+        if self.direct is not None:
+            # pulled rows first (they are gathered many times), then ONE kernel that sums local operand rows and rows
+            # read in place from the peers' operands over NVLink
+            self._pull_halo(cat, dpad)
+            y = self._spmm_segments(cat)
             return y if dpad == dim else y[:, :dim]
         if n_slabs == 1:
             self._pull_halo(cat, dpad)
@@ -492,7 +604,8 @@ class ShardedGCNLayer(torch.autograd.Function):
     def forward(ctx, x_local, weights, graph: ShardedGraph, graph_t):
         ctx.graph_t = graph_t if graph_t is not None else graph
         ctx.save_for_backward(x_local, weights)
-        return graph.aggregate(graph.update(x_local, weights))
+        # the Update product is written straight into the rank's rows of the exchange operand (no staging copy)
+        return graph.aggregate(graph.update(x_local, weights, out=graph.own_rows(weights.shape[1])))
 
     @staticmethod
     def backward(ctx, d_y):

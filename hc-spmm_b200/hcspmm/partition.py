@@ -58,3 +58,40 @@ def split_by_source(rowptr: torch.Tensor, colidx: torch.Tensor, cuts: list[int])
         rp[1:] = torch.cumsum(cnt, 0)
         out.append((rp.to(torch.int32), colidx[m].contiguous()))
     return out
+
+
+SEG_SHIFT = 29          # bits 29..31 of a segment-tagged column id: the X buffer the row is read from
+SEG_MASK = (1 << SEG_SHIFT) - 1
+
+
+def pulled_layout(colidx64: torch.Tensor, bounds: torch.Tensor, rank: int, max_refs: int):
+    """Segment mode of the peer exchange: which rows of X rank `rank` keeps in its operand.
+    colidx64: the shard's global column ids; bounds: the row cuts (int64 tensor, world + 1 entries).
+    -> (ids, cold): ids = the operand layout [pulled rows of lower ranks | ALL own rows | pulled rows of higher ranks],
+    ascending global ids in each part, where a remote row is pulled iff the shard references it more than max_refs
+    times; cold = the remote rows left at their owner (read in place by the gather), with their reference counts."""
+    uniq, refs = torch.unique(colidx64, return_counts=True)
+    own = torch.bucketize(uniq, bounds[1:-1], right=True)
+    cold = (own != rank) & (refs <= max_refs)
+    keep = ~cold
+    mine = torch.arange(int(bounds[rank]), int(bounds[rank + 1]), device=colidx64.device, dtype=torch.int64)
+    ids = torch.cat([uniq[keep & (own < rank)], mine, uniq[keep & (own > rank)]])
+    return ids, (uniq[cold], refs[cold])
+
+
+def tag_segments(colidx64: torch.Tensor, ids: torch.Tensor, bounds: torch.Tensor, rank: int, world: int,
+                 firsts) -> torch.Tensor:
+    """Segment-tagged int32 column ids of a shard (hcspmm_aux_t.d_colidx_segments): an entry whose row is in the local
+    operand `ids` -> its position there (segment 0); any other entry -> segment (owner - rank) mod world in bits 29..31
+    and, below, the row inside the OWNER's operand: firsts[owner] (where the owner's own rows start in its operand) +
+    the row's index at its owner."""
+    assert world <= 8 and ids.numel() <= SEG_MASK
+    pos = torch.searchsorted(ids, colidx64).clamp_(max=max(0, ids.numel() - 1))
+    local = ids[pos] == colidx64
+    owner = torch.bucketize(colidx64, bounds[1:-1], right=True)
+    first_t = torch.as_tensor(list(firsts), device=colidx64.device, dtype=torch.int64)
+    row = first_t[owner] + colidx64 - bounds[owner]
+    assert int(row.max()) <= SEG_MASK if row.numel() else True
+    far = (((owner - rank) % world) << SEG_SHIFT) | row
+    v = torch.where(local, pos, far)
+    return torch.where(v >= 2 ** 31, v - 2 ** 32, v).to(torch.int32).contiguous()

@@ -215,6 +215,16 @@ int hcspmm_spmm_plan(const float *d_x, int64_t ldx, int32_t x_rows, const int32_
  *                                        (hcspmm_tag_columns): when X does not fit the L2 budget (knob "l2_hot_mb"),
  *                                        the balanced kernel loads the hottest rows evict_last and the others
  *                                        evict_first instead of leaving residency to chance; NULL = every row evict_last
+ *   d_colidx_segments / segment_x        SEGMENT MODE: X lives in up to 8 buffers of equal row pitch; the CSR's
+ *                                        column ids carry, in bits 29..31, the segment their row is read from
+ *                                        (0 = d_x, s = segment_x[s]) and in bits 0..28 the row inside that segment.
+ *                                        The multi-GPU layer uses it to read rows of X that a shard references only
+ *                                        once or twice IN PLACE from the owners' peer-mapped exchange operands
+ *                                        (NVLink loads issued by the gather itself, overlapping the sums) instead of
+ *                                        copying them into the local operand first.  x_rows
+ *                                        bounds the row index of every segment.  CUDA-core balanced kernel only:
+ *                                        needs n_tc_windows = 0, no dense plan, 32-byte aligned rows, dim <= 256
+ *                                        (wider operands: column blocks); d_colidx itself is ignored.  NULL = off
  *   d_workspace / workspace_bytes        >= hcspmm_spmm_workspace_bytes() bytes, 16-byte aligned, for the row
  *                                        pieces of the balanced kernel; NULL = the library's private pool
  * hcspmm_spmm_aux(..., NULL, ...) is hcspmm_spmm.                                                              */
@@ -230,6 +240,8 @@ typedef struct {
   void *d_workspace;
   size_t workspace_bytes;
   const int32_t *d_colidx_tagged;   /* hcspmm_tag_columns output, or NULL */
+  const int32_t *d_colidx_segments; /* segment mode (multi-GPU), or NULL: see below */
+  const void *segment_x[8];         /* segment s = 1..7: base of that X buffer (same row pitch as d_x); [0] unused */
 } hcspmm_aux_t;
 size_t hcspmm_tag_columns_workspace_bytes(int32_t n_cols, int64_t nnz);
 int hcspmm_tag_columns(const int32_t *d_colidx, int64_t nnz, int32_t n_cols, int32_t *d_tagged, void *d_workspace,

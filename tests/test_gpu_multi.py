@@ -43,12 +43,19 @@ def _worker(rank, world, port, q):
         n = rp.size - 1
         d_rp, d_ci = torch.from_numpy(rp).to(dev), torch.from_numpy(ci).to(dev)
         results = []
-        cases = [("peer", 1, 1, "fp32"), ("gather", 1, 1, "fp32"), ("halo", 1, 1, "fp32"), ("peer", 2, 1, "fp32"),
-                 ("peer", 1, 2, "fp32"), ("peer", 1, 1, "bf16"), ("auto", 1, 1, "fp32"), ("push", 1, 1, "fp32"),
-                 ("push", 1, 1, "bf16")]
-        for schedule, slabs, passes, operand in cases:
-            g = hd.ShardedGraph(d_rp, d_ci, schedule=schedule, n_slabs=slabs, n_passes=passes, operand=operand)
-            for dim in (128, 100, 64):
+        # last field: direct_refs (segment mode: remote rows referenced <= T times are read in place by the SpMM;
+        # 0 = every halo row is pulled, None = auto, 10**6 = nothing is pulled at all)
+        cases = [("peer", 1, 1, "fp32", 0), ("gather", 1, 1, "fp32", 0), ("halo", 1, 1, "fp32", 0), ("peer", 2, 1, "fp32", 0),
+                 ("peer", 1, 2, "fp32", 0), ("peer", 1, 1, "bf16", 0), ("auto", 1, 1, "fp32", None), ("push", 1, 1, "fp32", 0),
+                 ("push", 1, 1, "bf16", 0), ("peer", 1, 1, "fp32", 2), ("peer", 1, 1, "fp32", 10 ** 6),
+                 ("peer", 1, 1, "bf16", 2), ("peer", 1, 1, "fp32", 1)]
+        for schedule, slabs, passes, operand, direct in cases:
+            g = hd.ShardedGraph(d_rp, d_ci, schedule=schedule, n_slabs=slabs, n_passes=passes, operand=operand,
+                                direct_refs=direct)
+            if direct:
+                assert g.direct is not None and g.direct["T"] == direct, "segment mode was not set up"
+                schedule = f"{schedule}+inplace{direct}"
+            for dim in (128, 100, 64) + ((320,) if direct else ()):
                 x = np.random.default_rng(dim).standard_normal((n, dim)).astype(np.float32)
                 want = oracle.spmm(rp, ci, x, precision=1)[g.r0:g.r1]
                 want_ts = torch_sparse_ref(rp, ci, x)[g.r0:g.r1]

@@ -84,3 +84,74 @@ def test_halo_push_matches_indexing(dim, col0, width):
         rest[offs[s]: offs[s] + counts[s], col0:col0 + width] = -1.0
         assert bool((rest == -1.0).all())                        # nothing else was written
     assert bool((peers[1] == -1.0).all())
+
+
+@pytest.mark.parametrize("dim,bf16", [(128, False), (32, False), (256, False), (64, True), (128, True), (512, True)])
+@pytest.mark.parametrize("graph", ["rmat_hub_4096", "products_like"])
+def test_spmm_segments_matches_one_buffer(graph, dim, bf16):
+    """Segment mode of the balanced kernel (hcspmm_aux_t.d_colidx_segments) on ONE device: the rows of X are dealt to
+    eight buffers (stand-ins for the local operand and seven peers' operands, different sizes, rows offset inside
+    them), column ids are tagged with the buffer of their row -- the result equals the plain aggregation of the same
+    X bit for bit (same loads, same sum order) in FP32 and in BF16-stored mode."""
+    import numpy as np
+    import HCSPMM
+    from helpers import small_graphs
+    from hcspmm import graphs
+    dev = torch.device("cuda", 0)
+    if graph == "products_like":
+        rp, ci = graphs.rmat(40_000, 1_000_000, seed=11)
+        rp, ci = rp.numpy(), ci.numpy()
+    else:
+        rp, ci = small_graphs()[graph]
+    n = rp.size - 1
+    d_rp, d_ci = torch.from_numpy(rp).to(dev), torch.from_numpy(ci).to(dev)
+    g = torch.Generator(device=dev).manual_seed(dim)
+    x = torch.randn(n, dim, device=dev, generator=g)
+    HCSPMM.set_classifier("shipped")
+    pre = HCSPMM.preprocess(d_ci, d_rp, n, d_ci.numel(), (n + 15) // 16)
+    xs = x.to(torch.bfloat16) if bf16 else x
+    want = torch.empty(n, dim, device=dev)
+    if bf16:
+        HCSPMM.spmm_bf16(xs, d_rp, d_ci, *pre[:4], want, False, *pre[4:6])
+    else:
+        want = HCSPMM.forward(x, d_rp, d_ci, *pre)[0]
+    # deal the rows: segment of row r, and its position inside that segment's buffer (after `lead` foreign rows)
+    seg_of = torch.randint(0, 8, (n,), device=dev, generator=g)
+    seg_of[: n // 2] = 0                                   # half of X stays local, like a real operand
+    leads = [0, 5, 0, 17, 3, 0, 9, 1]
+    bufs, row_in = [], torch.empty(n, dtype=torch.int64, device=dev)
+    for s_ in range(8):
+        idx = torch.nonzero(seg_of == s_).flatten()
+        b = torch.full((leads[s_] + idx.numel() + 2, dim), float("nan"), device=dev).to(xs.dtype)
+        b[leads[s_]: leads[s_] + idx.numel()] = xs[idx]
+        row_in[idx] = leads[s_] + torch.arange(idx.numel(), device=dev)
+        bufs.append(b)
+    c64 = d_ci.long()
+    v = (seg_of[c64] << 29) | row_in[c64]
+    tagged = torch.where(v >= 2 ** 31, v - 2 ** 32, v).to(torch.int32).contiguous()
+    x_rows = max(b.shape[0] for b in bufs)
+    out = torch.empty(n, dim, device=dev)
+    step = 256
+    for c0 in range(0, dim, step):
+        segs = [0] + [b.data_ptr() + c0 * b.element_size() for b in bufs[1:]]
+        HCSPMM.spmm_segments(bufs[0][:, c0:c0 + step], d_rp, tagged, segs, x_rows, out[:, c0:c0 + step], False, pre[4], pre[5])
+    torch.cuda.synchronize()
+    assert torch.equal(out, want)
+    assert not bool(torch.isnan(out).any())
+
+
+def test_spmm_segments_rejects_tensor_core_graphs():
+    import HCSPMM
+    from helpers import small_graphs
+    dev = torch.device("cuda", 0)
+    rp, ci = small_graphs()["rmat_hub_4096"]
+    n = rp.size - 1
+    d_rp, d_ci = torch.from_numpy(rp).to(dev), torch.from_numpy(ci).to(dev)
+    HCSPMM.set_classifier("all_tc")
+    try:
+        pre = HCSPMM.preprocess(d_ci, d_rp, n, d_ci.numel(), (n + 15) // 16)
+    finally:
+        HCSPMM.set_classifier("shipped")
+    x = torch.randn(n, 64, device=dev)
+    with pytest.raises(RuntimeError, match="segment"):
+        HCSPMM.spmm_segments(x, d_rp, d_ci, [0] * 8, n, torch.empty(n, 64, device=dev), False, pre[4], pre[5])

@@ -135,3 +135,52 @@ def test_halo_exchange_world3(tmp_path):
     """Three ranks: halo rows arrive from owners on both sides of the own block."""
     mp.spawn(_worker, args=(3, 29500 + (os.getpid() % 500) + 41, "rmat_1000", str(tmp_path), "halo"), nprocs=3, join=True)
     assert all((tmp_path / f"ok{r}").exists() for r in range(3))
+
+
+@pytest.mark.parametrize("name,world,max_refs", [("rmat_hub_4096", 2, 2), ("rmat_hub_4096", 8, 1), ("rmat_1000", 3, 2),
+                                                 ("holes_777", 4, 10 ** 6), ("sbm_1024", 5, 0)])
+def test_segment_tags_address_the_right_rows(name, world, max_refs):
+    """Segment mode of the peer exchange (hcspmm.partition.pulled_layout / tag_segments): every rank's operand keeps its
+    own rows and the remote rows it references more than max_refs times; every entry's tagged id must lead -- through
+    the operand layout of the rank that bits 29..31 name -- back to the entry's global column id, and the aggregation
+    computed through the tags must equal the oracle's."""
+    rp, ci = small_graphs()[name]
+    n = rp.size - 1
+    rp_t, ci_t = _t(rp), _t(ci)
+    cuts = partition.window_cuts(rp_t, world)
+    bounds = torch.tensor(cuts, dtype=torch.int64)
+    shards, layouts, firsts = [], [], []
+    for r in range(world):
+        rp_l, ci_l = partition.local_shard(rp_t, ci_t, cuts[r], cuts[r + 1])
+        ids, (cold, refs) = partition.pulled_layout(ci_l.to(torch.int64), bounds, r, max_refs)
+        assert bool((refs <= max_refs).all())
+        own = torch.bucketize(ids, bounds[1:-1], right=True)
+        firsts.append(int((own < r).sum()))
+        assert torch.equal(ids[firsts[r]: firsts[r] + cuts[r + 1] - cuts[r]], torch.arange(cuts[r], cuts[r + 1]))
+        shards.append((rp_l, ci_l))
+        layouts.append(ids)
+    x = np.random.default_rng(3).standard_normal((n, 8)).astype(np.float32)
+    want = oracle.spmm(rp, ci, x, precision=1)
+    for r in range(world):
+        rp_l, ci_l = shards[r]
+        tags = partition.tag_segments(ci_l.to(torch.int64), layouts[r], bounds, r, world, firsts).to(torch.int64) & 0xffffffff
+        seg, row = tags >> partition.SEG_SHIFT, tags & partition.SEG_MASK
+        gid = torch.empty_like(row)
+        for s_ in range(world):
+            m = seg == s_
+            gid[m] = layouts[(r + s_) % world][row[m]]
+        assert torch.equal(gid, ci_l.to(torch.int64))
+        if max_refs == 0:
+            assert bool((seg == 0).all())
+        # remote rows that stay at their owner are exactly the rarely referenced ones
+        remote = (ci_l < cuts[r]) | (ci_l >= cuts[r + 1])
+        u, c = torch.unique(ci_l[remote].to(torch.int64), return_counts=True)
+        far_ids = torch.unique(ci_l.to(torch.int64)[seg != 0])
+        assert torch.equal(far_ids, u[c <= max_refs])
+        # the aggregation through the tags: operand of every rank = its layout's rows of X
+        ops = [x[l.numpy()] for l in layouts]
+        y = np.zeros((cuts[r + 1] - cuts[r], 8), np.float32)
+        rows = np.repeat(np.arange(rp_l.numel() - 1), np.diff(rp_l.numpy()))
+        vals = np.stack([ops[(r + int(s_)) % world][int(w_)] for s_, w_ in zip(seg.tolist(), row.tolist())]) if row.numel() else np.zeros((0, 8), np.float32)
+        np.add.at(y, rows, vals)
+        assert rel_fro(y, want[cuts[r]:cuts[r + 1]]) <= 1e-5
