@@ -505,9 +505,15 @@ class ShardedGraph:
         cur, comm = torch.cuda.current_stream(dev), self._hi_stream
         comm.wait_stream(cur)
         events = []
+        from . import capi
         with torch.cuda.stream(comm):
             for k in range(len(edges) - 1):
+                # slab 0 has nothing to hide behind: full grid.  Later slabs travel while the SpMM of the previous slab
+                # runs: NVLink-bound, a few CTAs keep the links busy and leave the SMs to the SpMM
+                old = capi.set_tuning("pull_ctas", self.overlap_ctas) if k > 0 else None
                 self._pull_halo(cat, dpad, edges[k], edges[k + 1] - edges[k])
+                if old is not None:
+                    capi.set_tuning("pull_ctas", old)
                 ev = torch.cuda.Event()
                 ev.record(comm)
                 events.append(ev)

@@ -136,8 +136,11 @@ def test_spmm_segments_matches_one_buffer(graph, dim, bf16):
         segs = [0] + [b.data_ptr() + c0 * b.element_size() for b in bufs[1:]]
         HCSPMM.spmm_segments(bufs[0][:, c0:c0 + step], d_rp, tagged, segs, x_rows, out[:, c0:c0 + step], False, pre[4], pre[5])
     torch.cuda.synchronize()
-    assert torch.equal(out, want)
     assert not bool(torch.isnan(out).any())
+    if dim <= 256:
+        assert torch.equal(out, want)
+    else:       # column blocks of 256 use another item size than one 512-wide launch: same sums, other piece order
+        assert float((out - want).norm() / want.norm()) <= 1e-6
 
 
 def test_spmm_segments_rejects_tensor_core_graphs():
