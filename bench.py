@@ -65,9 +65,12 @@ def parse():
     ap.add_argument("--stage-copy", action="store_true",
                     help="N > 1: keep the rank's X shard in ordinary memory and copy it into the exchange operand every step "
                          "(default: X lives in the operand's own-rows segment)")
-    ap.add_argument("--direct-refs", type=int, default=None,
+    ap.add_argument("--direct-refs", type=int, default=0,
                     help="peer exchange: remote rows of X referenced at most this many times by a shard are read in place by "
-                         "the SpMM instead of being pulled (0 = off; default: auto, 2 on low-reuse halos)")
+                         "the SpMM instead of being pulled (0 = off, default; -1 = auto)")
+    ap.add_argument("--row-blocks", type=int, default=0,
+                    help="peer exchange: row-block pipeline -- the halo travels in the order the shard's row blocks need it, "
+                         "block b's SpMM starts when its part has landed (1 = off; 0 = auto, default: 8 blocks on low-degree graphs)")
     ap.add_argument("--exchange-slabs", type=int, default=1,
                     help="N > 1: all-gather X in this many feature slabs, slab k+1 in flight while the SpMM of slab k runs "
                          "(1 = one all-gather, then one SpMM)")
@@ -360,7 +363,8 @@ def run_workload(ctx, shape_name, dim, steps, warmup, classifier, dense, precisi
     HCSPMM.set_precision(precision)
     operand = "bf16" if (precision == "bf16" and world > 1) else "fp32"
     sg = hd.ShardedGraph(rp, ci, schedule=args.exchange, n_slabs=max(1, args.exchange_slabs), n_passes=args.exchange_passes,
-                         operand=operand, direct_refs=args.direct_refs)
+                         operand=operand, direct_refs=None if args.direct_refs < 0 else args.direct_refs,
+                         row_blocks=None if args.row_blocks <= 0 else args.row_blocks)
     sg.overlap_ctas = args.overlap_ctas
     r0, r1 = sg.r0, sg.r1
     rp_l, ci_run = sg.rowptr, sg.colidx
@@ -455,6 +459,11 @@ def run_workload(ctx, shape_name, dim, steps, warmup, classifier, dense, precisi
                   "exchange_rows_vs_allgather": sg.exchange_rows() / max(1, (world - 1) * sg.max_rows)}
         if phases["exchange_only_ms"] > 0:
             phases["exchange_gbs_per_rank"] = phases["exchange_bytes_per_rank"] / phases["exchange_only_ms"] / 1e6
+        if sg.blocks is not None:
+            phases["row_blocks"] = {"blocks": sg.blocks["B"], "halo_fraction_first_block": round(sg.blocks["first_fraction"], 4),
+                                    "halo_rows_per_block": [b_["rows"] for b_ in sg.blocks["list"]],
+                                    "note": "kernel_only_ms = the blocks' SpMMs back to back on one stream; in a step they run on "
+                                            "their own streams behind the pull of their part of the halo"}
         if sg.direct is not None:
             # segment mode: rows referenced <= T times are read in place by the SpMM (inside kernel_only_ms); only the
             # pulled rows travel in exchange_only_ms
@@ -514,6 +523,9 @@ def run_workload(ctx, shape_name, dim, steps, warmup, classifier, dense, precisi
     launches_per_step = spmm_launches * n_slabs + (1 if (precision == "bf16" and (world == 1 or dim % 8)) else 0) * n_slabs
     if world > 1 and sg.schedule in ("peer", "push"):
         launches_per_step += 1 + n_slabs + (1 if operand == "bf16" and dim % 8 == 0 else 0)   # barrier + pull(s) / push (+ f32->bf16 of own rows)
+    if world > 1 and sg.blocks is not None:     # row-block pipeline: per block one pull (if it brings rows) + the SpMM launches
+        launches_per_step = 1 + (1 if operand == "bf16" and dim % 8 == 0 else 0) + sum(
+            (1 if b_["rows"] > 0 else 0) + spmm_launches for b_ in sg.blocks["list"])
 
     # ---- roofline of the dominant kernel (the SpMM launch of a step) ------------------------------------------------
     esz_x = 2 if precision == "bf16" else 4

@@ -41,9 +41,10 @@ def main():
     ap.add_argument("--dense", action="store_true", help="tcgen05 dense super-window plans")
     ap.add_argument("--profile", action="store_true", help="print the CUDA-time breakdown of one epoch (torch.profiler)")
     ap.add_argument("--operand", default="fp32", choices=["fp32", "bf16"], help="N > 1: exchange operand storage")
-    ap.add_argument("--direct-refs", type=int, default=None,
+    ap.add_argument("--direct-refs", type=int, default=0,
                     help="N > 1, peer exchange: remote rows referenced at most this many times are read in place by the SpMM "
-                         "(0 = off, default auto)")
+                         "(0 = off, default; -1 = auto)")
+    ap.add_argument("--row-blocks", type=int, default=0, help="N > 1, peer exchange: row-block pipeline (1 = off, 0 = auto)")
     ap.add_argument("--fp32-matmul", action="store_true",
                     help="Update GEMMs (torch.mm) in full FP32; default TF32 like the reference's stack "
                          "(PyTorch 1.8: allow_tf32 on by default; its fused kernels use wmma TF32, :1809-1837)")
@@ -62,7 +63,8 @@ def main():
     HCSPMM.set_classifier(args.classifier)
     rp, ci, info = graphs.named(args.shape, device=dev, scale=args.scale)
     g = hd.ShardedGraph(rp, ci, schedule=args.schedule, n_slabs=args.slabs, operand=args.operand,
-                        direct_refs=args.direct_refs)
+                        direct_refs=None if args.direct_refs < 0 else args.direct_refs,
+                        row_blocks=None if args.row_blocks <= 0 else args.row_blocks)
     # the SAME problem at every N: global features / labels from one seed, then this rank's rows
     # (A is binary and unnormalised like the reference's; features are scaled so the logits start O(1))
     gen = torch.Generator(device=dev).manual_seed(100)
@@ -166,6 +168,7 @@ def main():
                                      "classes": args.classes, "schedule": g.schedule, "slabs": g.n_slabs,
                                      "exchange_rows_vs_allgather": (g.exchange_rows() / max(1, (world - 1) * g.max_rows)) if world > 1 else None,
                                      "classifier": args.classifier, "operand": args.operand,
+                                     "row_blocks": None if g.blocks is None else {"blocks": g.blocks["B"], "halo_fraction_first_block": g.blocks["first_fraction"]},
                                      "in_place": None if g.direct is None else {k_: g.direct[k_] for k_ in ("T", "rows", "refs", "pulled_rows", "halo_rows")},
                                      "update_gemm": "HCSPMM.gemm_tf32 (cvt.rna TF32, FP32 accumulate); weight gradients torch.mm " +
                                                     ("fp32" if args.fp32_matmul else "tf32")},

@@ -61,7 +61,8 @@ constexpr int PULL_ROWS = 8;   // rows in flight per warp
 __global__ void __launch_bounds__(256) halo_pull_kernel(const float *const *__restrict__ peer_x, long long lds,
                                                         const int *__restrict__ src_row, const int *__restrict__ seg,
                                                         int world, unsigned long long owner_mask, int first, int c0,
-                                                        int width, float *__restrict__ dst, long long ldd) {
+                                                        int width, float *__restrict__ dst, long long ldd,
+                                                        const int *__restrict__ dst_row) {
   __shared__ int s_seg[65];
   __shared__ const float *s_base[64];
   __shared__ int s_list[64];
@@ -96,13 +97,20 @@ __global__ void __launch_bounds__(256) halo_pull_kernel(const float *const *__re
     const float *src[PULL_ROWS];
 #pragma unroll
     for (int j = 0; j < PULL_ROWS; ++j) src[j] = base + (long long)__ldg(src_row + min(r0 + j, r1 - 1)) * lds;
+    // list entry i lands in operand row i, or (row-block pipeline: the list is a SUBSET of the halo) in dst_row[i]
+    float *drow[PULL_ROWS];
+#pragma unroll
+    for (int j = 0; j < PULL_ROWS; ++j) {
+      const int i = min(r0 + j, r1 - 1);
+      drow[j] = dst + (long long)(dst_row ? __ldg(dst_row + i) : i) * ldd + c0;
+    }
     for (int v = lane; v < nvec; v += 32) {
       float4 x[PULL_ROWS];
 #pragma unroll
       for (int j = 0; j < PULL_ROWS; ++j) x[j] = *reinterpret_cast<const float4 *>(src[j] + v * 4);
 #pragma unroll
       for (int j = 0; j < PULL_ROWS; ++j)
-        if (r0 + j < r1) *reinterpret_cast<float4 *>(dst + (long long)(r0 + j) * ldd + c0 + v * 4) = x[j];
+        if (r0 + j < r1) *reinterpret_cast<float4 *>(drow[j] + v * 4) = x[j];
     }
   }
 }
@@ -225,6 +233,13 @@ int hcspmm_peer_barrier(int32_t *const *d_flag_ptrs, int32_t rank, int32_t world
 int hcspmm_halo_pull(const float *const *d_peer_x, int64_t lds, const int32_t *d_src_row, const int32_t *d_seg,
                      int32_t world, uint64_t owner_mask, int32_t first_owner, int32_t rows, int32_t col0, int32_t width,
                      float *d_dst, int64_t ldd, void *stream) {
+  return hcspmm_halo_pull_rows(d_peer_x, lds, d_src_row, nullptr, d_seg, world, owner_mask, first_owner, rows, col0, width,
+                               d_dst, ldd, stream);
+}
+
+int hcspmm_halo_pull_rows(const float *const *d_peer_x, int64_t lds, const int32_t *d_src_row, const int32_t *d_dst_row,
+                          const int32_t *d_seg, int32_t world, uint64_t owner_mask, int32_t first_owner, int32_t rows,
+                          int32_t col0, int32_t width, float *d_dst, int64_t ldd, void *stream) {
   if (rows <= 0 || width == 0 || owner_mask == 0) return 0;
   if (!d_peer_x || !d_src_row || !d_seg || !d_dst || world < 1 || world > 64 || width < 0 || col0 < 0 ||
       first_owner < 0) {
@@ -240,7 +255,7 @@ int hcspmm_halo_pull(const float *const *d_peer_x, int64_t lds, const int32_t *d
   const long long cap = tuning().pull_ctas > 0 ? tuning().pull_ctas : 148 * 8;
   if (grid > cap) grid = cap;
   halo_pull_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(d_peer_x, lds, d_src_row, d_seg, world, owner_mask,
-                                                                     first_owner % world, col0, width, d_dst, ldd);
+                                                                     first_owner % world, col0, width, d_dst, ldd, d_dst_row);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("halo_pull: %s", cudaGetErrorString(e)); return (int)e; }
   return 0;

@@ -1181,6 +1181,13 @@ static cudaError_t run_balanced(const SpmmParams &p, long long nnz, bool v8, boo
   if (chunk < 64) chunk = 64;
   if (chunk > 16384) chunk = 16384;
   const long long total = (long long)p.n_rows + nnz;
+  // Items are equal pieces of work and one CTA takes one item, so a launch runs in whole "rounds" of the resident CTA
+  // slots (148 SMs x 2 or 3): a 1/8 shard of the products shape is 980 items of 8192 steps on 444 slots = 2.2 rounds
+  // paid as 3.  Small operands therefore take the smaller item size (the split points serve both), knob "chunk" unset.
+  if (tuning().chunk <= 0 && chunk > 4096) {
+    const long long slots = 148LL * ((nnz < 64LL * p.n_rows && tuning().occupancy3) ? 3 : 2);
+    if (total / chunk < 6 * slots) chunk = 4096;
+  }
   const long long n_items = total > 0 ? (total + chunk - 1) / chunk : 1;
   if (n_items > 0x7fffffffLL / 2) return cudaErrorInvalidValue;
   bp.chunk = chunk;

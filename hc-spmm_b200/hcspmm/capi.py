@@ -24,7 +24,7 @@ EXPORTS = [
     "hcspmm_dense_plan_fill", "hcspmm_spmm_plan", "hcspmm_debug_umma_error", "hcspmm_loa_workspace_bytes", "hcspmm_loa_reorder", "hcspmm_graph_create", "hcspmm_graph_spmm_host",
     "hcspmm_graph_get_preprocess", "hcspmm_graph_destroy",
     "hcspmm_peer_alloc", "hcspmm_peer_open", "hcspmm_peer_close", "hcspmm_peer_free", "hcspmm_peer_barrier",
-    "hcspmm_halo_pull", "hcspmm_debug_l2_gather",
+    "hcspmm_halo_pull", "hcspmm_halo_pull_rows", "hcspmm_debug_l2_gather",
     "hcspmm_merge_path_count", "hcspmm_merge_path_splits", "hcspmm_spmm_workspace_bytes", "hcspmm_spmm_aux",
     "hcspmm_f32_to_bf16", "hcspmm_spmm_gemm_aux", "hcspmm_halo_push",
     "hcspmm_tag_columns_workspace_bytes", "hcspmm_tag_columns",
@@ -88,6 +88,7 @@ def lib() -> ctypes.CDLL:
         L.hcspmm_peer_free.argtypes = [_vp]
         L.hcspmm_peer_barrier.argtypes = [_vp, _i32, _i32, _i32, _vp, _vp]
         L.hcspmm_halo_pull.argtypes = [_vp, _i64, _vp, _vp, _i32, ctypes.c_uint64, _i32, _i32, _i32, _i32, _vp, _i64, _vp]
+        L.hcspmm_halo_pull_rows.argtypes = [_vp, _i64, _vp, _vp, _vp, _i32, ctypes.c_uint64, _i32, _i32, _i32, _i32, _vp, _i64, _vp]
         L.hcspmm_debug_l2_gather.argtypes = [_vp, _i32, _i32, _i32, _i32, _vp, _vp]
         L.hcspmm_merge_path_count.restype = _sz
         L.hcspmm_merge_path_count.argtypes = [_i32, _i64, _i32]

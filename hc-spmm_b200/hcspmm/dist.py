@@ -71,7 +71,8 @@ def _default_spmm():
 class ShardedGraph:
     def __init__(self, rowptr: torch.Tensor, colidx: torch.Tensor, group=None, schedule: str = "gather",
                  n_slabs: int = 1, spmm=None, preprocess=None, cuts=None, n_passes: int = 1,
-                 operand: str = "fp32", single: bool = False, direct_refs: int | None = None):
+                 operand: str = "fp32", single: bool = False, direct_refs: int | None = 0,
+                 row_blocks: int | None = None):
         """rowptr / colidx: the FULL graph's CSR on this rank's device (identical on every rank).
         cuts: reuse another ShardedGraph's row cuts (the transposed graph for backward must be
         partitioned like the forward one).
@@ -85,9 +86,16 @@ class ShardedGraph:
         direct_refs = T ("peer" schedule): remote rows of X that this shard references at most T times are NOT pulled
         into the local operand; the SpMM's gather reads them in place from their owner's peer-mapped operand
         (segment-tagged column ids, HCSPMM.spmm_segments) -- on a power-law graph 40 % of a 1/8 shard's halo rows
-        are referenced exactly once (4.5 % of its remote references), so the pull shrinks by that much, those rows
-        are neither written to nor re-read from local memory, and their transfer overlaps the sums.  None = auto
-        (2 when at least a quarter of the halo rows qualify and the shard is all CUDA-core), 0 = off."""
+        are referenced exactly once (4.5 % of its remote references), so the pull shrinks by that much and those
+        rows are neither written to nor re-read from local memory.  Measured (profiles/README.md): the in-order
+        gather ring stalls on the NVLink latency of those loads, so the SpMM loses about what the pull saves -- T = 1
+        gains 7 % on the products shape at 8 GPUs, larger T and denser graphs lose.  0 (default) = off; None = 2 when at
+        least a quarter of the halo rows qualify and the shard is all CUDA-core.
+        row_blocks = B ("peer" schedule): the ROW-BLOCK PIPELINE.  The shard's rows are cut into B blocks of equal stored
+        entries and the halo is pulled in the order the blocks need it: block b's SpMM (own stream) starts as soon as
+        the rows first referenced by blocks <= b have landed, while the rest still travels on few CTAs -- on low-degree
+        graphs the first of 8 blocks needs only a third of the halo.  None = auto (8 when the first block needs <= 0.7
+        of the halo, else off), 1 = off."""
         assert operand in ("fp32", "bf16")
         self.operand = operand
         self.group = group
@@ -150,6 +158,10 @@ class ShardedGraph:
                 and self.world <= 8 and n_passes == 1 and self.n_slabs == 1):
             self._setup_direct(ci64, bounds, direct_refs)
         del ci64
+        self.blocks = None
+        if (native and self.peer is not None and not self.push and self.halo is not None and row_blocks != 1
+                and n_passes == 1 and self.n_slabs == 1):
+            self._setup_row_blocks(row_blocks, preprocess)
         self.passes = None
         self.overlap_ctas = 64
         if self.peer is not None and n_passes == 2 and self.world > 2:
@@ -226,6 +238,44 @@ class ShardedGraph:
                          src_row=(ids - bounds[own_ids]).to(torch.int32).contiguous(), seg=seg)
         self.direct = dict(T=T, rows=int(cold.sum()), refs=int(refs[cold].sum()), pulled_rows=self.halo["rows"] - self.n_local,
                            halo_rows=pulled_before, x_rows=max(rows_all), firsts=firsts)
+
+    def _setup_row_blocks(self, row_blocks, preprocess):
+        """Row-block pipeline (see __init__, row_blocks): per block its rebased CSR + preprocessing products, and the
+        part of the halo it is the first to reference, as a pull list with explicit destination rows."""
+        B = 8 if row_blocks is None else int(row_blocks)
+        hdr = self.pre[4] if len(self.pre) >= 6 and self.pre[4].device.type == "cpu" else None
+        all_cuda = hdr is not None and int(hdr[1]) == 0 and int(hdr[7]) == 0        # no dense plan, no label-1 windows
+        if B < 2 or not all_cuda or self.n_local < 16 * B or self.nnz_local < 64 * B:
+            return
+        h = self.halo
+        col = self.colidx_seg if self.direct is not None else self.colidx        # tagged ids: only segment 0 is local
+        cuts, first = partition.row_block_order(self.rowptr, col, h["rows"], B)
+        own0 = int(h["seg"][self.rank])
+        first[own0: own0 + self.n_local] = B + 1                                  # own rows are in place already
+        n_halo = h["rows"] - self.n_local
+        f1 = float((first == 0).sum()) / max(1, n_halo)
+        if row_blocks is None and f1 > 0.7:
+            return
+        dev = col.device
+        rp64 = self.rowptr.to(torch.int64)
+        seg64 = h["seg"].to(torch.int64)
+        blocks = []
+        for b in range(B):
+            c0, c1 = cuts[b], cuts[b + 1]
+            if c1 <= c0:
+                continue
+            e0, e1 = int(rp64[c0]), int(rp64[c1])
+            rp_b = (rp64[c0:c1 + 1] - e0).to(torch.int32).contiguous()
+            ci_b = self.colidx[e0:e1].clone()
+            blk = dict(r0=c0, r1=c1, rowptr=rp_b, colidx=ci_b, pre=preprocess(ci_b, rp_b),
+                       colidx_seg=self.colidx_seg[e0:e1].clone() if self.direct is not None else None)
+            dst = torch.nonzero(first == b).flatten()                             # ascending operand rows = owner order
+            seg_b = torch.searchsorted(dst, seg64).to(torch.int32).contiguous()   # entries of owner o: [seg_b[o], seg_b[o+1])
+            blk.update(dst_row=dst.to(torch.int32).contiguous(), src_row=h["src_row"][dst].contiguous(), seg=seg_b,
+                       rows=int(dst.numel()))
+            blocks.append(blk)
+        self.blocks = dict(B=len(blocks), list=blocks, first_fraction=f1,
+                           streams=[torch.cuda.Stream(device=dev) for _ in blocks])
 
     # ------------------------------------------------------------------------------------------
     def shard_rows(self, x_full: torch.Tensor) -> torch.Tensor:
@@ -460,8 +510,62 @@ class ShardedGraph:
                                  False, self.pre[4], self.pre[5])
         return y
 
+    def _spmm_block(self, blk, cat: torch.Tensor, y: torch.Tensor):
+        """Rows [r0, r1) of the shard on the operand `cat` -> y[r0:r1]."""
+        out = y[blk["r0"]:blk["r1"]]
+        if self.direct is None:
+            self._spmm(cat, blk["rowptr"], blk["colidx"], blk["pre"], out=out)
+            return
+        import HCSPMM
+        esz = cat.element_size()
+        for c0 in range(0, cat.shape[1], 256):
+            c1 = min(cat.shape[1], c0 + 256)
+            segs = [0] + [p_ + c0 * esz for p_ in self._peer_segs[1:]]
+            HCSPMM.spmm_segments(cat[:, c0:c1], blk["rowptr"], blk["colidx_seg"], segs, self.direct["x_rows"], out[:, c0:c1],
+                                 False, blk["pre"][4], blk["pre"][5])
+
+    def _aggregate_row_blocks(self, cat: torch.Tensor, dpad: int, dim: int) -> torch.Tensor:
+        """The row-block pipeline: the halo travels in the order the row blocks need it (communication stream; the
+        first part on the full grid, the later parts on few CTAs because they share the SMs with the SpMMs), block b's
+        SpMM starts on its own stream when its part has landed.  The blocks write disjoint rows of Y."""
+        from . import capi
+        dev = cat.device
+        cur, comm = torch.cuda.current_stream(dev), self._hi_stream
+        y = torch.empty(self.n_local, dpad, device=dev)
+        staged = torch.cuda.Event()
+        staged.record(cur)                                   # own rows written, barrier passed (and y allocated)
+        raw = cat.view(torch.float32) if cat.dtype == torch.bfloat16 else cat
+        lds = raw.shape[1]
+        landed = []
+        with torch.cuda.stream(comm):
+            comm.wait_event(staged)
+            for b, blk in enumerate(self.blocks["list"]):
+                if blk["rows"] > 0:
+                    old = capi.set_tuning("pull_ctas", self.overlap_ctas) if b > 0 else None
+                    mask = ((1 << self.world) - 1) & ~(1 << self.rank)
+                    self._pull(self._peer_tab, lds, blk["src_row"], blk["seg"], self.world, raw, 0, lds, mask, self.rank + 1,
+                               dst_row=blk["dst_row"])
+                    if old is not None:
+                        capi.set_tuning("pull_ctas", old)
+                ev = torch.cuda.Event()
+                ev.record(comm)
+                landed.append(ev)
+        for blk, ev, st in zip(self.blocks["list"], landed, self.blocks["streams"]):
+            with torch.cuda.stream(st):
+                st.wait_event(staged)
+                st.wait_event(ev)
+                self._spmm_block(blk, cat, y)
+            cur.wait_stream(st)
+        y.record_stream(cur)
+        return y if dpad == dim else y[:, :dim]
+
     def local_spmm(self, operand: torch.Tensor) -> torch.Tensor:
         """The compute step alone, on the operand the latest `exchange` returned (phase timing)."""
+        if self.blocks is not None:                         # the blocks back to back on the current stream
+            y = torch.empty(self.n_local, operand.shape[1], device=operand.device)
+            for blk in self.blocks["list"]:
+                self._spmm_block(blk, operand, y)
+            return y
         if self.direct is not None:
             return self._spmm_segments(operand)
         return self._spmm(operand, self.rowptr, self.colidx, self.pre)
@@ -489,6 +593,8 @@ class ShardedGraph:
             cur.wait_event(ev1)
             self._spmm(cat, p1["rowptr"], p1["colidx"], p1["pre"], out=y, accumulate=True)
             return y if dpad == dim else y[:, :dim]
+        if self.blocks is not None:
+            return self._aggregate_row_blocks(cat, dpad, dim)
         if self.direct is not None:
             # pulled rows first (they are gathered many times), then ONE kernel that sums local operand rows and rows
             # read in place from the peers' operands over NVLink

@@ -95,3 +95,24 @@ def tag_segments(colidx64: torch.Tensor, ids: torch.Tensor, bounds: torch.Tensor
     far = (((owner - rank) % world) << SEG_SHIFT) | row
     v = torch.where(local, pos, far)
     return torch.where(v >= 2 ** 31, v - 2 ** 32, v).to(torch.int32).contiguous()
+
+
+def row_block_order(rowptr: torch.Tensor, colidx_local: torch.Tensor, n_operand_rows: int, n_blocks: int):
+    """Row-block pipeline of the peer exchange: cut a shard's rows into n_blocks contiguous blocks of about equal
+    stored entries (16-row aligned) and find, for every row of the exchange operand, the FIRST block that references
+    it.  colidx_local: operand row of every entry, or a negative / out-of-range value for entries that do not read the
+    local operand (rows read in place from a peer).  -> (cuts: n_blocks + 1 row offsets, first: int64[n_operand_rows],
+    n_blocks where a row is never referenced).  Block b's SpMM can start once the operand rows with first <= b are in
+    place."""
+    n = rowptr.numel() - 1
+    cuts = window_cuts(rowptr, n_blocks)
+    dev = colidx_local.device
+    rp = rowptr.to(torch.int64)
+    ent_cuts = rp[torch.tensor(cuts, device=rp.device)]
+    pos = torch.arange(colidx_local.numel(), device=dev, dtype=torch.int64)
+    blk = torch.bucketize(pos, ent_cuts[1:-1].to(dev), right=True)               # block of every entry
+    c = colidx_local.to(torch.int64)
+    ok = (c >= 0) & (c < n_operand_rows)
+    first = torch.full((n_operand_rows,), n_blocks, dtype=torch.int64, device=dev)
+    first.scatter_reduce_(0, c[ok], blk[ok], reduce="amin", include_self=True)
+    return cuts, first

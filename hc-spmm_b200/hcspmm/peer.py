@@ -106,16 +106,19 @@ class PeerMemory:
 
 def halo_pull(peer_table: torch.Tensor, lds: int, src_row: torch.Tensor, seg: torch.Tensor, world: int,
               dst: torch.Tensor, col0: int = 0, width: int | None = None, owner_mask: int | None = None,
-              first_owner: int = 0):
-    """hcspmm_halo_pull on the current stream: dst[i, col0:col0+width] <- owner's row src_row[i] for the rows of
-    the owners in owner_mask (default: all), round-robin from first_owner."""
+              first_owner: int = 0, dst_row: torch.Tensor | None = None):
+    """hcspmm_halo_pull(_rows) on the current stream: dst[i, col0:col0+width] <- owner's row src_row[i] for the rows of
+    the owners in owner_mask (default: all), round-robin from first_owner.  dst_row: list entry i lands in
+    dst[dst_row[i]] instead (a subset of the halo: the row-block pipeline)."""
     width = dst.shape[1] - col0 if width is None else width
     owner_mask = (1 << world) - 1 if owner_mask is None else owner_mask
+    rows = dst.shape[0] if dst_row is None else int(src_row.numel())
     with torch.cuda.device(dst.device):
-        capi._check(capi.lib().hcspmm_halo_pull(peer_table.data_ptr(), lds, src_row.data_ptr(), seg.data_ptr(), world,
-                                                owner_mask, first_owner, dst.shape[0], col0, width, dst.data_ptr(),
-                                                dst.stride(0), torch.cuda.current_stream(dst.device).cuda_stream),
-                    "hcspmm_halo_pull")
+        capi._check(capi.lib().hcspmm_halo_pull_rows(peer_table.data_ptr(), lds, src_row.data_ptr(),
+                                                     None if dst_row is None else dst_row.data_ptr(), seg.data_ptr(), world,
+                                                     owner_mask, first_owner, rows, col0, width, dst.data_ptr(),
+                                                     dst.stride(0), torch.cuda.current_stream(dst.device).cuda_stream),
+                    "hcspmm_halo_pull_rows")
     return dst
 
 

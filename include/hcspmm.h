@@ -327,6 +327,13 @@ int hcspmm_peer_barrier(int32_t *const *d_flag_ptrs, int32_t rank, int32_t world
 int hcspmm_halo_pull(const float *const *d_peer_x, int64_t lds, const int32_t *d_src_row, const int32_t *d_seg,
                      int32_t world, uint64_t owner_mask, int32_t first_owner, int32_t rows, int32_t col0, int32_t width,
                      float *d_dst, int64_t ldd, void *stream);
+/* hcspmm_halo_pull for a SUBSET of the halo: list entry i (owner o: i in [d_seg[o], d_seg[o+1])) is the owner's row
+ * d_src_row[i] and lands in operand row d_dst_row[i] (NULL: row i, i.e. hcspmm_halo_pull).  The row-block pipeline
+ * of the multi-GPU layer pulls the halo in the order the shard's row blocks need it, block b's SpMM starting as soon
+ * as its part has landed while the later parts still travel.                                  */
+int hcspmm_halo_pull_rows(const float *const *d_peer_x, int64_t lds, const int32_t *d_src_row, const int32_t *d_dst_row,
+                          const int32_t *d_seg, int32_t world, uint64_t owner_mask, int32_t first_owner, int32_t rows,
+                          int32_t col0, int32_t width, float *d_dst, int64_t ldd, void *stream);
 
 /* The same exchange as a PUSH by the owner: rows d_send_row[j], j in [d_send_seg[s], d_send_seg[s+1]), of d_src are
  * written to peer s's operand at d_dst_base[s] + (j - d_send_seg[s]) * ldd (d_dst_base[s] = peer s's mapped operand

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--refs", type=int, nargs="+", default=[0, 1, 2, 3, 4, 8])
     ap.add_argument("--operands", nargs="+", default=["fp32", "bf16"])
     ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--row-blocks", type=int, nargs="+", default=[1])
     args = ap.parse_args()
     rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lr)
@@ -54,8 +55,8 @@ def main():
         return round(float(t), 4)
 
     for operand in args.operands:
-        for T in args.refs:
-            sg = hd.ShardedGraph(rp, ci, schedule="peer", operand=operand, direct_refs=T)
+        for T, rb in [(T_, rb_) for T_ in args.refs for rb_ in args.row_blocks]:
+            sg = hd.ShardedGraph(rp, ci, schedule="peer", operand=operand, direct_refs=T, row_blocks=rb)
             x_loc = x_full[sg.r0:sg.r1].contiguous()
             xo = sg.own_rows(dim)
             if xo is not None:
@@ -74,7 +75,8 @@ def main():
             sg.check()
             d = sg.direct
             if rank == 0:
-                print(json.dumps({"shape": args.shape, "dim": dim, "n_gpus": world, "operand": operand, "max_refs": T,
+                print(json.dumps({"shape": args.shape, "dim": dim, "n_gpus": world, "operand": operand, "max_refs": T, "row_blocks": sg.blocks["B"] if sg.blocks else 1,
+                                  "halo_fraction_first_block": sg.blocks["first_fraction"] if sg.blocks else 1.0,
                                   "step_ms": step, "exchange_only_ms": ex, "spmm_only_ms": sp, "rel_fro_vs_single_gpu": float(err),
                                   "rows_pulled": (d["pulled_rows"] if d else sg.exchange_rows()),
                                   "rows_in_place": d["rows"] if d else 0, "references_in_place": d["refs"] if d else 0,

@@ -45,16 +45,23 @@ def _worker(rank, world, port, q):
         results = []
         # last field: direct_refs (segment mode: remote rows referenced <= T times are read in place by the SpMM;
         # 0 = every halo row is pulled, None = auto, 10**6 = nothing is pulled at all)
-        cases = [("peer", 1, 1, "fp32", 0), ("gather", 1, 1, "fp32", 0), ("halo", 1, 1, "fp32", 0), ("peer", 2, 1, "fp32", 0),
-                 ("peer", 1, 2, "fp32", 0), ("peer", 1, 1, "bf16", 0), ("auto", 1, 1, "fp32", None), ("push", 1, 1, "fp32", 0),
-                 ("push", 1, 1, "bf16", 0), ("peer", 1, 1, "fp32", 2), ("peer", 1, 1, "fp32", 10 ** 6),
-                 ("peer", 1, 1, "bf16", 2), ("peer", 1, 1, "fp32", 1)]
-        for schedule, slabs, passes, operand, direct in cases:
+        # rb = row_blocks (row-block pipeline: the halo travels in the order the shard's row blocks need it and every
+        # block's SpMM starts when its part has landed; 1 = off, None = auto)
+        cases = [("peer", 1, 1, "fp32", 0, 1), ("gather", 1, 1, "fp32", 0, 1), ("halo", 1, 1, "fp32", 0, 1),
+                 ("peer", 2, 1, "fp32", 0, 1), ("peer", 1, 2, "fp32", 0, 1), ("peer", 1, 1, "bf16", 0, 1),
+                 ("auto", 1, 1, "fp32", None, None), ("push", 1, 1, "fp32", 0, 1), ("push", 1, 1, "bf16", 0, 1),
+                 ("peer", 1, 1, "fp32", 2, 1), ("peer", 1, 1, "fp32", 10 ** 6, 1), ("peer", 1, 1, "bf16", 2, 1),
+                 ("peer", 1, 1, "fp32", 1, 1), ("peer", 1, 1, "fp32", 0, 4), ("peer", 1, 1, "bf16", 0, 2),
+                 ("peer", 1, 1, "fp32", 2, 3), ("peer", 1, 1, "fp32", 0, 8)]
+        for schedule, slabs, passes, operand, direct, rb in cases:
             g = hd.ShardedGraph(d_rp, d_ci, schedule=schedule, n_slabs=slabs, n_passes=passes, operand=operand,
-                                direct_refs=direct)
+                                direct_refs=direct, row_blocks=rb)
             if direct:
                 assert g.direct is not None and g.direct["T"] == direct, "segment mode was not set up"
                 schedule = f"{schedule}+inplace{direct}"
+            if rb is not None and rb > 1:
+                assert g.blocks is not None and g.blocks["B"] == rb, "row-block pipeline was not set up"
+                schedule = f"{schedule}+rowblocks{rb}"
             for dim in (128, 100, 64) + ((320,) if direct else ()):
                 x = np.random.default_rng(dim).standard_normal((n, dim)).astype(np.float32)
                 want = oracle.spmm(rp, ci, x, precision=1)[g.r0:g.r1]

@@ -34,6 +34,31 @@ def test_halo_pull_matches_indexing(dim, col0, width):
     assert bool((dst[:, untouched] == -1.0).all())
 
 
+def test_halo_pull_subset_with_destination_rows():
+    """hcspmm_halo_pull_rows: a subset of the halo (the part one row block needs first) lands in the operand rows the
+    list names; rows outside the list stay untouched."""
+    from hcspmm import peer
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(5)
+    dim = 128
+    owners = [torch.randn(n, dim, device=dev, generator=g) for n in (300, 40, 1000)]
+    counts = [123, 0, 777]                                                     # owner 1 is the caller: nothing pulled
+    src = [torch.sort(torch.randperm(o.shape[0], device=dev, generator=g)[:c]).values for o, c in zip(owners, counts)]
+    seg_all = [0, 123, 163, 940]                                               # operand: [owner 0 | 40 own rows | owner 2]
+    pos = torch.cat([torch.arange(0, 123, device=dev), torch.arange(163, 940, device=dev)])
+    src_all = torch.cat([src[0], src[2]])
+    pick = torch.sort(torch.randperm(900, device=dev, generator=g)[:300]).values     # this block's part of the halo
+    dst_row, src_row = pos[pick].to(torch.int32), src_all[pick].to(torch.int32)
+    seg = torch.searchsorted(dst_row.long(), torch.tensor(seg_all, device=dev)).to(torch.int32)
+    table = torch.tensor([o.data_ptr() for o in owners], dtype=torch.int64, device=dev)
+    dst = torch.full((940, dim), -1.0, device=dev)
+    peer.halo_pull(table, dim, src_row, seg, 3, dst, 0, dim, owner_mask=0b101, first_owner=2, dst_row=dst_row)
+    want = torch.full((940, dim), -1.0, device=dev)
+    full = torch.cat([owners[0][src[0]], torch.full((40, dim), -1.0, device=dev), owners[2][src[2]]])
+    want[dst_row.long()] = full[dst_row.long()]
+    assert torch.equal(dst, want)
+
+
 def test_peer_memory_single_rank_barrier_and_buffers():
     from hcspmm import peer
     dev = torch.device("cuda", 0)
@@ -143,18 +168,34 @@ def test_spmm_segments_matches_one_buffer(graph, dim, bf16):
         assert float((out - want).norm() / want.norm()) <= 1e-6
 
 
-def test_spmm_segments_rejects_tensor_core_graphs():
+def test_spmm_segments_rejects_dense_plans_and_ignores_labels():
+    """Segment mode runs on the CUDA-core balanced kernel in FP32: window labels do not matter (the result is the exact
+    aggregation), a dense super-window plan cannot be combined with it and is refused loudly."""
     import HCSPMM
     from helpers import small_graphs
     dev = torch.device("cuda", 0)
-    rp, ci = small_graphs()["rmat_hub_4096"]
+    rp, ci = small_graphs()["sbm_1024"]
     n = rp.size - 1
     d_rp, d_ci = torch.from_numpy(rp).to(dev), torch.from_numpy(ci).to(dev)
+    x = torch.randn(n, 64, device=dev)
+    HCSPMM.set_classifier("shipped")
+    pre0 = HCSPMM.preprocess(d_ci, d_rp, n, d_ci.numel(), (n + 15) // 16)
+    HCSPMM.set_precision("fp32")
+    try:
+        want = HCSPMM.forward(x, d_rp, d_ci, *HCSPMM.preprocess(d_ci, d_rp, n, d_ci.numel(), (n + 15) // 16))[0]
+    finally:
+        HCSPMM.set_precision("tf32")
     HCSPMM.set_classifier("all_tc")
     try:
-        pre = HCSPMM.preprocess(d_ci, d_rp, n, d_ci.numel(), (n + 15) // 16)
+        pre_tc = HCSPMM.preprocess(d_ci, d_rp, n, d_ci.numel(), (n + 15) // 16)
+        HCSPMM.set_dense(True)
+        pre_dense = HCSPMM.preprocess(d_ci, d_rp, n, d_ci.numel(), (n + 15) // 16)
     finally:
         HCSPMM.set_classifier("shipped")
-    x = torch.randn(n, 64, device=dev)
+        HCSPMM.set_dense(False)
+    assert int(pre_dense[4][1]) > 0
+    got = HCSPMM.spmm_segments(x, d_rp, d_ci, [0] * 8, n, torch.empty(n, 64, device=dev), False, pre_tc[4], pre_tc[5])
+    assert float((got - want).norm() / want.norm()) <= 1e-6
     with pytest.raises(RuntimeError, match="segment"):
-        HCSPMM.spmm_segments(x, d_rp, d_ci, [0] * 8, n, torch.empty(n, 64, device=dev), False, pre[4], pre[5])
+        HCSPMM.spmm_segments(x, d_rp, d_ci, [0] * 8, n, torch.empty(n, 64, device=dev), False, pre_dense[4], pre_dense[5])
+    del pre0

@@ -184,3 +184,24 @@ def test_segment_tags_address_the_right_rows(name, world, max_refs):
         vals = np.stack([ops[(r + int(s_)) % world][int(w_)] for s_, w_ in zip(seg.tolist(), row.tolist())]) if row.numel() else np.zeros((0, 8), np.float32)
         np.add.at(y, rows, vals)
         assert rel_fro(y, want[cuts[r]:cuts[r + 1]]) <= 1e-5
+
+
+@pytest.mark.parametrize("name,blocks", [("rmat_hub_4096", 4), ("rmat_1000", 3), ("holes_777", 8), ("sbm_1024", 2)])
+def test_row_block_order(name, blocks):
+    """Row-block pipeline (hcspmm.partition.row_block_order): blocks are contiguous, 16-row aligned and cover the shard;
+    every operand row's `first` is exactly the first block whose entries reference it, so a block never reads a row
+    that arrives with a later part of the halo; entries that do not address the local operand are ignored."""
+    rp, ci = small_graphs()[name]
+    n = rp.size - 1
+    rp_t, ci_t = _t(rp), _t(ci).clone()
+    ci_t[::7] = -5                                        # entries read in place from a peer (segment-tagged: negative)
+    cuts, first = partition.row_block_order(rp_t, ci_t, n, blocks)
+    assert cuts[0] == 0 and cuts[-1] == n and all(a <= b for a, b in zip(cuts, cuts[1:]))
+    assert all(c % 16 == 0 for c in cuts[:-1])
+    want = np.full(n, blocks, np.int64)
+    for b in range(blocks):
+        e0, e1 = rp[cuts[b]], rp[cuts[b + 1]]
+        cols = ci_t[e0:e1].numpy()
+        cols = cols[cols >= 0]
+        want[cols] = np.minimum(want[cols], b)
+    assert np.array_equal(first.numpy(), want)
