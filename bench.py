@@ -76,6 +76,8 @@ def parse():
                          "(1 = one all-gather, then one SpMM)")
     ap.add_argument("--dense", action="store_true", help="tcgen05 dense super-window plan (with --classifier b200|all_tc)")
     ap.add_argument("--tune", action="append", default=[], help="library tuning knob key=value (repeatable)")
+    ap.add_argument("--no-row-sort", action="store_true",
+                    help="preprocess() does not keep the row-sorted copy of low-degree CSRs (A/B of csrc/rowsort.cu)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="headline only: skip extra.sweep / extra.products")
@@ -279,6 +281,8 @@ def main():
     for kv in args.tune:
         k, v = kv.split("=")
         HCSPMM.set_tuning(k, int(v))
+    if args.no_row_sort:
+        HCSPMM.set_row_sort(False)
 
     ctx = Ctx(args, world, rank, dev)
     # the measured L2 -> SM gather roof (hcspmm_debug_l2_gather: random 1 KB rows of an L2-resident 32 MB buffer, the

@@ -44,6 +44,7 @@ def main():
     ap.add_argument("--direct-refs", type=int, default=0,
                     help="N > 1, peer exchange: remote rows referenced at most this many times are read in place by the SpMM "
                          "(0 = off, default; -1 = auto)")
+    ap.add_argument("--no-row-sort", action="store_true", help="no row-sorted CSR copy (A/B of csrc/rowsort.cu)")
     ap.add_argument("--row-blocks", type=int, default=0, help="N > 1, peer exchange: row-block pipeline (1 = off, 0 = auto)")
     ap.add_argument("--fp32-matmul", action="store_true",
                     help="Update GEMMs (torch.mm) in full FP32; default TF32 like the reference's stack "
@@ -61,6 +62,8 @@ def main():
     torch.backends.cuda.matmul.allow_tf32 = not args.fp32_matmul
     HCSPMM.set_dense(bool(args.dense))
     HCSPMM.set_classifier(args.classifier)
+    if args.no_row_sort:
+        HCSPMM.set_row_sort(False)
     rp, ci, info = graphs.named(args.shape, device=dev, scale=args.scale)
     g = hd.ShardedGraph(rp, ci, schedule=args.schedule, n_slabs=args.slabs, operand=args.operand,
                         direct_refs=None if args.direct_refs < 0 else args.direct_refs,

@@ -76,6 +76,9 @@ size_t dense_plan_workspace_bytes(int32_t n_rows, int64_t nnz);
 int dense_plan_count(const int32_t *, const int32_t *, const int32_t *, int32_t, int64_t, int, void *, size_t, int32_t *,
                      cudaStream_t);
 size_t dense_plan_words(int32_t n_rows, int32_t n_dense, int64_t total_cols);
+size_t row_sort_workspace_bytes(int32_t n_rows);
+int launch_row_sort(const int32_t *rowptr, const int32_t *colidx, int32_t n, int64_t nnz, int32_t *row_id,
+                    int32_t *rowptr_s, int32_t *colidx_s, void *ws, size_t ws_bytes, cudaStream_t stream);
 int dense_plan_fill(const int32_t *, const int32_t *, int32_t, int64_t, void *, int32_t, int64_t, int32_t *, size_t,
                     cudaStream_t);
 bool dense_supported(const float *, const float *, int64_t, int32_t);
@@ -247,6 +250,16 @@ int hcspmm_gemm_tf32(const float *d_a, int64_t lda, const float *d_b, int64_t ld
   if (tuning().umma_gemm == 1 && lda >= k && ldb >= n && ldo >= n && umma_gemm_supported(d_a, lda, d_b, ldb, k, n))
     return launch_umma_gemm(d_a, lda, d_b, ldb, m, k, n, d_out, ldo, umma_error_flag(), (cudaStream_t)stream);
   return launch_gemm_tf32(d_a, lda, d_b, ldb, m, k, n, d_out, ldo, (cudaStream_t)stream);
+}
+
+size_t hcspmm_row_sort_workspace_bytes(int32_t n_rows) { return row_sort_workspace_bytes(n_rows); }
+
+int hcspmm_row_sort(const int32_t *d_rowptr, const int32_t *d_colidx, int32_t n_rows, int64_t nnz, int32_t *d_row_id,
+                    int32_t *d_sorted_rowptr, int32_t *d_sorted_colidx, void *d_workspace, size_t workspace_bytes,
+                    void *stream) {
+  if (n_rows < 0 || nnz < 0) { set_error("row_sort: negative size"); return HCSPMM_E_INVALID; }
+  return launch_row_sort(d_rowptr, d_colidx, n_rows, nnz, d_row_id, d_sorted_rowptr, d_sorted_colidx, d_workspace,
+                         workspace_bytes, (cudaStream_t)stream);
 }
 
 size_t hcspmm_dense_plan_workspace_bytes(int32_t n_rows, int64_t nnz) { return dense_plan_workspace_bytes(n_rows, nnz); }

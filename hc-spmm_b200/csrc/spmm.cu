@@ -73,6 +73,8 @@ struct BalParams {
                      // other items (and 0) use the warp-per-row / CTA-per-long-row phases
   int hint_cls_min;  // >= 0: s.colidx is TAGGED (hcspmm_tag_columns); rows of class >= this are loaded evict_last,
                      // the others evict_first.  -1: plain column ids, every row evict_last
+  const int *row_id;      // row-sorted CSR (csrc/rowsort.cu): s.rowptr / s.colidx are the sorted copy and sorted row i is
+                          // row row_id[i] of Y (and of the window labels); nullptr = rows in place
   int seg_mode;           // 1: s.colidx carries segment tags, seg_x[] is valid
   const float *seg_x[8];  // segment mode (hcspmm_aux_t.d_colidx_segments): base of the X segment a column id's bits
                           // 29..31 name; seg_x[0] = s.x
@@ -741,9 +743,10 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) spmm_balanced_kernel(const 
   auto rp = [&](int i) -> int { return y0 + (int)rp16[i]; };
   const int L = rows_here - 1;
   const int s0 = __ldg(p.rowptr + x0), t0 = __ldg(p.rowptr + x0 + 1);
+  auto orig = [&](int row) -> int { return bp.row_id ? __ldg(bp.row_id + row) : row; };   // row of Y / of the labels
   auto elsewhere = [&](int row) -> bool {   // window labels 1 (mma.sync) / 2 (tcgen05 dense): not ours
     if (p.ht == nullptr) return false;
-    const int l = __ldg(p.ht + (row >> 4));
+    const int l = __ldg(p.ht + (orig(row) >> 4));
     return l == 1 || l == 2;
   };
   const bool lab0 = elsewhere(x0);
@@ -764,7 +767,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) spmm_balanced_kernel(const 
     if (i == 0 && is_head) { acc_flag = 0; return bp.partial + (size_t)(2 * k) * p.dim + feat0; }
     if (i == L && is_tail) { acc_flag = 0; return bp.partial + (size_t)(2 * k + 1) * p.dim + feat0; }
     acc_flag = p.accumulate;
-    return p.y + (long long)(x0 + i) * p.ldy + feat0;
+    return p.y + (long long)orig(x0 + i) * p.ldy + feat0;
   };
 
   const int q = lane / LPE, g = lane % LPE;
@@ -847,7 +850,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) spmm_balanced_kernel(const 
       for (int r = tid; r < rows_here; r += CTA_THREADS)
         if (rp(r + 1) == rp(r) && !skip(r))
           for (int v = 0; v < (S >> 2); ++v)
-            *reinterpret_cast<float4 *>(p.y + (long long)(x0 + r) * p.ldy + feat0 + v * 4) =
+            *reinterpret_cast<float4 *>(p.y + (long long)orig(x0 + r) * p.ldy + feat0 + v * 4) =
                 make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
     for (int b = 1; b < CTA_WARPS; ++b) {
@@ -904,7 +907,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) spmm_balanced_kernel(const 
     }
     if (d == 0 && short_row == 0 && !p.accumulate && !sk) {   // empty rows (never partial)
       for (int v = 0; v < (S >> 2); ++v)
-        *reinterpret_cast<float4 *>(p.y + (long long)(x0 + r) * p.ldy + feat0 + v * 4) =
+        *reinterpret_cast<float4 *>(p.y + (long long)orig(x0 + r) * p.ldy + feat0 + v * 4) =
             make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
@@ -987,7 +990,7 @@ __global__ void __launch_bounds__(64) spmm_balanced_fixup_kernel(const BalParams
       for (int kk = k1; kk < k; ++kk)
         add4(s, *reinterpret_cast<const float4 *>(bp.partial + (size_t)(2 * kk + 1) * p.dim + f));
       add4(s, *reinterpret_cast<const float4 *>(bp.partial + (size_t)(2 * k) * p.dim + f));
-      float4 *dst = reinterpret_cast<float4 *>(p.y + (long long)r * p.ldy + f);
+      float4 *dst = reinterpret_cast<float4 *>(p.y + (long long)(bp.row_id ? bp.row_id[r] : r) * p.ldy + f);
       if (p.accumulate) add4(s, *dst);
       *dst = s;
     }
@@ -1155,6 +1158,7 @@ struct BalAux {
   void *ws = nullptr;
   size_t ws_bytes = 0;
   const int *colidx_tagged = nullptr;   // hcspmm_tag_columns: column ids with their hotness class in bits 29..31
+  const int *sorted_rowptr = nullptr, *sorted_colidx = nullptr, *sorted_row_id = nullptr;   // hcspmm_row_sort
   const int *colidx_seg = nullptr;      // column ids with the SEGMENT of their X row in bits 29..31 (segment mode)
   const float *seg_x[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
@@ -1177,6 +1181,13 @@ static cudaError_t run_balanced(const SpmmParams &p, long long nnz, bool v8, boo
   BalParams bp;
   bp.s = p;
   bp.nnz = nnz;
+  bp.row_id = nullptr;
+  if (aux.sorted_rowptr != nullptr) {      // the row-sorted copy (aux.splits belong to it)
+    bp.s.rowptr = aux.sorted_rowptr;
+    bp.s.colidx = aux.sorted_colidx;
+    bp.row_id = aux.sorted_row_id;
+  }
+  const SpmmParams &ps = bp.s;
   int chunk = tuning().chunk > 0 ? tuning().chunk : default_chunk(p.slab, b16);
   if (chunk < 64) chunk = 64;
   if (chunk > 16384) chunk = 16384;
@@ -1213,7 +1224,7 @@ static cudaError_t run_balanced(const SpmmParams &p, long long nnz, bool v8, boo
     bp.splits = splits;
     bp.split_stride = 1;
     bp.split_max = (int)n_items;
-    merge_path_splits_kernel<<<(unsigned)((n_items + 1 + 127) / 128), 128, 0, stream>>>(p.rowptr, p.n_rows, nnz, chunk,
+    merge_path_splits_kernel<<<(unsigned)((n_items + 1 + 127) / 128), 128, 0, stream>>>(ps.rowptr, p.n_rows, nnz, chunk,
                                                                                       (int)n_items, splits);
   }
   bp.warp_split = tuning().warp_split;   // mean row length from which an item is cut by warp runs
@@ -1223,7 +1234,7 @@ static cudaError_t run_balanced(const SpmmParams &p, long long nnz, bool v8, boo
   // Measured (scripts/r2/hint_probe.py): the hints pay only for rows of >= 2 KB (Reddit shape dim 512: 15.5 -> 14.4 ms);
   // at 512-byte / 1 KB rows they LOSE 5-15 % (products dim 128: 3.26 -> 3.74 ms, Reddit dim 256: 6.37 -> 6.73 ms) -- LRU
   // already keeps the hub rows that matter -- so they apply from knob "l2_hot_min_row" bytes per row upwards.
-  if (aux.colidx_tagged != nullptr && tuning().l2_hot_mb > 0 && v8 && !b16 &&
+  if (aux.colidx_tagged != nullptr && aux.sorted_rowptr == nullptr && tuning().l2_hot_mb > 0 && v8 && !b16 &&
       (long long)p.dim * 4 >= tuning().l2_hot_min_row) {
     const long long row_bytes = (long long)p.dim * (b16 ? 2 : 4);
     const long long budget_rows = ((long long)tuning().l2_hot_mb << 20) / (row_bytes > 0 ? row_bytes : 1);
@@ -1313,6 +1324,12 @@ int launch_spmm(const float *x, int64_t ldx, int32_t x_rows, const int32_t *rowp
     aux.ws = aux_in->d_workspace; aux.ws_bytes = aux_in->workspace_bytes;
     aux.colidx_tagged = aux_in->d_colidx_tagged;
     aux.colidx_seg = aux_in->d_colidx_segments;
+    if (aux_in->d_sorted_rowptr && aux_in->d_sorted_row_id && (aux_in->d_sorted_colidx || nnz == 0) && !aux_in->d_colidx_segments) {
+      aux.sorted_rowptr = aux_in->d_sorted_rowptr; aux.sorted_colidx = aux_in->d_sorted_colidx;
+      aux.sorted_row_id = aux_in->d_sorted_row_id;
+    } else if (aux_in->d_sorted_rowptr) {
+      aux.splits = nullptr;   // the split points belong to the sorted copy, which this call does not use: recompute
+    }
     for (int i = 0; i < 8; ++i) aux.seg_x[i] = reinterpret_cast<const float *>(aux_in->segment_x[i]);
     n_tc_windows = aux_in->n_tc_windows;
   }

@@ -38,11 +38,13 @@ namespace {
 // graphs preprocessed afterwards, so two graphs (or two threads) never see each other's settings.
 constexpr int32_t kPlanMagic = 0x48435044;
 enum { H_MAGIC = 0, H_NDENSE, H_TOTALCOLS, H_NROWS, H_VERSION, H_PRECISION, H_DENSE, H_NTC, H_SPLITS_CHUNK, H_NSPLITS,
-       H_SPLITS_OFF, H_CLASSIFIER, H_PLAN_FULL, H_TAG_OFF, H_NCOLS, kHdrWords = 16 };
+       H_SPLITS_OFF, H_CLASSIFIER, H_PLAN_FULL, H_TAG_OFF, H_NCOLS, H_SORT_OFF, kHdrWords = 16 };
 bool g_dense = false;                        // defaults for the next preprocess()
 int g_classifier = HCSPMM_CLASSIFIER_SHIPPED;
 int g_precision = HCSPMM_PRECISION_TF32;
 bool g_bug_compat = false;
+bool g_row_sort = true;                      // preprocess() keeps a row-sorted copy of low-degree CSRs for the balanced
+                                             // kernel (hcspmm_row_sort; invisible to the caller)
 bool g_tag_columns = false;                  // preprocess() also emits hotness-tagged column ids (L2 residency hints:
                                              // they pay from 2 KB rows = dim 512 upwards, so they are opt-in)
 
@@ -164,7 +166,25 @@ std::vector<torch::Tensor> preprocess(torch::Tensor edgeList, torch::Tensor node
     n_cols = std::max<int64_t>(num_nodes, edgeList.max().item<int64_t>() + 1);
     if (n_cols * 128 > (64LL << 20) && n_cols < (1LL << 29)) tag_words = edge_num;
   }
-  auto col_nzr = torch::empty({plan_words + n_split_words + tag_words}, opts);
+  // row-sorted copy of the CSR (rows grouped by the power of two of their length): low-degree graphs on the balanced
+  // kernel -- an item then holds rows of similar length (products shape: -15 %).  [row_id | rowptr_s | colidx_s]
+  const bool row_sort = g_row_sort && tag_words == 0 && edge_num >= 8 * num_nodes && edge_num < 64 * num_nodes && num_nodes > 0;
+  const int64_t n4 = (num_nodes + 3) / 4 * 4, n14 = (num_nodes + 1 + 3) / 4 * 4;
+  const int64_t sort_words = row_sort ? n4 + n14 + edge_num : 0;
+  TORCH_CHECK(plan_words + n_split_words + tag_words + sort_words < (1LL << 31), "preprocess: per-graph products too large");
+  auto col_nzr = torch::empty({plan_words + n_split_words + tag_words + sort_words}, opts);
+  const int32_t *rowptr_for_splits = nodePointer.data_ptr<int32_t>();
+  if (row_sort) {
+    const int64_t off = plan_words + n_split_words + tag_words;
+    int32_t *base = col_nzr.data_ptr<int32_t>() + off;
+    const size_t sws = hcspmm_row_sort_workspace_bytes((int32_t)num_nodes);
+    auto sw = torch::empty({(int64_t)sws}, opts.dtype(torch::kUInt8));
+    check_rc(hcspmm_row_sort(nodePointer.data_ptr<int32_t>(), edgeList.data_ptr<int32_t>(), (int32_t)num_nodes, edge_num,
+                             base, base + n4, base + n4 + n14, sw.data_ptr(), sws, stream),
+             "row_sort");
+    h[H_SORT_OFF] = (int32_t)off;
+    rowptr_for_splits = base + n4;          // the split points below are those of the sorted copy
+  }
   if (tag_words > 0) {
     const size_t tws = hcspmm_tag_columns_workspace_bytes((int32_t)n_cols, edge_num);
     auto tw = torch::empty({(int64_t)tws}, opts.dtype(torch::kUInt8));
@@ -174,7 +194,7 @@ std::vector<torch::Tensor> preprocess(torch::Tensor edgeList, torch::Tensor node
     h[H_TAG_OFF] = (int32_t)(plan_words + n_split_words); h[H_NCOLS] = (int32_t)n_cols;
   }
   if (plan_words > 0) col_nzr.narrow(0, 0, plan_words).copy_(plan);
-  check_rc(hcspmm_merge_path_splits(nodePointer.data_ptr<int32_t>(), (int32_t)num_nodes, edge_num, HCSPMM_SPLITS_CHUNK,
+  check_rc(hcspmm_merge_path_splits(rowptr_for_splits, (int32_t)num_nodes, edge_num, HCSPMM_SPLITS_CHUNK,
                                     col_nzr.data_ptr<int32_t>() + plan_words, stream),
            "merge_path_splits");
   h[H_SPLITS_CHUNK] = HCSPMM_SPLITS_CHUNK;
@@ -211,6 +231,16 @@ AuxView make_aux(const torch::Tensor &input, const Graph &g, const torch::Tensor
     v.aux.d_splits = blob + h[H_SPLITS_OFF]; v.aux.splits_chunk = h[H_SPLITS_CHUNK]; v.aux.n_splits = h[H_NSPLITS];
   }
   if (h[H_TAG_OFF] > 0 && col_nzr.numel() >= (int64_t)h[H_TAG_OFF] + g.nnz) v.aux.d_colidx_tagged = blob + h[H_TAG_OFF];
+  if (h[H_SORT_OFF] > 0) {
+    const int64_t n4 = ((int64_t)g.n_rows + 3) / 4 * 4, n14 = ((int64_t)g.n_rows + 1 + 3) / 4 * 4;
+    if (col_nzr.numel() >= (int64_t)h[H_SORT_OFF] + n4 + n14 + g.nnz) {
+      v.aux.d_sorted_row_id = blob + h[H_SORT_OFF];
+      v.aux.d_sorted_rowptr = blob + h[H_SORT_OFF] + n4;
+      v.aux.d_sorted_colidx = blob + h[H_SORT_OFF] + n4 + n14;
+    } else {
+      v.aux.d_splits = nullptr;           // cannot happen with tensors from preprocess(); never pair foreign splits
+    }
+  }
   if (h[H_DENSE] && h[H_NDENSE] > 0) {
     v.aux.d_plan = blob; v.aux.n_dense = h[H_NDENSE]; v.aux.total_cols = h[H_TOTALCOLS]; v.aux.plan_full = h[H_PLAN_FULL];
   }
@@ -448,6 +478,12 @@ bool set_dense(bool on) {
   return old;
 }
 
+bool set_row_sort(bool on) {
+  bool old = g_row_sort;
+  g_row_sort = on;
+  return old;
+}
+
 bool set_tag_columns(bool on) {
   bool old = g_tag_columns;
   g_tag_columns = on;
@@ -512,6 +548,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("set_classifier", &set_classifier, "shipped | intended | b200 | all_cuda | all_tc; returns the previous mode");
   m.def("set_precision", &set_precision, "tf32 | tf32x2 | fp32 | bf16; returns the previous mode");
   m.def("set_dense", &set_dense, "tcgen05 kernels: dense super-window plans in preprocess()/forward*(), Update GEMM");
+  m.def("set_row_sort", &set_row_sort, "preprocess() keeps a row-sorted copy of low-degree CSRs for the balanced kernel (default on); returns the previous setting");
   m.def("set_tag_columns", &set_tag_columns, "preprocess() also emits hotness-tagged column ids for the L2 residency hints of wide gathers (default off)");
   m.def("set_bug_compat", &set_bug_compat, "read strided `weights` as raw memory like the reference");
   m.def("set_tuning", &set_tuning, "kernel tuning knob (long_row, slab); returns the previous value");

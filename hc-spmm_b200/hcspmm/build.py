@@ -21,7 +21,7 @@ LIB_DIR = os.path.join(PKG_ROOT, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libhcspmm.so")
 EXT_PATH = os.path.join(PKG_ROOT, "HCSPMM.so")
 
-CU_SOURCES = ["capi.cu", "preprocess.cu", "spmm.cu", "gemm.cu", "loa.cu", "umma_gemm.cu", "update_gemm.cu", "dense.cu", "dense_tma.cu", "peer.cu", "microbench.cu", "hotcols.cu"]
+CU_SOURCES = ["capi.cu", "preprocess.cu", "spmm.cu", "gemm.cu", "loa.cu", "umma_gemm.cu", "update_gemm.cu", "dense.cu", "dense_tma.cu", "peer.cu", "microbench.cu", "hotcols.cu", "rowsort.cu"]
 HEADERS = ["common.cuh", "umma.cuh", os.path.join(REPO_ROOT, "include", "hcspmm.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

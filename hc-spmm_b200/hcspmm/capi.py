@@ -27,7 +27,7 @@ EXPORTS = [
     "hcspmm_halo_pull", "hcspmm_halo_pull_rows", "hcspmm_debug_l2_gather",
     "hcspmm_merge_path_count", "hcspmm_merge_path_splits", "hcspmm_spmm_workspace_bytes", "hcspmm_spmm_aux",
     "hcspmm_f32_to_bf16", "hcspmm_spmm_gemm_aux", "hcspmm_halo_push",
-    "hcspmm_tag_columns_workspace_bytes", "hcspmm_tag_columns",
+    "hcspmm_tag_columns_workspace_bytes", "hcspmm_tag_columns", "hcspmm_row_sort_workspace_bytes", "hcspmm_row_sort",
 ]
 
 _lib = None
@@ -45,7 +45,8 @@ class Aux(ctypes.Structure):
                 ("n_tc_windows", ctypes.c_int32), ("d_plan", ctypes.c_void_p), ("n_dense", ctypes.c_int32),
                 ("plan_full", ctypes.c_int32), ("total_cols", ctypes.c_int64), ("d_workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
                 ("d_colidx_tagged", ctypes.c_void_p), ("d_colidx_segments", ctypes.c_void_p),
-                ("segment_x", ctypes.c_void_p * 8)]
+                ("segment_x", ctypes.c_void_p * 8), ("d_sorted_rowptr", ctypes.c_void_p),
+                ("d_sorted_colidx", ctypes.c_void_p), ("d_sorted_row_id", ctypes.c_void_p)]
 
 
 def lib() -> ctypes.CDLL:
@@ -101,6 +102,9 @@ def lib() -> ctypes.CDLL:
         L.hcspmm_tag_columns_workspace_bytes.restype = _sz
         L.hcspmm_tag_columns_workspace_bytes.argtypes = [_i32, _i64]
         L.hcspmm_tag_columns.argtypes = [_vp, _i64, _i32, _vp, _vp, _sz, _vp]
+        L.hcspmm_row_sort_workspace_bytes.restype = _sz
+        L.hcspmm_row_sort_workspace_bytes.argtypes = [_i32]
+        L.hcspmm_row_sort.argtypes = [_vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _sz, _vp]
         L.hcspmm_halo_push.argtypes = [_vp, _i64, _vp, _vp, _vp, _i64, _i32, ctypes.c_uint64, _i32, _i32, _i32, _i32, _vp]
         L.hcspmm_spmm_gemm_aux.argtypes = [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _int, _vp, _i64,
                                            _i32, _vp, _i64, _vp, _i64, ctypes.POINTER(Aux), _vp]
@@ -181,19 +185,48 @@ def tag_column_ids(colidx: torch.Tensor, n_cols: int) -> torch.Tensor:
     return out
 
 
+def want_row_sort(n_rows: int, nnz: int) -> bool:
+    """The rule preprocess() applies: graphs the balanced kernel serves (mean row >= 8 entries) whose rows are short
+    enough (mean < 64) that an item holds hundreds of them -- there grouping rows of similar length pays (products
+    shape: -15 %); on high-degree graphs the warp runs already balance an item."""
+    return 8 * n_rows <= nnz < 64 * n_rows
+
+
+def row_sort_csr(rowptr: torch.Tensor, colidx: torch.Tensor):
+    """hcspmm_row_sort -> (row_id [n], sorted_rowptr [n + 1], sorted_colidx [nnz])."""
+    n, nnz = rowptr.numel() - 1, colidx.numel()
+    dev = rowptr.device
+    row_id = torch.empty(n, dtype=torch.int32, device=dev)
+    rp_s = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    ci_s = torch.empty(nnz, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        nbytes = lib().hcspmm_row_sort_workspace_bytes(n)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _check(lib().hcspmm_row_sort(_ptr(rowptr), _ptr(colidx), n, nnz, _ptr(row_id), _ptr(rp_s), _ptr(ci_s), _ptr(ws), nbytes,
+                                     _stream(rowptr)), "hcspmm_row_sort")
+    return row_id, rp_s, ci_s
+
+
 class GraphAux:
     """The per-graph products of hcspmm_aux_t for a device CSR: merge-path split points (computed once), the count of
     windows labelled 1 and a reusable workspace -- what HCSPMM.preprocess() packs into its two opaque tensors."""
 
     def __init__(self, rowptr: torch.Tensor, colidx: torch.Tensor, ht: torch.Tensor | None = None, plan=None,
-                 tag_columns: bool = False, n_cols: int | None = None):
+                 tag_columns: bool = False, n_cols: int | None = None, row_sort: bool | None = None):
+        """row_sort: keep a row-sorted copy of the CSR for the balanced kernel (hcspmm_row_sort: rows grouped by the power
+        of two of their length; invisible to the caller).  None = the library's rule: low-degree graphs served by the
+        balanced kernel (8 <= mean row < 64 entries)."""
         n, nnz = rowptr.numel() - 1, colidx.numel()
         self.n, self.nnz = n, nnz
         self.tagged = tag_column_ids(colidx, n_cols if n_cols is not None else n) if (tag_columns and nnz > 0) else None
+        if row_sort is None:
+            row_sort = want_row_sort(n, nnz)
+        self.sorted = row_sort_csr(rowptr, colidx) if (row_sort and n > 0 and self.tagged is None) else None
         with torch.cuda.device(rowptr.device):
             cnt = lib().hcspmm_merge_path_count(n, nnz, SPLITS_CHUNK)
             self.splits = torch.empty(cnt, dtype=torch.int32, device=rowptr.device)
-            _check(lib().hcspmm_merge_path_splits(_ptr(rowptr), n, nnz, SPLITS_CHUNK, _ptr(self.splits), _stream(rowptr)),
+            rp_for_splits = self.sorted[1] if self.sorted is not None else rowptr
+            _check(lib().hcspmm_merge_path_splits(_ptr(rp_for_splits), n, nnz, SPLITS_CHUNK, _ptr(self.splits), _stream(rowptr)),
                    "hcspmm_merge_path_splits")
         self.n_tc = int((ht == 1).sum()) if ht is not None else -1
         self.plan = plan
@@ -217,6 +250,8 @@ class GraphAux:
         a.d_workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
         if self.tagged is not None:
             a.d_colidx_tagged = self.tagged.data_ptr()
+        if self.sorted is not None:
+            a.d_sorted_row_id, a.d_sorted_rowptr, a.d_sorted_colidx = (t.data_ptr() for t in self.sorted)
         return a
 
 

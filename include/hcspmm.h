@@ -242,7 +242,18 @@ typedef struct {
   const int32_t *d_colidx_tagged;   /* hcspmm_tag_columns output, or NULL */
   const int32_t *d_colidx_segments; /* segment mode (multi-GPU), or NULL: see below */
   const void *segment_x[8];         /* segment s = 1..7: base of that X buffer (same row pitch as d_x); [0] unused */
+  const int32_t *d_sorted_rowptr;   /* hcspmm_row_sort outputs, or NULL: the balanced kernel walks the row-sorted copy */
+  const int32_t *d_sorted_colidx;   /*   of the CSR and writes sorted row i to Y[d_sorted_row_id[i]]; d_splits must then */
+  const int32_t *d_sorted_row_id;   /*   be the split points of d_sorted_rowptr                                          */
 } hcspmm_aux_t;
+/* Row-sorted copy of a CSR for the balanced kernel (csrc/rowsort.cu): rows grouped by the power of two of their length,
+ * longest first, original order inside a class; every row keeps its entries in their original order, so each row sum
+ * is unchanged.  Items of the balanced kernel then hold rows of similar length (products shape: -15 %).  Invisible to
+ * the caller: no vertex is relabelled.  d_row_id[n_rows], d_sorted_rowptr[n_rows + 1], d_sorted_colidx[nnz].          */
+size_t hcspmm_row_sort_workspace_bytes(int32_t n_rows);
+int hcspmm_row_sort(const int32_t *d_rowptr, const int32_t *d_colidx, int32_t n_rows, int64_t nnz, int32_t *d_row_id,
+                    int32_t *d_sorted_rowptr, int32_t *d_sorted_colidx, void *d_workspace, size_t workspace_bytes,
+                    void *stream);
 size_t hcspmm_tag_columns_workspace_bytes(int32_t n_cols, int64_t nnz);
 int hcspmm_tag_columns(const int32_t *d_colidx, int64_t nnz, int32_t n_cols, int32_t *d_tagged, void *d_workspace,
                        size_t workspace_bytes, void *stream);

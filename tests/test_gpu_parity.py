@@ -337,7 +337,7 @@ def test_spmm_aux_is_the_same_computation(capi, name, dim):
     old = capi.set_tuning("balance", 2)
     try:
         plain = capi.spmm(dev(x), dev(rp), dev(ci), *pre)
-        aux = capi.GraphAux(dev(rp), dev(ci), pre[3])
+        aux = capi.GraphAux(dev(rp), dev(ci), pre[3], row_sort=False)      # the sorted copy: tests/test_gpu_rowsort.py
         assert aux.n_tc == int((pre[3] == 1).sum())
         got = capi.spmm_aux(dev(x), dev(rp), dev(ci), *pre, aux)
         again = capi.spmm_aux(dev(x), dev(rp), dev(ci), *pre, aux)
@@ -367,7 +367,7 @@ def test_spmm_bf16_stored_operand(capi, name):
     pre = capi.preprocess(dev(ci), dev(rp), "shipped")
     want = capi.spmm(dev(x), dev(rp), dev(ci), *pre, precision="bf16")
     xb = capi.f32_to_bf16(dev(x))
-    aux = capi.GraphAux(dev(rp), dev(ci), pre[3])
+    aux = capi.GraphAux(dev(rp), dev(ci), pre[3], row_sort=False)
     got = capi.spmm_aux(xb, dev(rp), dev(ci), *pre, aux, precision="bf16_stored")
     assert torch.equal(got, want)
     assert rel_fro(got.cpu().numpy(), oracle.spmm(rp, ci, x, precision=1)) <= 1e-2

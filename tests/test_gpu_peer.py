@@ -133,7 +133,11 @@ def test_spmm_segments_matches_one_buffer(graph, dim, bf16):
     g = torch.Generator(device=dev).manual_seed(dim)
     x = torch.randn(n, dim, device=dev, generator=g)
     HCSPMM.set_classifier("shipped")
-    pre = HCSPMM.preprocess(d_ci, d_rp, n, d_ci.numel(), (n + 15) // 16)
+    old_sort = HCSPMM.set_row_sort(False)       # segment mode walks the CSR in place: compare with the same walk
+    try:
+        pre = HCSPMM.preprocess(d_ci, d_rp, n, d_ci.numel(), (n + 15) // 16)
+    finally:
+        HCSPMM.set_row_sort(old_sort)
     xs = x.to(torch.bfloat16) if bf16 else x
     want = torch.empty(n, dim, device=dev)
     if bf16:
