@@ -255,7 +255,7 @@ __device__ __forceinline__ void gather_accumulate(Vec<VW, B16> (&acc)[NV], const
     const int nb = base + chunk_stride * 32;
     c_next = (nb + lane < ee) ? __ldg(colidx + nb + lane) : -1;  // next chunk's ids, early
     (void)all_active;
-    const bool fast = n == 32 && __all_sync(0xffffffffu, ((unsigned)c & (MODE ? h.mask : 0xffffffffu)) < (unsigned)x_rows);
+    const bool fast = n == 32 && __all_sync(0xffffffffu, ((unsigned)c & ((MODE == 1 || MODE == 2) ? h.mask : 0xffffffffu)) < (unsigned)x_rows);
     if (fast) {
       // full chunk, every id valid: unpredicated ring of U loads in flight -- slot s % U is consumed
       // and immediately refilled with step s + U.  Lanes beyond the slab width (voff < 0) re-read
@@ -299,9 +299,9 @@ __device__ __forceinline__ void gather_accumulate(Vec<VW, B16> (&acc)[NV], const
         for (int u = 0; u < U; ++u) {
           const int j = (t + u) * G + q;
           const unsigned ct = (unsigned)__shfl_sync(0xffffffffu, c, j & 31);
-          const unsigned cu = MODE ? (ct & h.mask) : ct;
+          const unsigned cu = (MODE == 1 || MODE == 2) ? (ct & h.mask) : ct;
           const bool ok = (j < n) && (cu < (unsigned)x_rows);
-          const float *src = row_ptr<MODE>(xlane, ldx, ok ? ct : 0u, h);
+          const float *src = row_ptr<MODE>(xlane, ldx, ct, h);
 #pragma unroll
           for (int i = 0; i < NV; ++i) {
             if (ok && active[i]) {
@@ -344,9 +344,9 @@ __device__ __forceinline__ void gather_group_row(Vec<VW, B16> (&acc)[NV], const 
 #pragma unroll
       for (int u = 0; u < UB; ++u) {
         const unsigned ct = (unsigned)__shfl_sync(gmask, my, q * LPE + ((j0 + u) & (LPE - 1)));
-        const unsigned cu = MODE ? (ct & h.mask) : ct;
+        const unsigned cu = (MODE == 1 || MODE == 2) ? (ct & h.mask) : ct;
         const bool ok = (j0 + u < cnt) && (cu < (unsigned)x_rows);
-        const float *src = row_ptr<MODE>(xlane, ldx, ok ? ct : 0u, h);
+        const float *src = row_ptr<MODE>(xlane, ldx, ct, h);
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
           if (ok && active[i]) {
@@ -743,7 +743,12 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) spmm_balanced_kernel(const 
   auto rp = [&](int i) -> int { return y0 + (int)rp16[i]; };
   const int L = rows_here - 1;
   const int s0 = __ldg(p.rowptr + x0), t0 = __ldg(p.rowptr + x0 + 1);
-  auto orig = [&](int row) -> int { return bp.row_id ? __ldg(bp.row_id + row) : row; };   // row of Y / of the labels
+  auto orig = [&](int row) -> int {   // row of Y / of the labels: MODE 3 walks the row-sorted copy (csrc/rowsort.cu)
+    // (written with the run-time test on purpose: in the 80-register build ptxas spills 16 bytes per thread with it
+    //  and 32 without -- products shape 2.93 vs 3.04 ms)
+    if constexpr (MODE == 3) return bp.row_id ? __ldg(bp.row_id + row) : row;
+    else return row;
+  };
   auto elsewhere = [&](int row) -> bool {   // window labels 1 (mma.sync) / 2 (tcgen05 dense): not ours
     if (p.ht == nullptr) return false;
     const int l = __ldg(p.ht + (orig(row) >> 4));
@@ -1119,6 +1124,11 @@ template <int LPE, int NV, int VW, bool B16>
 static cudaError_t launch_balanced_t(const BalParams &bp, dim3 grid, size_t smem, cudaStream_t stream) {
   // low-degree graphs (rows of a few dozen entries) are latency-bound: three CTAs per SM hide more of it than
   // the deeper gather ring of the two-CTA build does (FP32, one vector per lane: dim <= 256 / 128)
+  if (bp.row_id != nullptr) {   // the row-sorted copy of the CSR: its own build, so the in-place walk pays nothing for it
+    if constexpr (!B16 && NV == 1)
+      if (bp.low_degree && tuning().occupancy3) return launch_balanced_b<LPE, NV, VW, B16, 3, 3>(bp, grid, smem, stream);
+    return launch_balanced_b<LPE, NV, VW, B16, HCSPMM_MIN_CTAS, 3>(bp, grid, smem, stream);
+  }
   if (bp.seg_mode) {   // X in segments (peer-mapped operands read in place): 256-bit FP32 / BF16 rows up to 1 KB
     if constexpr (VW == 8 && NV == 1) {
       if constexpr (!B16)
@@ -1515,7 +1525,13 @@ int launch_spmm(const float *x, int64_t ldx, int32_t x_rows, const int32_t *rowp
           else err = launch_hybrid<32, 4, 4>(pt, grid, smem, stream);
         }
       }
-      if (err == cudaSuccess) err = run_balanced(p, nnz, v8, false, aux, stream);
+      if (err == cudaSuccess) {
+        // no window is labelled 1 and no dense plan relabelled any (its labels arrive with n_tc_windows = -1): every
+        // window is the balanced kernel's, which then needs no label look-up per row
+        SpmmParams pb = p;
+        if (n_tc_windows == 0) pb.ht = nullptr;
+        err = run_balanced(pb, nnz, v8, false, aux, stream);
+      }
     } else if (v8) {
       if (slab <= 32) err = launch_hybrid<4, 1, 8>(p, grid, smem, stream);
       else if (slab <= 64) err = launch_hybrid<8, 1, 8>(p, grid, smem, stream);
