@@ -17,7 +17,7 @@ void set_error(const char *fmt, ...) {
 }
 
 Tuning &tuning() {
-  static Tuning t = {1024, 0, 1, 1, 0, 1, 1, 2, 1, 1, 1, 0, 0, 64, 1, 0, 2048, 10000, 1, 1, 8, 72, 2048};
+  static Tuning t = {1024, 0, 1, 1, 0, 1, 1, 2, 1, 1, 1, 0, 0, 64, 1, 0, 2048, 10000, 1, 1, 8, 72, 2048, 0};
   return t;
 }
 
@@ -152,6 +152,7 @@ int hcspmm_set_tuning(const char *key, int value) {
   else if (key && !strcmp(key, "dense_min_rowlen")) slot = &tuning().dense_min_rowlen;
   else if (key && !strcmp(key, "l2_hot_mb")) slot = &tuning().l2_hot_mb;
   else if (key && !strcmp(key, "l2_hot_min_row")) slot = &tuning().l2_hot_min_row;
+  else if (key && !strcmp(key, "staged")) slot = &tuning().staged;
   if (!slot) return -1;
   int old = *slot;
   *slot = value;

@@ -39,6 +39,7 @@ struct Tuning {
   int dense_min_rowlen; // dense plan: minimum mean stored entries per row of a 128-row super-window
   int l2_hot_mb;   // balanced kernel with tagged column ids: megabytes of X rows kept L2-resident (evict_last); 0 = off
   int l2_hot_min_row; // ... applied only to gathers of at least this many bytes per row
+  int staged;      // 1: low-degree graphs with 260..512-byte rows gather through shared-memory staging (spmm_staged_kernel)
 };
 Tuning &tuning();
 
@@ -74,6 +75,12 @@ __device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src
   uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem_src),
                "r"(src_bytes));
+}
+// the same through L1 (.ca): the warp's 16-byte pieces are merged into whole sectors before they go to L2 -- the L1-bypassing
+// form fetches a 32-byte sector per 16-byte piece when the pieces of a warp cover a contiguous row (measured: 2 x the bytes)
+__device__ __forceinline__ void cp_async_16_ca(void *smem_dst, const void *gmem_src, int src_bytes) {
+  uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem_src), "r"(src_bytes));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N>

@@ -982,6 +982,212 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) spmm_balanced_kernel(const 
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Staged gather for low-degree graphs (rows of 260..512 bytes, every window CUDA-core).
+//
+// The balanced kernel above keeps gathered rows in REGISTERS while they are in flight: 4 ring slots per lane, 8 rows
+// per warp, 24 warps per SM = 192 rows of X on their way per SM, and that is all the 80-register build can hold.  On
+// the products shape the kernel then waits: long_scoreboard 12 warps per issue, DRAM at 0.66 of its copy bandwidth,
+// issue slots 32 % busy -- it is short of memory-level parallelism, not of bandwidth.  Here the rows in flight live
+// in SHARED MEMORY instead: every lane copies "its" 16 bytes of a row with cp.async (LDGSTS: no register is held
+// while the copy is outstanding, no depth limit), STG_S groups of STG_K rows deep, and later adds the same 16 bytes
+// back from shared memory -- lane L writes and reads only column L of the ring, so the pipeline needs no warp
+// synchronisation at all, only cp.async.wait_group.  20 rows in flight per warp, 16 warps per SM = 320 rows per SM.
+// A lane owns 4 features of the row (32 lanes x 16 bytes = 512 bytes), so a row sum is complete in its lane: no
+// cross-lane reduction at a row end, which on short rows is most of the non-gather work.
+//
+// Work decomposition, item boundaries, partial rows and the fix-up pass are those of the balanced kernel (same
+// BalParams, same split points): an item's entries are cut into eight equal warp runs; a warp streams its run
+// straight through the row boundaries (a row end only flushes the lane's sum), so the pipeline never drains on short
+// rows.  Sum order inside a row is CSR order, pieces are added in warp / item order: deterministic.
+// ---------------------------------------------------------------------------------------
+constexpr int STG_K = 4;                 // rows per cp.async group
+constexpr int STG_S = 5;                 // groups in flight per warp
+constexpr int STG_R = STG_K * STG_S;     // ring slots per warp
+constexpr int STG_ROW = 128;             // floats per ring slot
+
+static size_t staged_smem_bytes(int chunk) {
+  const size_t rp_words = (((size_t)chunk + 4) / 2 + 3) & ~(size_t)3;
+  return sizeof(float) * (2 * CTA_WARPS * STG_ROW + rp_words + (size_t)CTA_WARPS * STG_R * STG_ROW);
+}
+
+__global__ void __launch_bounds__(CTA_THREADS, 2) spmm_staged_kernel(const BalParams bp) {
+  const SpmmParams &p = bp.s;
+  extern __shared__ __align__(16) float smem[];   // [2 * CTA_WARPS * 128] row pieces | uint16 row offsets | rings
+  __shared__ int s_prow[CTA_WARPS][2];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int k = blockIdx.x;
+  const int S = p.dim;                            // 64 < S <= 128, S % 4 == 0, one feature slab
+  const bool act = lane * 4 < S;
+  const int rp_words = (((bp.chunk + 4) / 2) + 3) & ~3;
+  const unsigned short *rp16 = reinterpret_cast<const unsigned short *>(smem + 2 * CTA_WARPS * STG_ROW);
+  float *ring = smem + 2 * CTA_WARPS * STG_ROW + rp_words + (size_t)wid * STG_R * STG_ROW + lane * 4;
+
+  const long long total = (long long)p.n_rows + bp.nnz;
+  const long long d0 = min(total, (long long)k * bp.chunk), d1 = min(total, (long long)(k + 1) * bp.chunk);
+  const int x0 = __ldg(bp.splits + min(k * bp.split_stride, bp.split_max));
+  const int x1 = __ldg(bp.splits + min((k + 1) * bp.split_stride, bp.split_max));
+  const int y0 = (int)(d0 - x0), y1 = (int)(d1 - x1);
+  const bool last_in = x1 < p.n_rows && __ldg(p.rowptr + x1) < y1;
+  const int rows_here = x1 - x0 + (last_in ? 1 : 0);
+  if (rows_here <= 0) {
+    if (tid == 0) bp.split_row[2 * k] = bp.split_row[2 * k + 1] = -1;
+    return;
+  }
+  {
+    unsigned short *w16 = reinterpret_cast<unsigned short *>(smem + 2 * CTA_WARPS * STG_ROW);
+    for (int i = tid; i <= rows_here; i += CTA_THREADS)
+      w16[i] = (unsigned short)(min(max(__ldg(p.rowptr + x0 + i), y0), y1) - y0);
+  }
+  auto rp = [&](int i) -> int { return y0 + (int)rp16[i]; };
+  auto orig = [&](int row) -> int { return bp.row_id ? __ldg(bp.row_id + row) : row; };
+  const int L = rows_here - 1;
+  const int s0 = __ldg(p.rowptr + x0), t0 = __ldg(p.rowptr + x0 + 1);
+  const bool is_tail = last_in && __ldg(p.rowptr + x1 + 1) > y1;          // row x1 continues in item k+1
+  const bool head_skip = s0 < y0 && t0 <= y0;                              // row x0 was finished by item k-1
+  const bool is_head = s0 < y0 && t0 > y0 && !(is_tail && L == 0);         // row x0 began earlier, ends here
+  if (tid == 0) {
+    bp.split_row[2 * k] = is_head ? x0 : -1;
+    bp.split_row[2 * k + 1] = is_tail ? x1 : -1;
+  }
+  __syncthreads();
+  auto out_row = [&](int i, int &acc_flag) -> float * {
+    if (i == 0 && is_head) { acc_flag = 0; return bp.partial + (size_t)(2 * k) * p.dim; }
+    if (i == L && is_tail) { acc_flag = 0; return bp.partial + (size_t)(2 * k + 1) * p.dim; }
+    acc_flag = p.accumulate;
+    return p.y + (long long)orig(x0 + i) * p.ldy;
+  };
+
+  float *pieces = smem;   // [CTA_WARPS][2][S]
+  const int e_cta = y1 - y0;
+  const int ew = ((e_cta + CTA_WARPS - 1) / CTA_WARPS + 31) & ~31;
+  auto row_of = [&](int b) -> int {   // first row with entries beyond position b (y0 <= b < y1)
+    int lo = 0, hi = rows_here - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (rp(mid + 1) > b) hi = mid;
+      else lo = mid + 1;
+    }
+    return lo;
+  };
+  auto boundary = [&](int w) -> int {   // the equal cut, moved to a row boundary when one lies within a quarter run
+    const int b = y0 + w * ew;
+    if (w <= 0) return y0;
+    if (b >= y1) return y1;
+    const int r = row_of(b);
+    const int lo = rp(r), hi = rp(r + 1);
+    const int cand = (b - lo <= hi - b) ? lo : hi;
+    return (abs(cand - b) <= (ew >> 2)) ? cand : b;
+  };
+  const int wb = boundary(wid), we = boundary(wid + 1);
+  int head_row = -1, tail_row = -1;
+  if (wb < we) {
+    const int n_b = (we - wb + STG_K - 1) / STG_K;
+    const float *xl = p.x + lane * 4;
+    // column ids of the run, 32 at a time, one chunk ahead of the copies
+    int jc = 0;
+    int cid = (wb + lane < we) ? __ldg(p.colidx + wb + lane) : -1;
+    int cid_next = (wb + 32 + lane < we) ? __ldg(p.colidx + wb + 32 + lane) : -1;
+    int si = 0, sc = 0;                           // ring slot of the next batch to issue / to consume
+    // Every lane always copies: lanes beyond the row width, entries beyond the run and invalid ids copy zero bytes, which
+    // zero-fills their 16 bytes -- no branch around the shuffles, and the sums below need no predicate.  Row addresses
+    // are base + id * pitch with a 32-bit byte pitch (one IMAD.WIDE; the launcher guarantees x_rows * pitch < 4 GB).
+    const unsigned pitch = (unsigned)p.ldx * 4u;
+    const char *xb = reinterpret_cast<const char *>(p.x) + lane * 16;
+    const unsigned xr = act ? (unsigned)p.x_rows : 0u;
+    (void)xl;
+    auto issue = [&](int b) {
+      const int o0 = b * STG_K;
+      const int j = o0 >> 5;
+      if (j != jc) {
+        jc = j;
+        cid = cid_next;
+        const int nb = wb + (j + 1) * 32 + lane;
+        cid_next = nb < we ? __ldg(p.colidx + nb) : -1;
+      }
+      float *slot = ring + si * STG_ROW;
+      if (wb + o0 + STG_K <= we) {               // the whole batch lies inside the run (uniform)
+#pragma unroll
+        for (int kk = 0; kk < STG_K; ++kk) {
+          const unsigned c = (unsigned)__shfl_sync(0xffffffffu, cid, (o0 + kk) & 31);
+          const bool ok = c < xr;
+          cp_async_16_ca(slot + kk * STG_ROW, xb + (size_t)(ok ? c : 0u) * pitch, ok ? 16 : 0);
+        }
+      } else {
+#pragma unroll
+        for (int kk = 0; kk < STG_K; ++kk) {
+          const unsigned c = (unsigned)__shfl_sync(0xffffffffu, cid, (o0 + kk) & 31);
+          const bool ok = (wb + o0 + kk < we) && (c < xr);
+          cp_async_16_ca(slot + kk * STG_ROW, xb + (size_t)(ok ? c : 0u) * pitch, ok ? 16 : 0);
+        }
+      }
+      si = si + STG_K == STG_R ? 0 : si + STG_K;
+      cp_async_commit();
+    };
+#pragma unroll
+    for (int b = 0; b < STG_S - 1; ++b) issue(b);
+    int r = row_of(wb);
+    int cur_end = min(rp(r + 1), we);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int b = 0; b < n_b; ++b) {
+      issue(b + STG_S - 1);                      // refills the slots of batch b - 1, consumed last iteration
+      cp_async_wait<STG_S - 1>();                // this lane's copies of batch b have landed
+      const float *slot = ring + sc * STG_ROW;
+      const int e0 = wb + b * STG_K;
+      if (cur_end > e0 + STG_K) {                // no row ends inside this batch (uniform): four plain sums
+#pragma unroll
+        for (int kk = 0; kk < STG_K; ++kk) add4(acc, *reinterpret_cast<const float4 *>(slot + kk * STG_ROW));
+      } else {
+#pragma unroll
+        for (int kk = 0; kk < STG_K; ++kk) {
+          const int e = e0 + kk;
+          add4(acc, *reinterpret_cast<const float4 *>(slot + kk * STG_ROW));   // zero beyond the run / the width
+          if (e + 1 == cur_end) {                // the row's last entry inside this run: flush the lane's sum
+            int accf = 0;
+            float *dst;
+            if (rp(r + 1) > we) { dst = pieces + (wid * 2 + 1) * S; tail_row = r; }       // continues in the next warp
+            else if (rp(r) < wb) { dst = pieces + (wid * 2) * S; head_row = r; }          // began in an earlier warp
+            else dst = out_row(r, accf);
+            if (act) {
+              float4 *d4 = reinterpret_cast<float4 *>(dst + lane * 4);
+              if (accf) add4(acc, *d4);
+              *d4 = acc;
+            }
+            acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            do { ++r; } while (r < rows_here && rp(r + 1) <= e + 1);   // rows without entries are zero-filled below
+            cur_end = r < rows_here ? min(rp(r + 1), we) : 0x7fffffff;
+          }
+        }
+      }
+      sc = sc + STG_K == STG_R ? 0 : sc + STG_K;
+    }
+    cp_async_wait<0>();
+  }
+  if (lane == 0) { s_prow[wid][0] = head_row; s_prow[wid][1] = tail_row; }
+  if (!p.accumulate)
+    for (int r = tid; r < rows_here; r += CTA_THREADS)
+      if (rp(r + 1) == rp(r) && !(r == 0 && head_skip))
+        for (int v = 0; v < (S >> 2); ++v)
+          *reinterpret_cast<float4 *>(p.y + (long long)orig(x0 + r) * p.ldy + v * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  for (int b = 1; b < CTA_WARPS; ++b) {          // rows cut by warp boundaries: pieces added in warp order
+    const int r = s_prow[b][0];
+    if (r < 0) continue;
+    int a = b;
+    while (a > 0 && s_prow[a - 1][1] == r) --a;
+    int accf;
+    float *yrow = out_row(r, accf);
+    for (int v = tid; v < (S >> 2); v += CTA_THREADS) {
+      float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int w = a; w < b; ++w) add4(sum, *reinterpret_cast<const float4 *>(pieces + (w * 2 + 1) * S + v * 4));
+      add4(sum, *reinterpret_cast<const float4 *>(pieces + (b * 2) * S + v * 4));
+      float4 *dst = reinterpret_cast<float4 *>(yrow + v * 4);
+      if (accf) add4(sum, *dst);
+      *dst = sum;
+    }
+  }
+}
+
 // Y[r] (+)= sum of the pieces of every row that was cut by item boundaries, pieces in item order.
 __global__ void __launch_bounds__(64) spmm_balanced_fixup_kernel(const BalParams bp) {
   const SpmmParams &p = bp.s;
@@ -1267,7 +1473,18 @@ static cudaError_t run_balanced(const SpmmParams &p, long long nnz, bool v8, boo
   const int slab = p.slab;
   dim3 grid((unsigned)n_items, (p.dim + slab - 1) / slab, 1);
   const size_t smem = (size_t)2 * CTA_WARPS * slab * sizeof(float) + (size_t)(chunk + 4) / 2 * sizeof(int);
-  if (b16) {
+  // low-degree graphs with rows of 260..512 bytes, every window CUDA-core: rows in flight staged in shared memory
+  const bool staged = tuning().staged != 0 && !b16 && v8 && bp.low_degree && p.ht == nullptr && !bp.seg_mode &&
+                      bp.hint_cls_min < 0 && slab == p.dim && p.dim > 64 && p.dim <= STG_ROW &&
+                      (long long)p.x_rows * p.ldx * 4 < (1LL << 32);
+  if (staged) {
+    const size_t ssm = staged_smem_bytes(chunk);
+    err = cudaFuncSetAttribute(spmm_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm);
+    if (err == cudaSuccess) {
+      spmm_staged_kernel<<<(unsigned)n_items, CTA_THREADS, ssm, stream>>>(bp);
+      err = cudaGetLastError();
+    }
+  } else if (b16) {
     if (slab <= 32) err = launch_balanced_t<4, 1, 8, true>(bp, grid, smem, stream);
     else if (slab <= 64) err = launch_balanced_t<8, 1, 8, true>(bp, grid, smem, stream);
     else if (slab <= 128) err = launch_balanced_t<16, 1, 8, true>(bp, grid, smem, stream);

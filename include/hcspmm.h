@@ -95,6 +95,9 @@ const char *hcspmm_last_error(void);
  *                column ids (default 72 of the 126 MB L2; 0 = hints off)
  *   "l2_hot_min_row" the hints apply to gathers of at least this many bytes per row (default 2048: measured to lose
  *                below -- LRU already keeps the hub rows -- and to gain 7 % at the Reddit shape, dim 512)
+ *   "staged"     1: low-degree graphs (mean row < 64) with rows of 260..512 bytes and no tensor-core window gather
+ *                through shared-memory staging (spmm_staged_kernel: cp.async ring of 20 rows per warp, one lane per
+ *                16 bytes of a row, no register held by a row in flight) instead of the register ring
  *   "dense_tma"  which kernel multiplies dense super-windows.  csrc/dense_tma.cu is the five-role kernel (TMA for
  *                the plan's index chunks and W^T, dedicated epilogue warps, optional FUSED Update); csrc/dense.cu holds
  *                the earlier producer/issuer kernels.  1 (default): dense.cu for plain aggregation (measured fastest,

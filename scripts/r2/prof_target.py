@@ -8,8 +8,10 @@ from hcspmm import capi, graphs
 
 what = sys.argv[1]
 dev = torch.device("cuda", 0)
-if what in ("reddit_spmm", "products_spmm", "products_spmm_degree"):
+if what in ("reddit_spmm", "products_spmm", "products_spmm_degree", "products_spmm_staged"):
     shape = what.split("_")[0]
+    if what.endswith("staged"):          # shared-memory staged gather (knob "staged")
+        capi.set_tuning("staged", 1)
     rp, ci, info = graphs.named(shape, device=dev)
     if what.endswith("degree"):          # descending-degree relabelling (scripts/r2/locality.py)
         deg = (rp[1:] - rp[:-1]).long()
