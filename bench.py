@@ -70,7 +70,7 @@ def parse():
                          "the SpMM instead of being pulled (0 = off, default; -1 = auto)")
     ap.add_argument("--row-blocks", type=int, default=0,
                     help="peer exchange: row-block pipeline -- the halo travels in the order the shard's row blocks need it, "
-                         "block b's SpMM starts when its part has landed (1 = off; 0 = auto, default: 8 blocks on low-degree graphs)")
+                         "block b's SpMM starts when its part has landed (0 / 1 = off, default)")
     ap.add_argument("--exchange-slabs", type=int, default=1,
                     help="N > 1: all-gather X in this many feature slabs, slab k+1 in flight while the SpMM of slab k runs "
                          "(1 = one all-gather, then one SpMM)")

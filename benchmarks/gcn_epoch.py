@@ -45,7 +45,7 @@ def main():
                     help="N > 1, peer exchange: remote rows referenced at most this many times are read in place by the SpMM "
                          "(0 = off, default; -1 = auto)")
     ap.add_argument("--no-row-sort", action="store_true", help="no row-sorted CSR copy (A/B of csrc/rowsort.cu)")
-    ap.add_argument("--row-blocks", type=int, default=0, help="N > 1, peer exchange: row-block pipeline (1 = off, 0 = auto)")
+    ap.add_argument("--row-blocks", type=int, default=0, help="N > 1, peer exchange: row-block pipeline (0 / 1 = off, default)")
     ap.add_argument("--fp32-matmul", action="store_true",
                     help="Update GEMMs (torch.mm) in full FP32; default TF32 like the reference's stack "
                          "(PyTorch 1.8: allow_tf32 on by default; its fused kernels use wmma TF32, :1809-1837)")

@@ -94,8 +94,8 @@ class ShardedGraph:
         row_blocks = B ("peer" schedule): the ROW-BLOCK PIPELINE.  The shard's rows are cut into B blocks of equal stored
         entries and the halo is pulled in the order the blocks need it: block b's SpMM (own stream) starts as soon as
         the rows first referenced by blocks <= b have landed, while the rest still travels on few CTAs -- on low-degree
-        graphs the first of 8 blocks needs only a third of the halo.  None = auto (2 blocks when the first needs <= 0.78
-        of the halo and the operand is FP32, else off), 1 = off."""
+        graphs the first of 8 blocks needs only a third of the halo.  None / 1 = off (default: the measured gain, 5 % with
+        two blocks on the products shape at 8 GPUs, is inside the run-to-run spread)."""
         assert operand in ("fp32", "bf16")
         self.operand = operand
         self.group = group
@@ -159,7 +159,7 @@ class ShardedGraph:
             self._setup_direct(ci64, bounds, direct_refs)
         del ci64
         self.blocks = None
-        if (native and self.peer is not None and not self.push and self.halo is not None and row_blocks != 1
+        if (native and self.peer is not None and not self.push and self.halo is not None and row_blocks not in (None, 1)
                 and n_passes == 1 and self.n_slabs == 1):
             self._setup_row_blocks(row_blocks, preprocess)
         self.passes = None
@@ -242,12 +242,10 @@ class ShardedGraph:
     def _setup_row_blocks(self, row_blocks, preprocess):
         """Row-block pipeline (see __init__, row_blocks): per block its rebased CSR + preprocessing products, and the
         part of the halo it is the first to reference, as a pull list with explicit destination rows."""
-        # auto: two blocks, FP32 operand, and only where the first block leaves a quarter of the halo to hide -- measured
-        # on the products shape at 8 GPUs: 2 blocks 1.21 -> 1.15 ms, 4 blocks 1.17, 8 blocks 1.24 (the blocks' SpMMs fill
-        # the machine worse than one launch); BF16 operand: loses (0.93 -> 0.95 ms)
-        if row_blocks is None and self.operand == "bf16":
-            return
-        B = 2 if row_blocks is None else int(row_blocks)
+        # measured on the products shape at 8 GPUs: 2 blocks 1.18 -> 1.125 ms in the sweep and 1.194 ms in the bench line,
+        # 4 blocks 1.17, 8 blocks 1.24 (the blocks' SpMMs fill the machine worse than one launch); BF16 operand: loses
+        # (0.90 -> 0.98 ms).  A gain inside the run-to-run spread is not a default: opt-in.
+        B = int(row_blocks)
         hdr = self.pre[4] if len(self.pre) >= 6 and self.pre[4].device.type == "cpu" else None
         all_cuda = hdr is not None and int(hdr[1]) == 0 and int(hdr[7]) == 0        # no dense plan, no label-1 windows
         if B < 2 or not all_cuda or self.n_local < 16 * B or self.nnz_local < 64 * B:
@@ -259,8 +257,6 @@ class ShardedGraph:
         first[own0: own0 + self.n_local] = B + 1                                  # own rows are in place already
         n_halo = h["rows"] - self.n_local
         f1 = float((first == 0).sum()) / max(1, n_halo)
-        if row_blocks is None and f1 > 0.78:
-            return
         dev = col.device
         rp64 = self.rowptr.to(torch.int64)
         seg64 = h["seg"].to(torch.int64)
