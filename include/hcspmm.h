@@ -228,6 +228,10 @@ int hcspmm_spmm_plan(const float *d_x, int64_t ldx, int32_t x_rows, const int32_
  *                                        bounds the row index of every segment.  CUDA-core balanced kernel only:
  *                                        needs n_tc_windows = 0, no dense plan, 32-byte aligned rows, dim <= 256
  *                                        (wider operands: column blocks); d_colidx itself is ignored.  NULL = off
+ *   d_sorted_rowptr / _colidx / _row_id  the row-sorted copy of the CSR (hcspmm_row_sort, below): the balanced kernel
+ *                                        walks it instead of (d_rowptr, d_colidx) and writes sorted row i to
+ *                                        Y[d_sorted_row_id[i]]; d_splits must be the split points of d_sorted_rowptr.
+ *                                        Ignored in segment mode (split points are then recomputed).  NULL = off
  *   d_workspace / workspace_bytes        >= hcspmm_spmm_workspace_bytes() bytes, 16-byte aligned, for the row
  *                                        pieces of the balanced kernel; NULL = the library's private pool
  * hcspmm_spmm_aux(..., NULL, ...) is hcspmm_spmm.                                                              */
